@@ -104,20 +104,27 @@ def _iota(n):
 
 
 def nx_linspace(start, stop, n, endpoint=True):
-    """Nx.linspace for f32: iota * step + start, step computed in double.
+    """Nx.linspace for f32 as tensor ops: start/stop become f32 tensors,
+    step = f32(f32(stop - start) / divisor), out = f32(f32(iota * step) + start).
 
-    Pinned by the mel_filters doctest row (lib/nx_signal.ex:392) and the
-    fft_frequencies doctest (lib/nx_signal.ex:147-151).
+    Pinned by the stft doctest times (lib/nx_signal.ex:56-60), the
+    fft_frequencies doctest (:147-151) and the mel doctests (:384-394, :465-483).
     """
-    start = float(start)
-    stop = float(stop)
+    start = _tensor_scalar(start)
+    stop = _tensor_scalar(stop)
     div = (n - 1) if endpoint else n
-    if div == 0:
-        step = 0.0
-    else:
-        step = (stop - start) / div
-    # step and start are scalars promoted to f32 tensors by the binary op
-    return _add(_mul(_iota(n), _lit(step)), _lit(start))
+    diff = _sub(stop, start)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        step = _div(diff, div)
+        return _add(_mul(_iota(n), step), start)
+
+
+def _tensor_scalar(x):
+    """A number crossing into a defn as an argument: ints stay exact (s32),
+    floats become f32."""
+    if isinstance(x, (int, np.integer)):
+        return F64(x)
+    return F64(F32(x))
 
 
 # ---------------------------------------------------------------------------
@@ -364,10 +371,21 @@ def as_windowed(x, window_length: int, stride: int = 1, padding: PaddingT = "val
     return xp[..., idx]
 
 
-def fft_frequencies(sampling_rate: float, fft_length: int):
-    """lib/nx_signal.ex:154-166: linspace(0, step*fft_length, n, endpoint: false)."""
-    step = sampling_rate / fft_length
-    return nx_linspace(0, step * fft_length, fft_length, endpoint=False)
+def fft_frequencies(sampling_rate, fft_length: int):
+    """lib/nx_signal.ex:154-166: step = sr / nfft; linspace(0, step * nfft, n: nfft,
+    endpoint: false), every op an f32 tensor op."""
+    sr = _tensor_scalar(sampling_rate)
+    step = _div(sr, fft_length)
+    return nx_linspace(0, _mul(step, fft_length), fft_length, endpoint=False)
+
+
+def stft_times(frame_length: int, sampling_rate, num_frames: int):
+    """lib/nx_signal.ex:108-111: time_step = N / (2 sr); linspace(time_step,
+    time_step * M, n: M); sampling_rate is a defn argument (tensor)."""
+    sr = _tensor_scalar(sampling_rate)
+    time_step = _div(frame_length, _mul(2, sr))
+    last_frame = _mul(time_step, num_frames)
+    return nx_linspace(time_step, last_frame, num_frames)
 
 
 # ---------------------------------------------------------------------------
@@ -418,16 +436,14 @@ def stft(
     spectrum = (fft or nx_fft)(windowed, nfft)
     M = spectrum.shape[-2]
     freqs = fft_frequencies(sampling_rate, nfft)
-    time_step = N / (2 * sampling_rate)
-    last_frame = time_step * M
-    times = nx_linspace(time_step, last_frame, M)
+    times = stft_times(N, sampling_rate, M)
     wf = _to_f32_or_c64(window)
     if scaling == "spectrum":
         s = _f(np.sum(_d(wf)))
         out = _c(_d(spectrum.real) / _d(s) + 1j * (_d(spectrum.imag) / _d(s)))
     elif scaling == "psd":
         s2 = _f(np.sum(_d(_f(_d(wf) ** 2))))
-        den = _f(np.sqrt(_d(_mul(_lit(sampling_rate), s2))))
+        den = _f(np.sqrt(_d(_mul(_tensor_scalar(sampling_rate), s2))))
         out = _c(_d(spectrum.real) / _d(den) + 1j * (_d(spectrum.imag) / _d(den)))
     else:
         out = spectrum
@@ -484,7 +500,7 @@ def istft(
         frames = _c(_d(frames.real) * s + 1j * (_d(frames.imag) * s))
     elif scaling == "psd":
         s2 = _f(np.sum(_d(_f(_d(window) ** 2))))
-        s = _d(_f(np.sqrt(_d(_mul(_lit(sampling_rate), s2)))))
+        s = _d(_f(np.sqrt(_d(_mul(_tensor_scalar(sampling_rate), s2)))))
         frames = _c(_d(frames.real) * s + 1j * (_d(frames.imag) * s))
     if frames.shape[-1] != window.shape[0]:
         raise ValueError(
