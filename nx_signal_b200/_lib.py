@@ -1,0 +1,125 @@
+"""ctypes binding of libnxsignal_b200.so (C ABI in include/nxsignal_b200.h).
+
+There is no CPU implementation behind this module: if the shared library is missing the
+import of any compute entry fails loudly, and if there is no CUDA device
+``nxs_ctx_create`` returns NXS_ENODEVICE which is raised as RuntimeError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libnxsignal_b200.so")
+
+NXS_OK = 0
+NXS_EINVAL, NXS_ESHAPE, NXS_EUNSUPPORTED, NXS_ECUDA, NXS_ENCCL, NXS_ENOMEM, NXS_ENODEVICE = (
+    -1, -2, -3, -4, -5, -6, -7)
+
+PAD_VALID, PAD_SAME, PAD_REFLECT, PAD_EXPLICIT = 0, 1, 2, 3
+SCALE_NONE, SCALE_SPECTRUM, SCALE_PSD = 0, 1, 2
+WIN = {"rectangular": 0, "bartlett": 1, "triangular": 2, "blackman": 3, "hamming": 4, "hann": 5, "kaiser": 6}
+MODE = {"full": 0, "same": 1, "valid": 2}
+
+i64, f64, i32 = C.c_int64, C.c_double, C.c_int
+vp = C.c_void_p
+
+# name -> (restype, argtypes); every symbol include/nxsignal_b200.h declares
+SIGNATURES = {
+    "nxs_abi_version": (i32, []),
+    "nxs_strerror": (C.c_char_p, [i32]),
+    "nxs_device_count": (i32, []),
+    "nxs_ctx_create": (i32, [i32, C.POINTER(vp)]),
+    "nxs_ctx_destroy": (i32, [vp]),
+    "nxs_last_error": (C.c_char_p, [vp]),
+    "nxs_ctx_synchronize": (i32, [vp]),
+    "nxs_ctx_launch_count": (C.c_uint64, [vp]),
+    "nxs_window_f32": (i32, [i32, i64, i32, f64, f64, vp]),
+    "nxs_firwin_f32": (i32, [i64, C.POINTER(f64), i32, i32, f64, i32, i32, f64, vp]),
+    "nxs_fft_frequencies_f32": (i32, [f64, i64, vp]),
+    "nxs_stft_times_f32": (i32, [i64, f64, i64, vp]),
+    "nxs_num_frames": (i32, [i64, i64, i64, i32, i64, i64, C.POINTER(i64)]),
+    "nxs_stft_f32_dev": (i32, [vp, vp, i64, i64, i64, vp, i64, i64, i64, i32, i64, i64, i32, f64, vp, vp]),
+    "nxs_stft_f32_host": (i32, [vp, vp, i64, i64, i64, vp, i64, i64, i64, i32, i64, i64, i32, f64, vp]),
+    "nxs_istft_c64_dev": (i32, [vp, vp, i64, i64, i64, vp, i64, i64, i64, i32, f64, vp, vp]),
+    "nxs_istft_c64_host": (i32, [vp, vp, i64, i64, i64, vp, i64, i64, i64, i32, f64, vp]),
+    "nxs_as_windowed_dev": (i32, [vp, vp, i32, i64, i64, i64, i64, i64, i32, i64, i64, vp, vp]),
+    "nxs_as_windowed_host": (i32, [vp, vp, i32, i64, i64, i64, i64, i64, i32, i64, i64, vp]),
+    "nxs_overlap_and_add_f32_dev": (i32, [vp, vp, i64, i64, i64, i64, vp, vp]),
+    "nxs_overlap_and_add_c64_dev": (i32, [vp, vp, i64, i64, i64, i64, vp, vp]),
+    "nxs_overlap_and_add_f32_host": (i32, [vp, vp, i64, i64, i64, i64, vp]),
+    "nxs_overlap_and_add_c64_host": (i32, [vp, vp, i64, i64, i64, i64, vp]),
+    "nxs_fir_out_len": (i32, [i64, i64, i32, C.POINTER(i64)]),
+    "nxs_fir_f32_dev": (i32, [vp, vp, i64, i64, i64, vp, i64, i32, vp, i64, vp]),
+    "nxs_fir_f32_host": (i32, [vp, vp, i64, i64, i64, vp, i64, i32, vp, i64]),
+    "nxs_convolve_nd_dev": (i32, [vp, vp, C.POINTER(i64), vp, C.POINTER(i64), i32, i32, vp, vp]),
+    "nxs_convolve_nd_host": (i32, [vp, vp, C.POINTER(i64), vp, C.POINTER(i64), i32, i32, vp]),
+    "nxs_bcast_coeffs_dev": (i32, [vp, vp, vp, i64, i32, vp]),
+}
+
+_lib = None
+_lock = threading.Lock()
+_ctxs = {}
+
+
+class NxSignalArgumentError(ValueError):
+    """The reference's only error convention is ``ArgumentError``; this is its Python face."""
+
+
+def lib():
+    """Loads the shared library (built by ``__graft_entry__.build()`` / ``make -C nx_signal_b200/csrc``)."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(nx_signal_b200 has no CPU fallback)")
+                l = C.CDLL(LIB_PATH)
+                for name, (res, args) in SIGNATURES.items():
+                    fn = getattr(l, name)
+                    fn.restype = res
+                    fn.argtypes = args
+                _lib = l
+    return _lib
+
+
+def strerror(code):
+    return lib().nxs_strerror(code).decode()
+
+
+def check(code, ctx=None, what=""):
+    if code == NXS_OK:
+        return
+    msg = strerror(code)
+    if ctx is not None and code in (NXS_ECUDA, NXS_ENCCL, NXS_ENOMEM):
+        detail = lib().nxs_last_error(ctx).decode()
+        if detail:
+            msg += f" ({detail})"
+    if what:
+        msg = f"{what}: {msg}"
+    if code in (NXS_EINVAL, NXS_ESHAPE):
+        raise NxSignalArgumentError(msg)
+    raise RuntimeError(msg)
+
+
+def context(device=0):
+    """One context per (thread, device); created lazily, needs a CUDA device."""
+    key = (threading.get_ident(), int(device))
+    ctx = _ctxs.get(key)
+    if ctx is None:
+        h = vp()
+        check(lib().nxs_ctx_create(int(device), C.byref(h)), what="nxs_ctx_create")
+        ctx = h
+        _ctxs[key] = ctx
+    return ctx
+
+
+def launch_count(device=0):
+    return int(lib().nxs_ctx_launch_count(context(device)))
+
+
+def synchronize(device=0):
+    check(lib().nxs_ctx_synchronize(context(device)), context(device))

@@ -1,0 +1,486 @@
+// nxs_abi.cu -- context object and the extern "C" entry points declared in
+// include/nxsignal_b200.h.  Argument checking mirrors the reference's ArgumentError
+// conditions (cited per entry); no entry point ever falls back to the CPU.
+#include <dlfcn.h>
+#include <string.h>
+
+#include "nxs_common.cuh"
+
+namespace nxs {
+
+int set_cuda_error(nxs_ctx* ctx, cudaError_t e, const char* where) {
+  if (ctx) {
+    ctx->last_error = std::string(cudaGetErrorName(e)) + ": " + cudaGetErrorString(e) + " at " + where;
+  }
+  cudaGetLastError();  // clear sticky-less errors
+  return e == cudaErrorMemoryAllocation ? NXS_ENOMEM : NXS_ECUDA;
+}
+
+static int grow(nxs_ctx* ctx, void** p, size_t* have, size_t need, bool host) {
+  if (*have >= need) return NXS_OK;
+  if (*p) {
+    if (host) cudaFreeHost(*p);
+    else cudaFree(*p);
+    *p = nullptr;
+    *have = 0;
+  }
+  size_t sz = need + need / 8;
+  cudaError_t e = host ? cudaMallocHost(p, sz) : cudaMalloc(p, sz);
+  if (e != cudaSuccess) {
+    sz = need;
+    e = host ? cudaMallocHost(p, sz) : cudaMalloc(p, sz);
+  }
+  if (e != cudaSuccess) return set_cuda_error(ctx, e, host ? "cudaMallocHost" : "cudaMalloc");
+  *have = sz;
+  return NXS_OK;
+}
+
+int ensure_coef(nxs_ctx* ctx, size_t bytes) {
+  void* p = ctx->d_coef;
+  int rc = grow(ctx, &p, &ctx->d_coef_bytes, bytes < 4096 ? 4096 : bytes, false);
+  ctx->d_coef = (float*)p;
+  return rc;
+}
+
+int ensure_scratch(nxs_ctx* ctx, size_t bytes) {
+  return grow(ctx, &ctx->d_scratch, &ctx->d_scratch_bytes, bytes, false);
+}
+
+int resolve_padding(int64_t length, int64_t window_length, int pad_mode, int64_t pad_lo, int64_t pad_hi,
+                    PadGeom* g) {
+  (void)length;
+  g->reflect = 0;
+  switch (pad_mode) {
+    case NXS_PAD_VALID: g->lo = g->hi = 0; return NXS_OK;
+    case NXS_PAD_SAME: {  // lib/nx_signal.ex:308-312
+      int64_t total = window_length - 1;
+      if (total < 0) total = 0;
+      g->lo = total / 2;
+      g->hi = total - g->lo;
+      return NXS_OK;
+    }
+    case NXS_PAD_REFLECT:  // lib/nx_signal.ex:257-264, 343-349
+      g->lo = g->hi = window_length / 2;
+      g->reflect = 1;
+      return NXS_OK;
+    case NXS_PAD_EXPLICIT: g->lo = pad_lo; g->hi = pad_hi; return NXS_OK;
+    default: return NXS_EINVAL;  // lib/nx_signal.ex:325-329
+  }
+}
+
+int64_t frames_for(int64_t length, int64_t window_length, int64_t stride, const PadGeom& g) {
+  const int64_t padded = length + g.lo + g.hi;
+  return padded < window_length ? 0 : (padded - window_length) / stride + 1;
+}
+
+static cudaStream_t pick(nxs_ctx* ctx, void* stream) { return stream ? (cudaStream_t)stream : ctx->stream; }
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// host-pointer helper: stage in -> run -> stage out, on the context's stream
+template <class F>
+static int host_roundtrip(nxs_ctx* ctx, const void* in, size_t in_bytes, const void* in2, size_t in2_bytes,
+                          void* out, size_t out_bytes, F&& run) {
+  int rc = grow(ctx, &ctx->d_stage_in, &ctx->d_stage_in_bytes, in_bytes + in2_bytes + 512, false);
+  if (rc) return rc;
+  rc = grow(ctx, &ctx->d_stage_out, &ctx->d_stage_out_bytes, out_bytes + 256, false);
+  if (rc) return rc;
+  char* d_in = (char*)ctx->d_stage_in;
+  const size_t off2 = (in_bytes + 255) / 256 * 256;
+  char* d_in2 = d_in + off2;
+  if (in_bytes) NXS_CUDA(ctx, cudaMemcpyAsync(d_in, in, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  if (in2_bytes) NXS_CUDA(ctx, cudaMemcpyAsync(d_in2, in2, in2_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  rc = run(d_in, d_in2, ctx->d_stage_out);
+  if (rc) return rc;
+  if (out_bytes) NXS_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_stage_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  NXS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return NXS_OK;
+}
+
+}  // namespace nxs
+
+using namespace nxs;
+
+extern "C" {
+
+int nxs_abi_version(void) { return NXS_ABI_VERSION; }
+
+const char* nxs_strerror(int code) {
+  switch (code) {
+    case NXS_OK: return "ok";
+    case NXS_EINVAL: return "invalid argument";
+    case NXS_ESHAPE: return "incompatible shapes";
+    case NXS_EUNSUPPORTED: return "unsupported configuration";
+    case NXS_ECUDA: return "CUDA error";
+    case NXS_ENCCL: return "NCCL error";
+    case NXS_ENOMEM: return "out of memory";
+    case NXS_ENODEVICE: return "no CUDA device (this backend has no CPU path)";
+    default: return "unknown error";
+  }
+}
+
+int nxs_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int nxs_ctx_create(int device, nxs_ctx** out) {
+  if (!out) return NXS_EINVAL;
+  *out = nullptr;
+  const int n = nxs_device_count();
+  if (n <= 0) return NXS_ENODEVICE;
+  if (device < 0 || device >= n) return NXS_EINVAL;
+  nxs_ctx* ctx = new nxs_ctx();
+  ctx->device = device;
+  DeviceGuard guard(device);
+  cudaDeviceProp prop;
+  if (!guard.ok || cudaGetDeviceProperties(&prop, device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    cudaGetLastError();
+    return NXS_ECUDA;
+  }
+  for (auto& e : ctx->ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+  ctx->sm_count = prop.multiProcessorCount;
+  *out = ctx;
+  return NXS_OK;
+}
+
+int nxs_ctx_destroy(nxs_ctx* ctx) {
+  if (!ctx) return NXS_OK;
+  DeviceGuard guard(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& kv : ctx->tables) {
+    cudaFree(kv.second.tw);
+    cudaFree(kv.second.post);
+  }
+  for (auto& kv : ctx->dft_tables) cudaFree(kv.second);
+  cudaFree(ctx->d_coef);
+  cudaFree(ctx->d_scratch);
+  cudaFree(ctx->d_stage_in);
+  cudaFree(ctx->d_stage_out);
+  if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+  cudaStreamDestroy(ctx->stream);
+  cudaStreamDestroy(ctx->copy_stream);
+  delete ctx;
+  return NXS_OK;
+}
+
+const char* nxs_last_error(const nxs_ctx* ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+
+int nxs_ctx_synchronize(nxs_ctx* ctx) {
+  if (!ctx) return NXS_EINVAL;
+  DeviceGuard guard(ctx->device);
+  NXS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return NXS_OK;
+}
+
+uint64_t nxs_ctx_launch_count(const nxs_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- STFT -----------------------------------------------------------------------------------
+static int stft_check(int64_t channels, int64_t length, int64_t x_ld, int64_t frame_length, int64_t hop,
+                      int64_t fft_length, int pad_mode, int64_t pad_lo, int64_t pad_hi, int scaling,
+                      double sampling_rate, PadGeom* g, int64_t* M) {
+  if (channels < 0 || length < 1 || x_ld < length || frame_length < 1 || fft_length < 1) return NXS_ESHAPE;
+  if (hop < 1) return NXS_EINVAL;  // stride must be an integer >= 1 (lib/nx_signal.ex:279-284)
+  if (scaling != NXS_SCALE_NONE && scaling != NXS_SCALE_SPECTRUM && scaling != NXS_SCALE_PSD)
+    return NXS_EINVAL;  // lib/nx_signal.ex:124-126
+  if (!(sampling_rate == sampling_rate)) return NXS_EINVAL;
+  int rc = resolve_padding(length, frame_length, pad_mode, pad_lo, pad_hi, g);
+  if (rc) return rc;
+  *M = frames_for(length, frame_length, hop, *g);
+  return NXS_OK;
+}
+
+int nxs_stft_f32_dev(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, int64_t x_ld,
+                     const float* window, int64_t frame_length, int64_t hop, int64_t fft_length,
+                     int pad_mode, int64_t pad_lo, int64_t pad_hi, int scaling, double sampling_rate,
+                     float* z, void* stream) {
+  if (!ctx || !x || !window || !z) return NXS_EINVAL;
+  PadGeom g;
+  int64_t M = 0;
+  int rc = stft_check(channels, length, x_ld, frame_length, hop, fft_length, pad_mode, pad_lo, pad_hi,
+                      scaling, sampling_rate, &g, &M);
+  if (rc) return rc;
+  DeviceGuard guard(ctx->device);
+  return launch_stft(ctx, x, channels, length, x_ld, window, frame_length, hop, fft_length, g, M, scaling,
+                     sampling_rate, reinterpret_cast<float2*>(z), pick(ctx, stream));
+}
+
+int nxs_stft_f32_host(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, int64_t x_ld,
+                      const float* window, int64_t frame_length, int64_t hop, int64_t fft_length,
+                      int pad_mode, int64_t pad_lo, int64_t pad_hi, int scaling, double sampling_rate,
+                      float* z) {
+  if (!ctx || !x || !window || !z) return NXS_EINVAL;
+  PadGeom g;
+  int64_t M = 0;
+  int rc = stft_check(channels, length, x_ld, frame_length, hop, fft_length, pad_mode, pad_lo, pad_hi,
+                      scaling, sampling_rate, &g, &M);
+  if (rc) return rc;
+  DeviceGuard guard(ctx->device);
+  const size_t in_bytes = size_t(channels > 0 ? (channels - 1) * x_ld + length : 0) * sizeof(float);
+  const size_t out_bytes = size_t(channels) * size_t(M) * size_t(fft_length) * sizeof(float2);
+  return host_roundtrip(ctx, x, in_bytes, window, size_t(frame_length) * sizeof(float), z, out_bytes,
+                        [&](void* dx, void* dw, void* dz) {
+                          return launch_stft(ctx, (const float*)dx, channels, length, x_ld, (const float*)dw,
+                                             frame_length, hop, fft_length, g, M, scaling, sampling_rate,
+                                             (float2*)dz, ctx->stream);
+                        });
+}
+
+// ---- ISTFT ----------------------------------------------------------------------------------
+static int istft_check(int64_t channels, int64_t num_frames, int64_t z_len, int64_t frame_length, int64_t hop,
+                       int64_t fft_length, int scaling) {
+  if (channels < 0 || num_frames < 1 || z_len < 1 || frame_length < 1 || fft_length < 1) return NXS_ESHAPE;
+  if (fft_length != frame_length) return NXS_ESHAPE;  // `frames * window` must broadcast (lib/nx_signal.ex:628)
+  if (hop < 1 || hop > frame_length) return NXS_EINVAL;  // overlap_length >= 0 and < window (lib/nx_signal.ex:692-695)
+  if (scaling != NXS_SCALE_NONE && scaling != NXS_SCALE_SPECTRUM && scaling != NXS_SCALE_PSD)
+    return NXS_EINVAL;  // lib/nx_signal.ex:622-624
+  return NXS_OK;
+}
+
+int nxs_istft_c64_dev(nxs_ctx* ctx, const float* z, int64_t channels, int64_t num_frames, int64_t z_len,
+                      const float* window, int64_t frame_length, int64_t hop, int64_t fft_length,
+                      int scaling, double sampling_rate, float* y, void* stream) {
+  if (!ctx || !z || !window || !y) return NXS_EINVAL;
+  int rc = istft_check(channels, num_frames, z_len, frame_length, hop, fft_length, scaling);
+  if (rc) return rc;
+  DeviceGuard guard(ctx->device);
+  return launch_istft(ctx, reinterpret_cast<const float2*>(z), channels, num_frames, z_len, window,
+                      frame_length, hop, fft_length, scaling, sampling_rate, reinterpret_cast<float2*>(y),
+                      pick(ctx, stream));
+}
+
+int nxs_istft_c64_host(nxs_ctx* ctx, const float* z, int64_t channels, int64_t num_frames, int64_t z_len,
+                       const float* window, int64_t frame_length, int64_t hop, int64_t fft_length,
+                       int scaling, double sampling_rate, float* y) {
+  if (!ctx || !z || !window || !y) return NXS_EINVAL;
+  int rc = istft_check(channels, num_frames, z_len, frame_length, hop, fft_length, scaling);
+  if (rc) return rc;
+  DeviceGuard guard(ctx->device);
+  const size_t in_bytes = size_t(channels) * num_frames * z_len * sizeof(float2);
+  const size_t out_len = size_t(num_frames) * hop + (frame_length - hop);
+  return host_roundtrip(ctx, z, in_bytes, window, size_t(frame_length) * sizeof(float), y,
+                        size_t(channels) * out_len * sizeof(float2), [&](void* dz, void* dw, void* dy) {
+                          return launch_istft(ctx, (const float2*)dz, channels, num_frames, z_len,
+                                              (const float*)dw, frame_length, hop, fft_length, scaling,
+                                              sampling_rate, (float2*)dy, ctx->stream);
+                        });
+}
+
+// ---- as_windowed ------------------------------------------------------------------------------
+static int aw_check(int elem_size, int64_t channels, int64_t length, int64_t x_ld, int64_t window_length,
+                    int64_t stride, int pad_mode, int64_t pad_lo, int64_t pad_hi, PadGeom* g, int64_t* M) {
+  if (elem_size != 4 && elem_size != 8) return NXS_EUNSUPPORTED;
+  if (channels < 0 || length < 1 || x_ld < length || window_length < 1) return NXS_ESHAPE;
+  if (stride < 1) return NXS_EINVAL;  // lib/nx_signal.ex:282-284
+  int rc = resolve_padding(length, window_length, pad_mode, pad_lo, pad_hi, g);
+  if (rc) return rc;
+  *M = frames_for(length, window_length, stride, *g);
+  return NXS_OK;
+}
+
+int nxs_as_windowed_dev(nxs_ctx* ctx, const void* x, int elem_size, int64_t channels, int64_t length,
+                        int64_t x_ld, int64_t window_length, int64_t stride, int pad_mode, int64_t pad_lo,
+                        int64_t pad_hi, void* out, void* stream) {
+  if (!ctx || !x || !out) return NXS_EINVAL;
+  PadGeom g;
+  int64_t M = 0;
+  int rc = aw_check(elem_size, channels, length, x_ld, window_length, stride, pad_mode, pad_lo, pad_hi, &g, &M);
+  if (rc) return rc;
+  DeviceGuard guard(ctx->device);
+  return launch_as_windowed(ctx, x, elem_size, channels, length, x_ld, window_length, stride, g, M, out,
+                            pick(ctx, stream));
+}
+
+int nxs_as_windowed_host(nxs_ctx* ctx, const void* x, int elem_size, int64_t channels, int64_t length,
+                         int64_t x_ld, int64_t window_length, int64_t stride, int pad_mode, int64_t pad_lo,
+                         int64_t pad_hi, void* out) {
+  if (!ctx || !x || !out) return NXS_EINVAL;
+  PadGeom g;
+  int64_t M = 0;
+  int rc = aw_check(elem_size, channels, length, x_ld, window_length, stride, pad_mode, pad_lo, pad_hi, &g, &M);
+  if (rc) return rc;
+  DeviceGuard guard(ctx->device);
+  const size_t in_bytes = size_t(channels > 0 ? (channels - 1) * x_ld + length : 0) * elem_size;
+  const size_t out_bytes = size_t(channels) * M * window_length * elem_size;
+  return host_roundtrip(ctx, x, in_bytes, nullptr, 0, out, out_bytes, [&](void* dx, void*, void* dout) {
+    return launch_as_windowed(ctx, dx, elem_size, channels, length, x_ld, window_length, stride, g, M, dout,
+                              ctx->stream);
+  });
+}
+
+// ---- overlap_and_add --------------------------------------------------------------------------
+static int ola_check(int64_t batch, int64_t num_frames, int64_t frame_length, int64_t overlap) {
+  if (batch < 0 || num_frames < 1 || frame_length < 1) return NXS_ESHAPE;
+  if (overlap >= frame_length || overlap < 0) return NXS_EINVAL;  // lib/nx_signal.ex:692-695
+  return NXS_OK;
+}
+
+static int ola_dev(nxs_ctx* ctx, const float* t, int cplx, int64_t batch, int64_t num_frames,
+                   int64_t frame_length, int64_t overlap, float* out, void* stream) {
+  if (!ctx || !t || !out) return NXS_EINVAL;
+  int rc = ola_check(batch, num_frames, frame_length, overlap);
+  if (rc) return rc;
+  DeviceGuard guard(ctx->device);
+  return launch_overlap_and_add(ctx, t, cplx, batch, num_frames, frame_length, overlap, out, pick(ctx, stream));
+}
+
+static int ola_host(nxs_ctx* ctx, const float* t, int cplx, int64_t batch, int64_t num_frames,
+                    int64_t frame_length, int64_t overlap, float* out) {
+  if (!ctx || !t || !out) return NXS_EINVAL;
+  int rc = ola_check(batch, num_frames, frame_length, overlap);
+  if (rc) return rc;
+  DeviceGuard guard(ctx->device);
+  const size_t es = cplx ? 8 : 4;
+  const size_t out_len = size_t(num_frames) * (frame_length - overlap) + overlap;
+  return host_roundtrip(ctx, t, size_t(batch) * num_frames * frame_length * es, nullptr, 0, out,
+                        size_t(batch) * out_len * es, [&](void* dt, void*, void* dout) {
+                          return launch_overlap_and_add(ctx, (const float*)dt, cplx, batch, num_frames,
+                                                        frame_length, overlap, (float*)dout, ctx->stream);
+                        });
+}
+
+int nxs_overlap_and_add_f32_dev(nxs_ctx* ctx, const float* t, int64_t batch, int64_t num_frames,
+                                int64_t frame_length, int64_t overlap_length, float* out, void* stream) {
+  return ola_dev(ctx, t, 0, batch, num_frames, frame_length, overlap_length, out, stream);
+}
+int nxs_overlap_and_add_c64_dev(nxs_ctx* ctx, const float* t, int64_t batch, int64_t num_frames,
+                                int64_t frame_length, int64_t overlap_length, float* out, void* stream) {
+  return ola_dev(ctx, t, 1, batch, num_frames, frame_length, overlap_length, out, stream);
+}
+int nxs_overlap_and_add_f32_host(nxs_ctx* ctx, const float* t, int64_t batch, int64_t num_frames,
+                                 int64_t frame_length, int64_t overlap_length, float* out) {
+  return ola_host(ctx, t, 0, batch, num_frames, frame_length, overlap_length, out);
+}
+int nxs_overlap_and_add_c64_host(nxs_ctx* ctx, const float* t, int64_t batch, int64_t num_frames,
+                                 int64_t frame_length, int64_t overlap_length, float* out) {
+  return ola_host(ctx, t, 1, batch, num_frames, frame_length, overlap_length, out);
+}
+
+// ---- FIR --------------------------------------------------------------------------------------
+static int fir_check(int64_t channels, int64_t length, int64_t x_ld, int64_t num_taps, int mode,
+                     int64_t y_ld, int64_t* out_len) {
+  if (channels < 0 || length < 1 || x_ld < length || num_taps < 1) return NXS_ESHAPE;
+  int rc = nxs_fir_out_len(length, num_taps, mode, out_len);  // convolution.ex:41-44
+  if (rc) return rc;
+  if (y_ld < *out_len) return NXS_ESHAPE;
+  return NXS_OK;
+}
+
+int nxs_fir_f32_dev(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, int64_t x_ld,
+                    const float* taps, int64_t num_taps, int mode, float* y, int64_t y_ld, void* stream) {
+  if (!ctx || !x || !taps || !y) return NXS_EINVAL;
+  int64_t out_len = 0;
+  int rc = fir_check(channels, length, x_ld, num_taps, mode, y_ld, &out_len);
+  if (rc) return rc;
+  DeviceGuard guard(ctx->device);
+  return launch_fir(ctx, x, channels, length, x_ld, taps, num_taps, mode, y, y_ld, pick(ctx, stream));
+}
+
+int nxs_fir_f32_host(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, int64_t x_ld,
+                     const float* taps, int64_t num_taps, int mode, float* y, int64_t y_ld) {
+  if (!ctx || !x || !taps || !y) return NXS_EINVAL;
+  int64_t out_len = 0;
+  int rc = fir_check(channels, length, x_ld, num_taps, mode, y_ld, &out_len);
+  if (rc) return rc;
+  DeviceGuard guard(ctx->device);
+  const size_t in_bytes = size_t(channels > 0 ? (channels - 1) * x_ld + length : 0) * sizeof(float);
+  const size_t out_bytes = size_t(channels > 0 ? (channels - 1) * y_ld + out_len : 0) * sizeof(float);
+  return host_roundtrip(ctx, x, in_bytes, taps, size_t(num_taps) * sizeof(float), y, out_bytes,
+                        [&](void* dx, void* dt, void* dy) {
+                          return launch_fir(ctx, (const float*)dx, channels, length, x_ld, (const float*)dt,
+                                            num_taps, mode, (float*)dy, y_ld, ctx->stream);
+                        });
+}
+
+// ---- N-d convolution ----------------------------------------------------------------------------
+static int conv_check(const int64_t* as, const int64_t* bs, int mode, int64_t* os) {
+  if (mode != NXS_MODE_FULL && mode != NXS_MODE_SAME && mode != NXS_MODE_VALID) return NXS_EINVAL;
+  bool ok1 = true, ok2 = true;
+  for (int d = 0; d < 3; ++d) {
+    if (as[d] < 1 || bs[d] < 1) return NXS_ESHAPE;
+    ok1 = ok1 && as[d] >= bs[d];
+    ok2 = ok2 && as[d] <= bs[d];
+  }
+  for (int d = 0; d < 3; ++d) {
+    if (mode == NXS_MODE_FULL) os[d] = as[d] + bs[d] - 1;
+    else if (mode == NXS_MODE_SAME) os[d] = as[d];
+    else {
+      if (!ok1 && !ok2) return NXS_ESHAPE;  // convolution.ex:131-134, 342-345
+      os[d] = (ok1 ? as[d] - bs[d] : bs[d] - as[d]) + 1;
+    }
+  }
+  return NXS_OK;
+}
+
+int nxs_convolve_nd_dev(nxs_ctx* ctx, const float* a, const int64_t a_shape[3], const float* b,
+                        const int64_t b_shape[3], int is_complex, int mode, float* out, void* stream) {
+  if (!ctx || !a || !b || !out || !a_shape || !b_shape) return NXS_EINVAL;
+  int64_t os[3];
+  int rc = conv_check(a_shape, b_shape, mode, os);
+  if (rc) return rc;
+  DeviceGuard guard(ctx->device);
+  return launch_convolve_nd(ctx, a, a_shape, b, b_shape, is_complex, mode, out, pick(ctx, stream));
+}
+
+int nxs_convolve_nd_host(nxs_ctx* ctx, const float* a, const int64_t a_shape[3], const float* b,
+                         const int64_t b_shape[3], int is_complex, int mode, float* out) {
+  if (!ctx || !a || !b || !out || !a_shape || !b_shape) return NXS_EINVAL;
+  int64_t os[3];
+  int rc = conv_check(a_shape, b_shape, mode, os);
+  if (rc) return rc;
+  DeviceGuard guard(ctx->device);
+  const size_t es = is_complex ? 8 : 4;
+  const size_t na = size_t(a_shape[0]) * a_shape[1] * a_shape[2], nb = size_t(b_shape[0]) * b_shape[1] * b_shape[2];
+  const size_t no = size_t(os[0]) * os[1] * os[2];
+  return host_roundtrip(ctx, a, na * es, b, nb * es, out, no * es, [&](void* da, void* db, void* dout) {
+    return launch_convolve_nd(ctx, (const float*)da, a_shape, (const float*)db, b_shape, is_complex, mode,
+                              (float*)dout, ctx->stream);
+  });
+}
+
+// ---- coefficient broadcast (the path's only collective) -------------------------------------------
+int nxs_bcast_coeffs_dev(nxs_ctx* ctx, void* comm, float* buf, int64_t count, int root, void* stream) {
+  if (!ctx || !comm || !buf || count < 0) return NXS_EINVAL;
+  // NCCL is resolved from whatever libnccl the process already carries (torch's bundled one in
+  // this repo's harness), so this library has no link-time NCCL dependency.
+  typedef int (*bcast_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+  static bcast_fn fn = nullptr;
+  if (!fn) {
+    fn = (bcast_fn)dlsym(RTLD_DEFAULT, "ncclBroadcast");
+    if (!fn) {
+      void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+      if (h) fn = (bcast_fn)dlsym(h, "ncclBroadcast");
+    }
+  }
+  if (!fn) {
+    ctx->last_error = "ncclBroadcast not found (libnccl.so.2 not loadable)";
+    return NXS_ENCCL;
+  }
+  DeviceGuard guard(ctx->device);
+  const int rc = fn(buf, buf, (size_t)count, /*ncclFloat32*/ 7, root, comm, pick(ctx, stream));
+  if (rc != 0) {
+    ctx->last_error = "ncclBroadcast failed with code " + std::to_string(rc);
+    return NXS_ENCCL;
+  }
+  return NXS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,97 @@
+// nxs_common.cuh -- shared declarations of the library's translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/nxsignal_b200.h"
+
+namespace nxs {
+
+// One device-resident table set per FFT plan (built on first use, lives with the ctx).
+struct PlanTables {
+  float2* tw = nullptr;    // per-pass twiddles, Plan::TW_TOTAL entries
+  float2* post = nullptr;  // r2c post-pass: -i * exp(-i pi k / N), k in [0, N/2]   (N = nfft/2)
+};
+
+}  // namespace nxs
+
+struct nxs_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  std::string last_error;
+  uint64_t launches = 0;
+  // scratch: prepared (scaled, zero-extended) window and small coefficient blocks
+  float* d_coef = nullptr;
+  size_t d_coef_bytes = 0;
+  // generic device scratch (FIR spectra, etc.)
+  void* d_scratch = nullptr;
+  size_t d_scratch_bytes = 0;
+  // staging for the _host entry points
+  void* h_pinned = nullptr;
+  size_t h_pinned_bytes = 0;
+  void* d_stage_in = nullptr;
+  size_t d_stage_in_bytes = 0;
+  void* d_stage_out = nullptr;
+  size_t d_stage_out_bytes = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  // twiddle tables keyed by (kind << 32 | N)
+  std::unordered_map<uint64_t, nxs::PlanTables> tables;
+  std::unordered_map<uint64_t, float2*> dft_tables;  // generic DFT: exp(-2 pi i m / n), m < n
+};
+
+namespace nxs {
+
+int set_cuda_error(nxs_ctx* ctx, cudaError_t e, const char* where);
+#define NXS_CUDA(ctx, call)                                            \
+  do {                                                                 \
+    cudaError_t e__ = (call);                                          \
+    if (e__ != cudaSuccess) return nxs::set_cuda_error(ctx, e__, #call); \
+  } while (0)
+
+int ensure_coef(nxs_ctx* ctx, size_t bytes);
+int ensure_scratch(nxs_ctx* ctx, size_t bytes);
+
+// padding geometry shared by stft / as_windowed (lib/nx_signal.ex:303-331, 343-349)
+struct PadGeom {
+  int64_t lo, hi;  // samples added in front / behind
+  int reflect;     // 1: numpy-style reflect, 0: zeros
+};
+int resolve_padding(int64_t length, int64_t window_length, int pad_mode, int64_t pad_lo, int64_t pad_hi,
+                    PadGeom* g);
+int64_t frames_for(int64_t length, int64_t window_length, int64_t stride, const PadGeom& g);
+
+// kernels' host launchers (each returns NXS_* and bumps ctx->launches)
+int launch_stft(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, int64_t x_ld,
+                const float* window, int64_t frame_length, int64_t hop, int64_t fft_length,
+                const PadGeom& g, int64_t num_frames, int scaling, double sampling_rate, float2* z,
+                cudaStream_t st);
+int launch_istft(nxs_ctx* ctx, const float2* z, int64_t channels, int64_t num_frames, int64_t z_len,
+                 const float* window, int64_t frame_length, int64_t hop, int64_t fft_length, int scaling,
+                 double sampling_rate, float2* y, cudaStream_t st);
+int launch_as_windowed(nxs_ctx* ctx, const void* x, int elem_size, int64_t channels, int64_t length,
+                       int64_t x_ld, int64_t window_length, int64_t stride, const PadGeom& g,
+                       int64_t num_frames, void* out, cudaStream_t st);
+int launch_overlap_and_add(nxs_ctx* ctx, const float* t, int complex_, int64_t batch, int64_t num_frames,
+                           int64_t frame_length, int64_t overlap, float* out, cudaStream_t st);
+int launch_fir(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, int64_t x_ld,
+               const float* taps, int64_t num_taps, int mode, float* y, int64_t y_ld, cudaStream_t st);
+int launch_convolve_nd(nxs_ctx* ctx, const float* a, const int64_t* as, const float* b, const int64_t* bs,
+                       int is_complex, int mode, float* out, cudaStream_t st);
+
+// numpy-style reflect of index i into [0, L)
+__host__ __device__ inline int64_t reflect_index(int64_t i, int64_t L) {
+  if (L <= 1) return 0;
+  const int64_t per = 2 * (L - 1);
+  int64_t r = i % per;
+  if (r < 0) r += per;
+  return r < L ? r : per - r;
+}
+
+}  // namespace nxs

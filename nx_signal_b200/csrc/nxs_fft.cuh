@@ -1,0 +1,261 @@
+// nxs_fft.cuh -- register/shared-memory Stockham FFT building blocks for sm_100a.
+//
+// The reference does every FFT as `Nx.fft` / `Nx.ifft` (lib/nx_signal.ex:102, :609;
+// lib/nx_signal/transforms.ex:10,19), executed by Nx.BinaryBackend as a recursive
+// radix-2 over Elixir lists.  Here one FFT of N complex points is computed by a
+// group of T threads holding P = N/T points each in registers: radix-R butterflies
+// in registers, one shared-memory exchange per pass (autosort, natural order in and
+// out), bank-conflict-free padded layouts found by tools/smem_layout_search.py.
+// Index algebra validated by tools/stockham_model.py.
+//
+// Pass p (radix R, NS = product of earlier radices), butterfly j = t + b*T:
+//   in  : x[j + q*N/R]              q = 0..R-1   (stride-1 across threads)
+//   tw  : W_{NS*R}^{q*(j mod NS)}
+//   out : y[expand(j) + q*NS],  expand(j) = (j/NS)*NS*R + (j mod NS)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nxs {
+
+typedef float2 cpx;
+
+__device__ __forceinline__ cpx cadd(cpx a, cpx b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ cpx csub(cpx a, cpx b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ cpx cmul(cpx a, cpx b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ cpx cconj(cpx a) { return make_float2(a.x, -a.y); }
+
+constexpr int ilog2(int x) { return x <= 1 ? 0 : 1 + ilog2(x >> 1); }
+constexpr int bitrev(int k, int bits) {
+  int r = 0;
+  for (int i = 0; i < bits; ++i) { r = (r << 1) | (k & 1); k >>= 1; }
+  return r;
+}
+
+// a * W_16^I, I in [0,8), W_16 = exp(-2 pi i / 16); constants become FFMA immediates
+template <int I>
+__device__ __forceinline__ cpx mul_w16(cpx a) {
+  constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, H = 0.70710678118654752f;
+  if constexpr (I == 0) return a;
+  else if constexpr (I == 4) return make_float2(a.y, -a.x);
+  else if constexpr (I == 2) return make_float2((a.x + a.y) * H, (a.y - a.x) * H);
+  else if constexpr (I == 6) return make_float2((a.y - a.x) * H, -(a.x + a.y) * H);
+  else if constexpr (I == 1) return make_float2(a.x * C1 + a.y * S1, a.y * C1 - a.x * S1);
+  else if constexpr (I == 3) return make_float2(a.x * S1 + a.y * C1, a.y * S1 - a.x * C1);
+  else if constexpr (I == 5) return make_float2(a.y * C1 - a.x * S1, -(a.x * C1 + a.y * S1));
+  else return make_float2(a.y * S1 - a.x * C1, -(a.x * S1 + a.y * C1));  // I == 7
+}
+
+// In-place decimation-in-frequency DFT of R points (forward, e^{-i...}).
+// Result X[k] is left at v[bitrev(k, log2 R)].
+template <int R, int I>
+struct DifStage {
+  static __device__ __forceinline__ void run(cpx* v) {
+    if constexpr (I < R / 2) {
+      cpx a = v[I], b = v[I + R / 2];
+      v[I] = cadd(a, b);
+      v[I + R / 2] = mul_w16<I * (16 / R)>(csub(a, b));
+      DifStage<R, I + 1>::run(v);
+    }
+  }
+};
+
+template <int R>
+struct Dft {
+  static_assert(R == 2 || R == 4 || R == 8 || R == 16, "radix");
+  static __device__ __forceinline__ void run(cpx* v) {
+    if constexpr (R == 2) {
+      cpx a = v[0], b = v[1];
+      v[0] = cadd(a, b);
+      v[1] = csub(a, b);
+    } else {
+      DifStage<R, 0>::run(v);
+      Dft<R / 2>::run(v);
+      Dft<R / 2>::run(v + R / 2);
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// Plan: N points, T threads, up to 4 passes (unused radices = 1).
+// ---------------------------------------------------------------------------------------
+template <int N_, int T_, int R0, int R1 = 1, int R2 = 1, int R3 = 1>
+struct Plan {
+  static constexpr int N = N_, T = T_, P = N_ / T_;
+  static constexpr int NP = 1 + (R1 > 1) + (R2 > 1) + (R3 > 1);
+  static_assert(R0 * R1 * R2 * R3 == N_, "radices must multiply to N");
+  static_assert(N_ % T_ == 0, "T must divide N");
+  static constexpr int R(int p) { return p == 0 ? R0 : p == 1 ? R1 : p == 2 ? R2 : R3; }
+  static constexpr int NS(int p) { return p == 0 ? 1 : p == 1 ? R0 : p == 2 ? R0 * R1 : R0 * R1 * R2; }
+  // exchange after pass p is laid out as pad(i) = i + (i >> A) * C   (A < 0: no padding)
+  static constexpr int padA(int p) {
+    return NS(p) >= 16 ? -1 : (ilog2(NS(p) * R(p)) > 4 ? ilog2(NS(p) * R(p)) : 4);
+  }
+  static constexpr int padC(int p) { return NS(p) >= 16 ? 0 : NS(p); }
+  // complex elements one exchange buffer needs (largest padded layout, multiple of 16)
+  static constexpr int bufNeed(int p) {
+    return padA(p) < 0 ? N_ : N_ + ((N_ - 1) >> padA(p)) * padC(p) + 1;
+  }
+  static constexpr int bufMax() {
+    int m = N_;
+    for (int p = 0; p + 1 < NP; ++p) m = bufNeed(p) > m ? bufNeed(p) : m;
+    return (m + 15) / 16 * 16;
+  }
+  static constexpr int BUF = bufMax();
+  // per-pass twiddle table: for p >= 1, entries [(q-1)*NS + k], q = 1..R-1, k < NS
+  static constexpr int twOffset(int p) {
+    int o = 0;
+    for (int i = 1; i < p; ++i) o += (R(i) - 1) * NS(i);
+    return o;
+  }
+  static constexpr int TW_TOTAL = twOffset(NP);
+  // number of distinct twiddle sets a thread needs in pass p (1 when k = t mod NS for every b)
+  static constexpr int twSets(int p) { return (T_ % NS(p) == 0) ? 1 : (P / R(p)); }
+  static constexpr int twRegOffset(int p) {
+    int o = 0;
+    for (int i = 1; i < p; ++i) o += (R(i) - 1) * twSets(i);
+    return o;
+  }
+  static constexpr int TW_REGS = twRegOffset(NP);
+};
+
+template <int A, int C>
+__device__ __forceinline__ int pad_idx(int i) {
+  if constexpr (A < 0) return i;
+  else return i + (i >> A) * C;
+}
+
+// Twiddles held in registers for the lifetime of a persistent CTA.
+template <class PL>
+struct TwRegs {
+  cpx w[PL::TW_REGS > 0 ? PL::TW_REGS : 1];
+  template <int PASS>
+  __device__ __forceinline__ void init_pass(const cpx* __restrict__ tab, int t) {
+    if constexpr (PASS < PL::NP) {
+      constexpr int R = PL::R(PASS), NS = PL::NS(PASS), SETS = PL::twSets(PASS);
+#pragma unroll
+      for (int s = 0; s < SETS; ++s) {
+        int k = (t + s * PL::T) % NS;
+#pragma unroll
+        for (int q = 1; q < R; ++q)
+          w[PL::twRegOffset(PASS) + s * (R - 1) + q - 1] = tab[PL::twOffset(PASS) + (q - 1) * NS + k];
+      }
+      init_pass<PASS + 1>(tab, t);
+    }
+  }
+  __device__ __forceinline__ void init(const cpx* __restrict__ tab, int t) { init_pass<1>(tab, t); }
+  template <int PASS>
+  __device__ __forceinline__ cpx get(int b, int q, int /*k*/) const {
+    constexpr int R = PL::R(PASS), SETS = PL::twSets(PASS);
+    return w[PL::twRegOffset(PASS) + (SETS == 1 ? 0 : b) * (R - 1) + q - 1];
+  }
+};
+
+// Twiddles read from a table (shared or global memory) on every use.
+template <class PL>
+struct TwTable {
+  const cpx* tab;
+  __device__ __forceinline__ void init(const cpx* t_, int) { tab = t_; }
+  template <int PASS>
+  __device__ __forceinline__ cpx get(int /*b*/, int q, int k) const {
+    return tab[PL::twOffset(PASS) + (q - 1) * PL::NS(PASS) + k];
+  }
+};
+
+struct SyncBlock {
+  __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+// named barrier over `count` threads (count % 32 == 0), id 1..15
+struct SyncNamed {
+  int id, count;
+  __device__ __forceinline__ void operator()() const {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+  }
+};
+struct SyncWarp {
+  __device__ __forceinline__ void operator()() const { __syncwarp(); }
+};
+
+// ---------------------------------------------------------------------------------------
+// One pass: (load from the previous exchange) -> twiddle -> butterflies -> (store to this
+// pass's exchange).  The first pass expects v preloaded by the caller with
+// v[b*R0 + q] = x[t + b*T + q*N/R0]; the last pass leaves X[t + b*T + q*N/R] in
+// v[b*R + bitrev(q)].
+// ---------------------------------------------------------------------------------------
+template <class PL, int PASS, class TW, class SYNC>
+struct PassRunner {
+  static __device__ __forceinline__ void run(cpx (&v)[PL::P], int t, cpx* buf0, cpx* buf1,
+                                             const TW& tw, const SYNC& sync) {
+    constexpr int N = PL::N, T = PL::T, P = PL::P;
+    constexpr int R = PL::R(PASS), NS = PL::NS(PASS), B = P / R;
+    static_assert(P % R == 0, "radix must divide points per thread");
+    if constexpr (PASS > 0) {
+      constexpr int A = PL::padA(PASS - 1), C = PL::padC(PASS - 1);
+      const cpx* in = ((PASS - 1) & 1) ? buf1 : buf0;
+      constexpr int unit = (A < 0) ? 1 : (1 << (A < 0 ? 0 : A));
+      // pad(t + X) splits into pad(t) + pad(X) when every X is a multiple of 2^A
+      constexpr bool split = (A < 0) || (T % unit == 0 && (N / R) % unit == 0);
+      const int tb = pad_idx<A, C>(t);
+#pragma unroll
+      for (int b = 0; b < B; ++b)
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+          const int X = b * T + q * (N / R);
+          if constexpr (split) v[b * R + q] = in[tb + pad_idx<A, C>(X)];
+          else v[b * R + q] = in[pad_idx<A, C>(t + X)];
+        }
+#pragma unroll
+      for (int b = 0; b < B; ++b) {
+        const int k = (t + b * T) % NS;
+#pragma unroll
+        for (int q = 1; q < R; ++q) v[b * R + q] = cmul(v[b * R + q], tw.template get<PASS>(b, q, k));
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < B; ++b) Dft<R>::run(&v[b * R]);
+    if constexpr (PASS + 1 < PL::NP) {
+      constexpr int A = PL::padA(PASS), C = PL::padC(PASS);
+      constexpr int LR = ilog2(NS * R);
+      cpx* out = (PASS & 1) ? buf1 : buf0;
+#pragma unroll
+      for (int b = 0; b < B; ++b) {
+        const int j = t + b * T;
+        const int hi = j / NS, lo = j % NS;
+        int base = hi * (NS * R) + lo;
+        if constexpr (A >= 0) base += (A >= LR ? (hi >> (A - LR)) : (hi << (LR - A))) * C;
+#pragma unroll
+        for (int q = 0; q < R; ++q) out[base + q * NS] = v[b * R + bitrev(q, ilog2(R))];
+      }
+      sync();
+      PassRunner<PL, PASS + 1, TW, SYNC>::run(v, t, buf0, buf1, tw, sync);
+    }
+  }
+};
+
+// Runs all passes.  buf0/buf1: two exchange buffers of PL::BUF complex each, private to
+// the T-thread group.  The caller must order its own later use of buf0/buf1 against the
+// reads of the last exchange (see the kernels).
+template <class PL, class TW, class SYNC>
+__device__ __forceinline__ void block_fft(cpx (&v)[PL::P], int t, cpx* buf0, cpx* buf1, const TW& tw,
+                                          const SYNC& sync) {
+  PassRunner<PL, 0, TW, SYNC>::run(v, t, buf0, buf1, tw, sync);
+}
+
+// logical index of the element the caller must preload into v[b*R0 + q]
+template <class PL>
+__device__ __forceinline__ int fft_in_index(int t, int b, int q) {
+  return t + b * PL::T + q * (PL::N / PL::R(0));
+}
+// after block_fft: X[fft_out_index(t,b,q)] is at v[b*RL + bitrev(q)], RL = last radix
+template <class PL>
+__device__ __forceinline__ int fft_out_index(int t, int b, int q) {
+  return t + b * PL::T + q * (PL::N / PL::R(PL::NP - 1));
+}
+template <class PL>
+__device__ __forceinline__ constexpr int fft_out_reg(int b, int q) {
+  return b * PL::R(PL::NP - 1) + bitrev(q, ilog2(PL::R(PL::NP - 1)));
+}
+
+}  // namespace nxs

@@ -1,0 +1,344 @@
+// nxs_stft.cu -- fused forward STFT for sm_100a.
+//
+// Replaces NxSignal.stft/3 (lib/nx_signal.ex:68-130): as_windowed (:94-100, :249-364) ->
+// Nx.multiply(window) (:101) -> Nx.fft(length: fft_length) (:102) -> optional scaling
+// (:113-127), without ever materialising the {M, N} frame tensor.  One group of T threads
+// transforms one frame: the real frame is packed as nfft/2 complex points, run through
+// the register/shared-memory Stockham FFT (nxs_fft.cuh), and a split post-pass produces
+// the full two-sided spectrum (the reference returns all nfft bins, lib/nx_signal.ex:49)
+// with coalesced 8-byte stores.  The window is pre-multiplied by 1/2 (the split
+// post-pass' factor) and by the :spectrum / :psd scale, so scaling costs nothing.
+//
+// Any fft_length that is not a supported power of two falls back to a direct O(n^2)
+// DFT kernel on the GPU (the reference does the same for odd lengths).
+#include <math.h>
+
+#include "nxs_common.cuh"
+#include "nxs_fft.cuh"
+
+namespace nxs {
+
+// ------------------------------------------------------------------------------------------
+// window preparation: out[s] = w[s] * prescale / S for s < min(N, nfft), 0 up to nfft
+//   :spectrum  S = f32(sum w)                       (lib/nx_signal.ex:116)
+//   :psd       S = f32(sqrt(f32(sr * f32(sum w^2))))  (lib/nx_signal.ex:119)
+// ------------------------------------------------------------------------------------------
+__global__ void prep_window_kernel(const float* __restrict__ w, int n, int nfft, int scaling, float sr,
+                                   float prescale, int invert, float* __restrict__ out) {
+  __shared__ double red[256];
+  double acc = 0.0;
+  if (scaling != NXS_SCALE_NONE) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      float v = w[i];
+      acc += (scaling == NXS_SCALE_SPECTRUM) ? (double)v : (double)(float)((double)v * (double)v);
+    }
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  double S = 1.0;
+  if (scaling == NXS_SCALE_SPECTRUM) S = (double)(float)red[0];
+  else if (scaling == NXS_SCALE_PSD) S = (double)(float)sqrt((double)(float)((double)sr * (double)(float)red[0]));
+  // stft divides by S, istft multiplies by S
+  const float f = (float)(invert ? (double)prescale * S : (double)prescale / S);
+  const int nload = n < nfft ? n : nfft;
+  for (int i = threadIdx.x; i < nfft; i += blockDim.x) out[i] = (i < nload) ? w[i] * f : 0.f;
+}
+
+struct StftArgs {
+  const float* x;
+  int64_t x_ld, L;
+  const float* wprep;  // [nfft], scaled, zero-extended
+  float2* z;           // [total_frames][nfft]
+  int64_t M, total_frames, hop, pad_lo;
+  int nload;           // min(frame_length, nfft)
+  int reflect;
+  const float2* tw;
+  const float2* post;
+};
+
+__device__ __forceinline__ float load_padded(const float* __restrict__ xrow, int64_t src, int64_t L,
+                                             int reflect) {
+  if (src >= 0 && src < L) return __ldg(xrow + src);
+  if (reflect) return __ldg(xrow + reflect_index(src, L));
+  return 0.f;
+}
+
+template <class PL, class TW, int THREADS>
+__global__ void __launch_bounds__(THREADS) stft_r2c_kernel(const StftArgs a) {
+  constexpr int N = PL::N, T = PL::T, P = PL::P, G = THREADS / T, NFFT = 2 * N;
+  constexpr int R0 = PL::R(0), B0 = P / R0;
+  constexpr int RL = PL::R(PL::NP - 1), BL = P / RL;
+  static_assert(THREADS % T == 0 && P >= 2, "bad plan");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, g = tid / T, t = tid % T;
+  cpx* bufA = reinterpret_cast<cpx*>(smem_raw) + (size_t)(2 * g) * PL::BUF;
+  cpx* bufB = bufA + PL::BUF;
+
+  TW tw;
+  tw.init(a.tw, t);
+  cpx wpost[P / 2];
+#pragma unroll
+  for (int i = 0; i < P / 2; ++i) wpost[i] = __ldg(a.post + t + i * T);
+  const SyncBlock sync;
+
+  const int64_t num_tiles = (a.total_frames + G - 1) / G;
+  for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int64_t f = tile * G + g;
+    const bool active = f < a.total_frames;
+    cpx v[P];
+    if (active) {
+      const int64_t c = f / a.M, m = f - c * a.M;
+      const float* __restrict__ xrow = a.x + c * a.x_ld;
+      const int64_t src0 = m * a.hop - a.pad_lo;
+      const bool fast = (a.nload == NFFT) && src0 >= 0 && src0 + NFFT <= a.L &&
+                        ((reinterpret_cast<uintptr_t>(xrow + src0) & 7) == 0);
+      if (fast) {
+        const float2* __restrict__ xp = reinterpret_cast<const float2*>(xrow + src0);
+        const float2* __restrict__ wp = reinterpret_cast<const float2*>(a.wprep);
+#pragma unroll
+        for (int b = 0; b < B0; ++b)
+#pragma unroll
+          for (int q = 0; q < R0; ++q) {
+            const int i = fft_in_index<PL>(t, b, q);
+            const float2 xx = __ldg(xp + i), ww = __ldg(wp + i);
+            v[b * R0 + q] = make_float2(xx.x * ww.x, xx.y * ww.y);
+          }
+      } else {
+#pragma unroll
+        for (int b = 0; b < B0; ++b)
+#pragma unroll
+          for (int q = 0; q < R0; ++q) {
+            const int s = 2 * fft_in_index<PL>(t, b, q);
+            float re = 0.f, im = 0.f;
+            if (s < a.nload) re = load_padded(xrow, src0 + s, a.L, a.reflect) * __ldg(a.wprep + s);
+            if (s + 1 < a.nload) im = load_padded(xrow, src0 + s + 1, a.L, a.reflect) * __ldg(a.wprep + s + 1);
+            v[b * R0 + q] = make_float2(re, im);
+          }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < P; ++i) v[i] = make_float2(0.f, 0.f);
+    }
+
+    block_fft<PL>(v, t, bufA, bufB, tw, sync);
+
+    // split post-pass through the next exchange buffer (unpadded: both Z[k] and Z[N-k]
+    // reads are stride +-1 across threads)
+    cpx* pb = ((PL::NP - 1) & 1) ? bufB : bufA;
+#pragma unroll
+    for (int b = 0; b < BL; ++b)
+#pragma unroll
+      for (int q = 0; q < RL; ++q) pb[fft_out_index<PL>(t, b, q)] = v[fft_out_reg<PL>(b, q)];
+    sync();
+    if (active) {
+      float2* __restrict__ zf = a.z + f * NFFT;
+#pragma unroll
+      for (int i = 0; i < P / 2; ++i) {
+        const int kk = t + i * T;
+        const cpx A = pb[kk];
+        const cpx Bc = cconj(pb[(N - kk) & (N - 1)]);
+        const cpx E = cadd(A, Bc), O = csub(A, Bc);
+        const cpx Tm = cmul(wpost[i], O);
+        const cpx X0 = cadd(E, Tm), X1 = csub(E, Tm);
+        zf[kk] = X0;
+        zf[N + kk] = X1;
+        if (kk > 0) {
+          zf[N - kk] = cconj(X1);
+          zf[NFFT - kk] = cconj(X0);
+        } else {
+          const cpx Zh = pb[N / 2];
+          zf[N / 2] = make_float2(2.f * Zh.x, -2.f * Zh.y);
+          zf[N + N / 2] = make_float2(2.f * Zh.x, 2.f * Zh.y);
+        }
+      }
+    }
+    if constexpr (PL::NP & 1) {
+      cpx* tmp = bufA;
+      bufA = bufB;
+      bufB = tmp;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// generic path: direct DFT, any fft_length >= 1.  One CTA per frame.
+//   tab[m] = exp(-2 pi i m / nfft) (double-computed), X[k] = sum_s xw[s] * tab[(k*s) mod nfft]
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) stft_dft_kernel(const StftArgs a, int nfft, const float2* __restrict__ tab) {
+  extern __shared__ float xw[];
+  for (int64_t f = blockIdx.x; f < a.total_frames; f += gridDim.x) {
+    const int64_t c = f / a.M, m = f - c * a.M;
+    const float* __restrict__ xrow = a.x + c * a.x_ld;
+    const int64_t src0 = m * a.hop - a.pad_lo;
+    __syncthreads();
+    for (int s = threadIdx.x; s < a.nload; s += blockDim.x)
+      xw[s] = load_padded(xrow, src0 + s, a.L, a.reflect) * a.wprep[s];
+    __syncthreads();
+    for (int k = threadIdx.x; k < nfft; k += blockDim.x) {
+      float re = 0.f, im = 0.f;
+      int idx = 0;
+      for (int s = 0; s < a.nload; ++s) {
+        const float2 w = __ldg(tab + idx);
+        const float xv = xw[s];
+        re = fmaf(xv, w.x, re);
+        im = fmaf(xv, w.y, im);
+        idx += k;
+        if (idx >= nfft) idx -= nfft;
+      }
+      a.z[f * nfft + k] = make_float2(re, im);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+template <class PL>
+static int get_tables(nxs_ctx* ctx, PlanTables* out) {
+  const uint64_t key = (uint64_t(PL::N) << 32) | (uint64_t(PL::T) << 8) | uint64_t(PL::NP);
+  auto it = ctx->tables.find(key);
+  if (it != ctx->tables.end()) {
+    *out = it->second;
+    return NXS_OK;
+  }
+  std::vector<float2> tw(PL::TW_TOTAL > 0 ? PL::TW_TOTAL : 1);
+  for (int p = 1; p < PL::NP; ++p) {
+    const int R = PL::R(p), NS = PL::NS(p);
+    for (int q = 1; q < R; ++q)
+      for (int k = 0; k < NS; ++k) {
+        const double ang = -2.0 * M_PI * double(q) * double(k) / double(NS * R);
+        tw[PL::twOffset(p) + (q - 1) * NS + k] = make_float2((float)cos(ang), (float)sin(ang));
+      }
+  }
+  std::vector<float2> post(PL::N / 2 + 1);
+  for (int k = 0; k <= PL::N / 2; ++k) {
+    const double th = M_PI * double(k) / double(PL::N);
+    post[k] = make_float2((float)(-sin(th)), (float)(-cos(th)));
+  }
+  PlanTables t;
+  NXS_CUDA(ctx, cudaMalloc(&t.tw, tw.size() * sizeof(float2)));
+  NXS_CUDA(ctx, cudaMalloc(&t.post, post.size() * sizeof(float2)));
+  NXS_CUDA(ctx, cudaMemcpy(t.tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+  NXS_CUDA(ctx, cudaMemcpy(t.post, post.data(), post.size() * sizeof(float2), cudaMemcpyHostToDevice));
+  ctx->tables[key] = t;
+  *out = t;
+  return NXS_OK;
+}
+
+int get_dft_table(nxs_ctx* ctx, int64_t n, int sign, float2** out) {
+  const uint64_t key = (uint64_t(sign < 0 ? 2 : 3) << 32) | uint64_t(n);
+  auto it = ctx->dft_tables.find(key);
+  if (it != ctx->dft_tables.end()) {
+    *out = it->second;
+    return NXS_OK;
+  }
+  std::vector<float2> tab(n);
+  for (int64_t m = 0; m < n; ++m) {
+    const double ang = (sign < 0 ? -2.0 : 2.0) * M_PI * double(m) / double(n);
+    tab[m] = make_float2((float)cos(ang), (float)sin(ang));
+  }
+  float2* d = nullptr;
+  NXS_CUDA(ctx, cudaMalloc(&d, n * sizeof(float2)));
+  NXS_CUDA(ctx, cudaMemcpy(d, tab.data(), n * sizeof(float2), cudaMemcpyHostToDevice));
+  ctx->dft_tables[key] = d;
+  *out = d;
+  return NXS_OK;
+}
+
+template <class PL, class TW, int THREADS>
+static int run_r2c(nxs_ctx* ctx, StftArgs a, cudaStream_t st) {
+  PlanTables tabs;
+  int rc = get_tables<PL>(ctx, &tabs);
+  if (rc) return rc;
+  a.tw = tabs.tw;
+  a.post = tabs.post;
+  constexpr int G = THREADS / PL::T;
+  const size_t smem = size_t(G) * 2 * PL::BUF * sizeof(cpx);
+  auto kern = stft_r2c_kernel<PL, TW, THREADS>;
+  NXS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 1;
+  NXS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
+  if (occ < 1) occ = 1;
+  const int64_t tiles = (a.total_frames + G - 1) / G;
+  int64_t grid = int64_t(ctx->sm_count) * occ;
+  if (grid > tiles) grid = tiles;
+  if (grid < 1) grid = 1;
+  kern<<<(unsigned)grid, THREADS, smem, st>>>(a);
+  ctx->launches++;
+  NXS_CUDA(ctx, cudaGetLastError());
+  return NXS_OK;
+}
+
+int launch_prep_window(nxs_ctx* ctx, const float* window, int64_t n, int64_t nfft, int scaling,
+                       double sampling_rate, float prescale, int invert, float* out, cudaStream_t st) {
+  prep_window_kernel<<<1, 256, 0, st>>>(window, (int)n, (int)nfft, scaling, (float)sampling_rate, prescale,
+                                        invert, out);
+  ctx->launches++;
+  NXS_CUDA(ctx, cudaGetLastError());
+  return NXS_OK;
+}
+
+int launch_stft(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, int64_t x_ld,
+                const float* window, int64_t frame_length, int64_t hop, int64_t fft_length,
+                const PadGeom& g, int64_t num_frames, int scaling, double sampling_rate, float2* z,
+                cudaStream_t st) {
+  if (num_frames <= 0 || channels <= 0) return NXS_OK;
+  if (fft_length > (int64_t(1) << 24) || frame_length > (int64_t(1) << 24)) return NXS_EUNSUPPORTED;
+  const int64_t nfft = fft_length;
+  int rc = ensure_coef(ctx, size_t(nfft) * sizeof(float));
+  if (rc) return rc;
+
+  StftArgs a;
+  a.x = x;
+  a.x_ld = x_ld;
+  a.L = length;
+  a.wprep = ctx->d_coef;
+  a.z = z;
+  a.M = num_frames;
+  a.total_frames = num_frames * channels;
+  a.hop = hop;
+  a.pad_lo = g.lo;
+  a.nload = (int)(frame_length < nfft ? frame_length : nfft);
+  a.reflect = g.reflect;
+  a.tw = nullptr;
+  a.post = nullptr;
+
+  const bool pow2 = (nfft & (nfft - 1)) == 0;
+  const bool fast = pow2 && nfft >= 64 && nfft <= 16384;
+  rc = launch_prep_window(ctx, window, frame_length, nfft, scaling, sampling_rate, fast ? 0.5f : 1.0f, 0,
+                          ctx->d_coef, st);
+  if (rc) return rc;
+
+  if (fast) {
+    switch (nfft) {
+      case 64: return run_r2c<Plan<32, 4, 8, 4>, TwTable<Plan<32, 4, 8, 4>>, 256>(ctx, a, st);
+      case 128: return run_r2c<Plan<64, 8, 8, 8>, TwTable<Plan<64, 8, 8, 8>>, 256>(ctx, a, st);
+      case 256: return run_r2c<Plan<128, 16, 8, 8, 2>, TwTable<Plan<128, 16, 8, 8, 2>>, 256>(ctx, a, st);
+      case 512: return run_r2c<Plan<256, 32, 8, 8, 4>, TwTable<Plan<256, 32, 8, 8, 4>>, 256>(ctx, a, st);
+      case 1024: return run_r2c<Plan<512, 64, 8, 8, 8>, TwRegs<Plan<512, 64, 8, 8, 8>>, 512>(ctx, a, st);
+      case 2048: return run_r2c<Plan<1024, 64, 16, 8, 8>, TwTable<Plan<1024, 64, 16, 8, 8>>, 512>(ctx, a, st);
+      case 4096: return run_r2c<Plan<2048, 128, 16, 16, 8>, TwTable<Plan<2048, 128, 16, 16, 8>>, 512>(ctx, a, st);
+      case 8192: return run_r2c<Plan<4096, 256, 16, 16, 16>, TwTable<Plan<4096, 256, 16, 16, 16>>, 512>(ctx, a, st);
+      case 16384:
+        return run_r2c<Plan<8192, 512, 16, 16, 16, 2>, TwTable<Plan<8192, 512, 16, 16, 16, 2>>, 512>(ctx, a, st);
+      default: break;
+    }
+  }
+  float2* tab = nullptr;
+  rc = get_dft_table(ctx, nfft, -1, &tab);
+  if (rc) return rc;
+  const size_t smem = size_t(a.nload) * sizeof(float);
+  if (smem > 200 * 1024) return NXS_EUNSUPPORTED;
+  NXS_CUDA(ctx, cudaFuncSetAttribute(stft_dft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int64_t grid = a.total_frames < int64_t(ctx->sm_count) * 8 ? a.total_frames : int64_t(ctx->sm_count) * 8;
+  stft_dft_kernel<<<(unsigned)grid, 256, smem, st>>>(a, (int)nfft, tab);
+  ctx->launches++;
+  NXS_CUDA(ctx, cudaGetLastError());
+  return NXS_OK;
+}
+
+}  // namespace nxs

@@ -1,0 +1,141 @@
+"""CPU-side tests: the C-ABI library loads and exports every declared symbol, and its
+host-side closed forms (windows, firwin, frequencies, times, frame counts) equal the
+oracle bit for bit.  No compute call needs a GPU here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import nx_signal_b200 as nx
+from nx_signal_b200 import _lib
+from oracle import nxsignal_oracle as o
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "nxsignal_b200.h")).read()
+    declared = set(re.findall(r"\b(nxs_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"nxs_ctx"}
+    assert len(declared) >= 29
+    lib = C.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert _lib.lib().nxs_abi_version() == 1
+
+
+def test_error_strings_and_no_device_behaviour():
+    assert _lib.strerror(0) == "ok"
+    assert "no CUDA device" in _lib.strerror(_lib.NXS_ENODEVICE)
+    if _lib.lib().nxs_device_count() == 0:
+        with pytest.raises(RuntimeError, match="no CUDA device"):
+            nx.stft(np.zeros(64, np.float32), nx.windows.hann(16))
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 6, 7, 8, 16, 31, 64, 257, 1024, 2049, 4096])
+def test_windows_bit_exact_vs_oracle(n):
+    for periodic in (True, False):
+        if n == 1 and not periodic:
+            continue  # l - 1 == 0: the reference divides by zero here as well
+        np.testing.assert_array_equal(nx.windows.hann(n, is_periodic=periodic), o.hann(n, periodic))
+        np.testing.assert_array_equal(nx.windows.hamming(n, is_periodic=periodic), o.hamming(n, periodic))
+        np.testing.assert_array_equal(nx.windows.blackman(n, is_periodic=periodic), o.blackman(n, periodic))
+        np.testing.assert_array_equal(
+            nx.windows.kaiser(n, beta=8.6, is_periodic=periodic), o.kaiser(n, beta=8.6, is_periodic=periodic))
+    np.testing.assert_array_equal(nx.windows.bartlett(n), o.bartlett(n))
+    np.testing.assert_array_equal(nx.windows.triangular(n), o.triangular(n))
+    np.testing.assert_array_equal(nx.windows.rectangular(n), o.rectangular(n))
+    assert nx.windows.rectangular(n).dtype == np.int64
+
+
+def test_window_doctest_vectors():  # lib/nx_signal/windows.ex:266-275, 322-338
+    f = lambda xs: np.array(xs, dtype=np.float64).astype(np.float32)
+    np.testing.assert_array_equal(nx.windows.hann(5), f([0.0, 0.34549153, 0.90450853, 0.9045085, 0.34549144]))
+    np.testing.assert_array_equal(nx.windows.kaiser(4, beta=12.0), f([5.277619e-5, 0.21566667, 1.0, 0.21566667]))
+    np.testing.assert_array_equal(
+        nx.windows.kaiser(4, beta=12.0, is_periodic=False), f([5.277619e-5, 0.5188395, 0.51883906, 5.277619e-5]))
+
+
+FIRWIN = [
+    dict(num_taps=5, cutoff=[0.3]),
+    dict(num_taps=7, cutoff=[0.4], pass_zero=False),
+    dict(num_taps=9, cutoff=[0.2, 0.6], pass_zero=False, window="hann"),
+    dict(num_taps=11, cutoff=[0.3, 0.7], window="blackman"),
+    dict(num_taps=7, cutoff=[0.5], window=("kaiser", 5.0)),
+    dict(num_taps=7, cutoff=[0.4], window="rectangular"),
+    dict(num_taps=5, cutoff=[0.3], scale=False),
+    dict(num_taps=5, cutoff=[1000], sampling_rate=8000),
+    dict(num_taps=2049, cutoff=[6000], sampling_rate=48000),
+    dict(num_taps=64, cutoff=[0.1, 0.5], window="bartlett", pass_zero=False),
+]
+
+
+@pytest.mark.parametrize("kw", FIRWIN)
+def test_firwin_bit_exact_vs_oracle(kw):
+    np.testing.assert_array_equal(nx.filters.firwin(**kw), o.firwin(**kw))
+
+
+def test_firwin_errors():  # test/nx_signal/filters_test.exs:396-416
+    with pytest.raises(nx.NxSignalArgumentError, match="cutoff must be strictly between 0 and Nyquist"):
+        nx.filters.firwin(5, [1.0])
+    with pytest.raises(nx.NxSignalArgumentError, match="cutoff must be strictly between 0 and Nyquist"):
+        nx.filters.firwin(5, [0.0])
+    with pytest.raises(nx.NxSignalArgumentError, match="odd number of taps"):
+        nx.filters.firwin(6, [0.4], pass_zero=False)
+    with pytest.raises(nx.NxSignalArgumentError, match="unknown window"):
+        nx.filters.firwin(5, [0.3], window="bogus")
+    with pytest.raises(nx.NxSignalArgumentError, match="cutoff must be a list"):
+        nx.filters.firwin(5, 0.3)
+    # the C entry itself also rejects these (no Python pre-check involved)
+    cuts = (C.c_double * 1)(1.0)
+    out = np.empty(5, np.float32)
+    assert _lib.lib().nxs_firwin_f32(5, cuts, 1, 4, 0.0, 1, 1, 2.0, out.ctypes.data) == _lib.NXS_EINVAL
+
+
+@pytest.mark.parametrize("sr,nfft", [(1.6e4, 10), (48000, 1024), (100, 4096), (44100.5, 7)])
+def test_fft_frequencies_vs_oracle(sr, nfft):
+    np.testing.assert_array_equal(nx.fft_frequencies(sr, nfft), o.fft_frequencies(sr, nfft))
+
+
+@pytest.mark.parametrize("N,sr,M", [(2, 400, 3), (1024, 48000, 184), (4096, 48000.0, 2809), (4, 1, 3)])
+def test_stft_times_vs_oracle(N, sr, M):
+    np.testing.assert_array_equal(nx.stft_times(N, sr, M), o.stft_times(N, sr, M))
+
+
+@pytest.mark.parametrize(
+    "L,N,stride,padding",
+    [(8, 4, 1, "valid"), (7, 2, 2, [(0, 3)]), (7, 6, 1, "reflect"), (10, 6, 2, "reflect"), (48000, 1024, 256, "valid"),
+     (100, 16, 4, "same"), (3, 8, 1, "valid"), (28_800_000, 1024, 256, "valid")])
+def test_num_frames_vs_oracle(L, N, stride, padding):
+    mode, lo, hi = nx._padding_code(padding)
+    assert nx._num_frames(L, N, stride, mode, lo, hi) == o.num_frames(L, N, stride, padding)
+
+
+def test_option_validation_matches_reference_messages():
+    x = np.zeros(64, np.float32)
+    w = nx.windows.hann(16)
+    with pytest.raises(nx.NxSignalArgumentError, match="invalid :scaling"):
+        nx.stft(x, w, scaling="power")
+    with pytest.raises(nx.NxSignalArgumentError, match="missing sampling_rate"):
+        nx.stft(x, w, sampling_rate=None)
+    with pytest.raises(nx.NxSignalArgumentError, match="invalid padding mode"):
+        nx.stft(x, w, window_padding="zeros")
+    with pytest.raises(nx.NxSignalArgumentError, match="padding must be a list"):
+        nx.as_windowed(x, window_length=4, padding=[(0.5, 1)])
+    with pytest.raises(nx.NxSignalArgumentError, match="expected an integer >= 1"):
+        nx.as_windowed(x, window_length=4, stride=0)
+    with pytest.raises(nx.NxSignalArgumentError, match="overlap_length must be a number less than"):
+        nx.overlap_and_add(np.zeros((3, 4), np.float32), overlap_length=4)
+    with pytest.raises(nx.NxSignalArgumentError, match="expected mode to be one of"):
+        nx.convolution.convolve([1, 2, 3], [1, 2], mode="spam")
+    with pytest.raises(nx.NxSignalArgumentError, match="expected method to be one of"):
+        nx.convolution.convolve([1, 2, 3], [1, 2], method="bacon")
+    with pytest.raises(nx.NxSignalArgumentError, match=":sampling_rate is mandatory"):
+        nx.istft(np.zeros((3, 16), np.complex64), w, scaling="psd", sampling_rate=None)
+    with pytest.raises(nx.NxSignalArgumentError):
+        nx.convolution.convolve(np.array([1]), np.array(2))
+    with pytest.raises(nx.NxSignalArgumentError):
+        nx.convolution.convolve(np.arange(6).reshape(2, 3), np.arange(6).reshape(3, 2), mode="valid")

@@ -1,0 +1,139 @@
+"""GPU parity of the fused STFT kernel (through the C ABI) against the oracle.
+Tolerance: per-frame max|gpu - oracle| / max|oracle| <= 1e-5 (north_star's 1e-5 relative
+fp32; element-wise relative error is meaningless at near-zero bins)."""
+import numpy as np
+import pytest
+
+import nx_signal_b200 as nx
+from oracle import nxsignal_oracle as o
+from tests.util import TOL, frame_rel_err, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_doctest_stft_rect2():  # lib/nx_signal.ex:46-65 (generic DFT path, nfft = 2)
+    z, t, f = nx.stft(np.arange(4, dtype=np.int32), nx.windows.rectangular(2), overlap_length=1, fft_length=2,
+                      sampling_rate=400)
+    np.testing.assert_array_equal(z, np.array([[1, -1], [3, -1], [5, -1]], dtype=np.complex64))
+    np.testing.assert_array_equal(t, np.array([0.0025, 0.005, 0.0075], dtype=np.float32))
+    np.testing.assert_array_equal(f, np.array([0.0, 200.0], dtype=np.float32))
+
+
+def test_doctest_stft_reflect_nfft16():  # lib/nx_signal.ex:465-471
+    kw = dict(overlap_length=2, fft_length=16, sampling_rate=8.0e3, window_padding="reflect")
+    z, _, _ = nx.stft(np.arange(10, dtype=np.int32), nx.windows.hann(4), **kw)
+    zo, _, _ = o.stft(np.arange(10, dtype=np.int32), o.hann(4), **kw)
+    assert z.shape == (6, 16)
+    assert frame_rel_err(z, zo) <= TOL
+
+
+def test_cfg1_vs_literal_oracle():
+    """BASELINE config 1: 1 x 48000, nfft 1024, hop 256, Hann -- against the literal
+    recursive-radix-2 f64 restatement of Nx.BinaryBackend."""
+    x = synth((48000,), 1001)
+    w = nx.windows.hann(1024)
+    z, t, f = nx.stft(x, w, overlap_length=768, fft_length=1024, sampling_rate=48000)
+    zo, to, fo = o.stft(x, o.hann(1024), overlap_length=768, fft_length=1024, sampling_rate=48000)
+    assert z.shape == (184, 1024) and z.dtype == np.complex64
+    assert frame_rel_err(z, zo) <= TOL
+    np.testing.assert_array_equal(t, to)
+    np.testing.assert_array_equal(f, fo)
+
+
+@pytest.mark.parametrize("nfft", [64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384])
+def test_every_pow2_plan(nfft):
+    x = synth((3, 6 * nfft + 37), 7 + nfft)
+    w = o.hann(nfft)
+    z, _, _ = nx.stft(x, w, overlap_length=nfft - nfft // 4, fft_length=nfft, sampling_rate=48000)
+    zo, _, _ = o.stft_fast(x, w, overlap_length=nfft - nfft // 4, fft_length=nfft, sampling_rate=48000)
+    assert z.shape == zo.shape
+    assert frame_rel_err(z, zo) <= TOL
+
+
+@pytest.mark.parametrize("nfft", [1, 2, 3, 5, 10, 16, 30, 32, 100, 250, 1000])
+def test_generic_dft_lengths(nfft):
+    N = max(2, min(nfft, 24))
+    x = synth((2, 400), 99 + nfft)
+    w = o.hamming(N)
+    z, _, _ = nx.stft(x, w, overlap_length=N // 2, fft_length=nfft, sampling_rate=100)
+    zo, _, _ = o.stft(x, w, overlap_length=N // 2, fft_length=nfft, sampling_rate=100)
+    assert frame_rel_err(z, zo) <= TOL
+
+
+@pytest.mark.parametrize("padding", ["valid", "same", "reflect", [(5, 9)], [(0, 300)]])
+@pytest.mark.parametrize("N,hop,nfft", [(256, 64, 256), (200, 50, 256), (300, 77, 256), (256, 255, 1024), (64, 64, 64)])
+def test_padding_modes_and_lengths(padding, N, hop, nfft):
+    x = synth((2, 3001), 5)
+    w = o.blackman(N)
+    kw = dict(overlap_length=N - hop, fft_length=nfft, sampling_rate=8000, window_padding=padding)
+    z, t, f = nx.stft(x, w, **kw)
+    zo, to, fo = o.stft_fast(x, w, **kw)
+    assert z.shape == zo.shape
+    assert frame_rel_err(z, zo) <= TOL
+    np.testing.assert_array_equal(t, to)
+    np.testing.assert_array_equal(f, fo)
+
+
+@pytest.mark.parametrize("scaling", [None, "spectrum", "psd"])
+def test_scaling(scaling):
+    x = synth((4, 9000), 11)
+    w = o.hann(512)
+    kw = dict(overlap_length=384, fft_length=512, sampling_rate=16000, scaling=scaling)
+    z, _, _ = nx.stft(x, w, **kw)
+    zo, _, _ = o.stft_fast(x, w, **kw)
+    assert frame_rel_err(z, zo) <= TOL
+
+
+def test_batch_axes_and_int_input():
+    x = (synth((2, 3, 5000), 3) * 1000).astype(np.int32)
+    w = o.hann(128)
+    z, _, _ = nx.stft(x, w, fft_length=128, sampling_rate=100)
+    zo, _, _ = o.stft_fast(x.astype(np.float32), w, fft_length=128, sampling_rate=100)
+    assert z.shape == (2, 3, zo.shape[-2], 128)
+    assert frame_rel_err(z, zo) <= TOL
+
+
+def test_device_entry_matches_host_entry():
+    import torch
+
+    x = synth((5, 40000), 21)
+    w = nx.windows.hann(1024)
+    zh, _, _ = nx.stft(x, w, overlap_length=768, sampling_rate=48000)
+    xd = torch.from_numpy(x).cuda()
+    zd, td, fd = nx.stft(xd, torch.from_numpy(w).cuda(), overlap_length=768, sampling_rate=48000)
+    torch.cuda.synchronize()
+    assert zd.is_cuda and zd.dtype == torch.complex64
+    np.testing.assert_array_equal(zd.cpu().numpy(), zh)
+
+
+def test_empty_and_ragged():
+    w = nx.windows.hann(64)
+    z, t, f = nx.stft(np.zeros(10, np.float32), w, sampling_rate=100)  # shorter than one frame
+    assert z.shape == (0, 64) and t.shape == (0,) and f.shape == (64,)
+    z, _, _ = nx.stft(synth((1, 64), 1), w, sampling_rate=100)  # exactly one frame
+    zo, _, _ = o.stft_fast(synth((1, 64), 1), w, sampling_rate=100)
+    assert z.shape == (1, 1, 64) and frame_rel_err(z, zo) <= TOL
+
+
+def test_properties_at_scale():
+    """Size-independent checks on a large shape (oracle would take minutes): linearity and
+    Parseval per frame, Hermitian symmetry of the two-sided spectrum."""
+    import torch
+
+    C, L, N, H = 4, 2_000_000, 1024, 256
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = torch.randn(C, L, device="cuda", generator=g)
+    b = torch.randn(C, L, device="cuda", generator=g)
+    w = torch.from_numpy(nx.windows.hann(N)).cuda()
+    za, _, _ = nx.stft(a, w, overlap_length=N - H, sampling_rate=48000)
+    zb, _, _ = nx.stft(b, w, overlap_length=N - H, sampling_rate=48000)
+    zab, _, _ = nx.stft(2.0 * a - 3.0 * b, w, overlap_length=N - H, sampling_rate=48000)
+    lin = (zab - (2.0 * za - 3.0 * zb)).abs().amax(dim=-1) / zab.abs().amax(dim=-1)
+    assert float(lin.max()) < 5e-6
+    # Parseval: sum |X|^2 = nfft * sum (x w)^2
+    frames = a.unfold(-1, N, H) * w
+    e_t = (frames.double() ** 2).sum(-1) * N
+    e_f = (za.abs().double() ** 2).sum(-1)
+    assert float(((e_t - e_f).abs() / e_t).max()) < 1e-5
+    herm = (za[..., 1:] - za[..., 1:].flip(-1).conj()).abs().amax(dim=-1) / za.abs().amax(dim=-1)
+    assert float(herm.max()) < 1e-6
