@@ -189,7 +189,8 @@ __global__ void __launch_bounds__(256) stft_dft_kernel(const StftArgs a, int nff
         idx += k;
         if (idx >= nfft) idx -= nfft;
       }
-      a.z[f * nfft + k] = make_float2(re, im);
+      // Nx.fft snaps |re|, |im| <= eps (1e-10) to zero
+      a.z[f * nfft + k] = make_float2(fabsf(re) <= 1e-10f ? 0.f : re, fabsf(im) <= 1e-10f ? 0.f : im);
     }
   }
 }
@@ -239,7 +240,10 @@ int get_dft_table(nxs_ctx* ctx, int64_t n, int sign, float2** out) {
   std::vector<float2> tab(n);
   for (int64_t m = 0; m < n; ++m) {
     const double ang = (sign < 0 ? -2.0 : 2.0) * M_PI * double(m) / double(n);
-    tab[m] = make_float2((float)cos(ang), (float)sin(ang));
+    double c = cos(ang), sn = sin(ang);
+    if (fabs(c) < 1e-15) c = 0.0;  // exact zeros at multiples of pi/2
+    if (fabs(sn) < 1e-15) sn = 0.0;
+    tab[m] = make_float2((float)c, (float)sn);
   }
   float2* d = nullptr;
   NXS_CUDA(ctx, cudaMalloc(&d, n * sizeof(float2)));
