@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- STFT frames/s (1024-pt, 256-hop, fp32) on N B200s, with roofline, end-to-end
+(host buffers) and CPU-baseline figures.  Contract: see the task brief / DESIGN.md.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of NxSignal.stft over the BASELINE config-2 workload
+(8 ch x 600 s @ 48 kHz f32, Hann(1024), hop 256, :valid  ->  899 976 frames) per GPU.
+N > 1: one rank per GPU (torchrun), each rank owns its own 8 channels (weak scaling);
+the only collective is one NCCL broadcast of the window at setup.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FS = 48000
+CHANNELS = 8
+SECONDS = 600
+NFFT = 1024
+HOP = 256
+L = FS * SECONDS
+M = (L - NFFT) // HOP + 1
+FRAMES_PER_GPU = CHANNELS * M
+ALGO_BYTES = 4 * CHANNELS * L + 8 * CHANNELS * M * NFFT + 4 * NFFT
+METRIC = "STFT frames/sec (1024-pt, 256-hop, fp32)"
+WORKLOAD = "cfg2: 8ch x 600s @48kHz f32, hann(1024), hop 256, :valid -> 899976 frames per GPU"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks line sampled during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        inside = [l for (t, l) in self.lines if t0 - 0.05 <= t <= t1 + 0.15] or [l for _, l in self.lines]
+        for l in inside:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_port_rate(seconds_target, nthreads=0):
+    """Times the oracle's C port (the reference's algorithm restated, f64 recursive radix-2)
+    on a bounded sample of the same workload; returns (frames/s, cores, sample text)."""
+    from oracle import c_port
+    from oracle import nxsignal_oracle as o
+    from tests.util import synth
+
+    w = o.hann(NFFT)
+    cores = c_port.threads() if nthreads <= 0 else nthreads
+    cal_frames = 2048 * max(cores // 8, 1)
+    x = synth((1, cal_frames * HOP + NFFT - HOP), 1002)
+    t = time.perf_counter()
+    c_port.stft(x, w, HOP, NFFT, nthreads=nthreads)
+    rate = cal_frames / (time.perf_counter() - t)
+    frames = int(max(cal_frames, min(rate * seconds_target, 8_000_000)))
+    x = synth((1, frames * HOP + NFFT - HOP), 1002)
+    t = time.perf_counter()
+    z = c_port.stft(x, w, HOP, NFFT, nthreads=nthreads)
+    dt = time.perf_counter() - t
+    assert z.shape[1] == frames
+    return frames / dt, cores, f"{frames} frames of cfg2 channel 0 ({frames * HOP / FS:.0f} s of audio), {dt:.1f} s"
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference's own CPU algorithm (Nx.BinaryBackend's recursive radix-2 in
+    f64, restated in C: oracle/nxs_oracle.c -- the BEAM cannot run here) on all host threads."""
+    if rank != 0:
+        return
+    per_step = max(1.0, min(5.0, 120.0 / max(args.steps + args.warmup, 1)))
+    for _ in range(min(args.warmup, 1)):
+        cpu_port_rate(0.5)
+    rates, sample, cores = [], "", 1
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r, cores, sample = cpu_port_rate(per_step)
+        rates.append(r)
+    total = time.perf_counter() - t0
+    value = float(np.mean(rates))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (rounded to f32/c64)",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "sample_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def make_input(torch, dev, seed):
+    g = torch.Generator(device=dev).manual_seed(seed)
+    x = torch.randn(CHANNELS, L, device=dev, generator=g, dtype=torch.float32) * 0.25
+    t = torch.arange(L, device=dev, dtype=torch.float32) / FS
+    x += 0.5 * torch.sin(2 * np.pi * 440.0 * t) + 0.5 * torch.sin(2 * np.pi * 3000.0 * t)
+    return x
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+
+    import nx_signal_b200 as nx
+    from nx_signal_b200 import _arrays as A
+    from nx_signal_b200 import _lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (nx_signal_b200 has no CPU path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+
+    # window: built on rank 0, one NCCL broadcast (the path's only collective)
+    w = torch.from_numpy(nx.windows.hann(NFFT)).to(dev) if rank == 0 else torch.empty(NFFT, device=dev)
+    if dist is not None:
+        dist.broadcast(w, src=0)
+
+    x = make_input(torch, dev, 1002 + rank)
+    z = torch.empty((CHANNELS, M, NFFT), dtype=torch.complex64, device=dev)
+    ctx = _lib.context(local_rank)
+    lib = _lib.lib()
+    stream = torch.cuda.current_stream(dev)
+    sptr = A.stream_of(x)
+
+    def step_dev():
+        rc = lib.nxs_stft_f32_dev(ctx, A.ptr(x), CHANNELS, L, L, A.ptr(w), NFFT, HOP, NFFT, _lib.PAD_VALID, 0, 0,
+                                  _lib.SCALE_NONE, float(FS), A.ptr(z), sptr)
+        _lib.check(rc, ctx, "stft")
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step_dev()
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    _lib.profile(True, local_rank)
+    _lib.profile_read(local_rank)
+    launches0 = _lib.launch_count(local_rank)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.time()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_dev()
+    e1.record(stream)
+    barrier()
+    t1 = time.time()
+    ms = e0.elapsed_time(e1)
+    kern_ms, kern_n = _lib.profile_read(local_rank)
+    _lib.profile(False, local_rank)
+    launches = _lib.launch_count(local_rank) - launches0
+    clocks = sampler.stop(t0, t1)
+    if dist is not None:
+        tms = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    ms_per_step = ms / args.steps
+    value = world * FRAMES_PER_GPU / (ms_per_step * 1e-3)
+
+    # spot parity inside the bench run (oracle = checker only): first frames of channel 0
+    parity = None
+    if rank == 0:
+        from oracle import nxsignal_oracle as o
+
+        nchk = 16
+        xs = x[0, : (nchk - 1) * HOP + NFFT].cpu().numpy()
+        zo, _, _ = o.stft_fast(xs, w.cpu().numpy(), overlap_length=NFFT - HOP, fft_length=NFFT, sampling_rate=FS)
+        got = z[0, :nchk].cpu().numpy()
+        parity = float((np.abs(got - zo).max(-1) / np.abs(zo).max(-1)).max())
+
+    # end to end: the C-ABI host entry on pinned host buffers, H2D + kernels + D2H per step
+    e2e = None
+    try:
+        xh = torch.empty((CHANNELS, L), dtype=torch.float32, pin_memory=True)
+        zh = torch.empty((CHANNELS, M, NFFT), dtype=torch.complex64, pin_memory=True)
+        xh.copy_(x)
+        wh = w.cpu().numpy()
+        del z
+        torch.cuda.empty_cache()
+
+        def step_host():
+            rc = lib.nxs_stft_f32_host(ctx, A.ptr(xh), CHANNELS, L, L, wh.ctypes.data, NFFT, HOP, NFFT,
+                                       _lib.PAD_VALID, 0, 0, _lib.SCALE_NONE, float(FS), A.ptr(zh))
+            _lib.check(rc, ctx, "stft(host)")
+
+        step_host()
+        barrier()
+        te = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            step_host()
+        barrier()
+        e2e_s = (time.perf_counter() - te) / args.e2e_steps
+        if dist is not None:
+            tt = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e_s = float(tt.item())
+        e2e = {"value": world * FRAMES_PER_GPU / e2e_s, "unit": "frames/s",
+               "h2d_bytes_per_step": int(xh.numel() * 4 + NFFT * 4), "d2h_bytes_per_step": int(zh.numel() * 8),
+               "steps": args.e2e_steps, "ms_per_step": 1e3 * e2e_s,
+               "path": "nxs_stft_f32_host on pinned host buffers (wall clock, max over ranks)"}
+        if rank == 0:
+            got = zh[0, :16].numpy()
+            e2e["parity"] = float((np.abs(got - zo).max(-1) / np.abs(zo).max(-1)).max())
+    except Exception as ex:  # report, never fake
+        e2e = {"value": None, "unit": "frames/s", "error": repr(ex)[:200]}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = peaks()
+    kern_avg_ms = kern_ms / max(kern_n, 1)
+    achieved = ALGO_BYTES / (kern_avg_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("stft_r2c_1024_bytes_per_launch")
+        except Exception:
+            traffic = None
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        r, cores, sample = cpu_port_rate(12.0)
+        cpu = {"value": r, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample,
+               "note": "oracle/nxs_oracle.c: Nx.BinaryBackend's f64 recursive radix-2 restated in C + OpenMP; "
+                       "the real BEAM backend cannot run here and is far slower"}
+    line = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "channels_per_gpu": CHANNELS, "fft_length": NFFT, "hop": HOP,
+                   "l2": "inputs larger than L2 (0.92 GB in, 7.37 GB out per step)", "parity_frame_rel_err": parity},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src, "kernel": "stft_r2c_kernel<Plan<512,64,8,8,8>>",
+                     "kernel_ms": kern_avg_ms, "kernel_launches_timed": kern_n, "algorithmic_bytes": ALGO_BYTES},
+        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

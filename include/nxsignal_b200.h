@@ -15,7 +15,7 @@
  *   - layouts are row-major, native-endian, exactly what Nx.to_binary/1
  *     yields: f32 = float, c64 = interleaved (re, im) float pairs.
  *   - "_dev" entries take DEVICE pointers, enqueue on `stream` (a cudaStream_t
- *     passed as void*, NULL = the context's own stream) and return without
+ *     passed as void*, NULL = CUDA's default stream) and return without
  *     synchronising.  "_host" entries take HOST pointers, stage through pinned
  *     buffers owned by the context, and return when the result is in `out`.
  *   - the caller owns every input/output buffer; the library never keeps a
@@ -76,6 +76,12 @@ const char* nxs_last_error(const nxs_ctx* ctx);
 int nxs_ctx_synchronize(nxs_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t nxs_ctx_launch_count(const nxs_ctx* ctx);
+
+/* kernel timing for the roofline figure: while enabled, the dominant kernel of every compute
+ * call is bracketed by CUDA events on its launch stream.  nxs_ctx_profile_read waits for
+ * them, returns the summed kernel time and launch count since the last read, and resets. */
+int nxs_ctx_profile(nxs_ctx* ctx, int enable);
+int nxs_ctx_profile_read(nxs_ctx* ctx, double* total_ms, int64_t* launches);
 
 /* ---- host-side closed forms (O(n); no GPU needed) ----------------------- */
 /* NxSignal.Windows.{rectangular,bartlett,triangular,blackman,hamming,hann,kaiser}(n, opts)

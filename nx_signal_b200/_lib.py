@@ -35,6 +35,8 @@ SIGNATURES = {
     "nxs_last_error": (C.c_char_p, [vp]),
     "nxs_ctx_synchronize": (i32, [vp]),
     "nxs_ctx_launch_count": (C.c_uint64, [vp]),
+    "nxs_ctx_profile": (i32, [vp, i32]),
+    "nxs_ctx_profile_read": (i32, [vp, C.POINTER(f64), C.POINTER(i64)]),
     "nxs_window_f32": (i32, [i32, i64, i32, f64, f64, vp]),
     "nxs_firwin_f32": (i32, [i64, C.POINTER(f64), i32, i32, f64, i32, i32, f64, vp]),
     "nxs_fft_frequencies_f32": (i32, [f64, i64, vp]),
@@ -119,6 +121,17 @@ def context(device=0):
 
 def launch_count(device=0):
     return int(lib().nxs_ctx_launch_count(context(device)))
+
+
+def profile(enable, device=0):
+    check(lib().nxs_ctx_profile(context(device), int(bool(enable))))
+
+
+def profile_read(device=0):
+    """(summed dominant-kernel milliseconds, launches) since the last read."""
+    ms, n = f64(), i64()
+    check(lib().nxs_ctx_profile_read(context(device), C.byref(ms), C.byref(n)), context(device))
+    return ms.value, n.value
 
 
 def synchronize(device=0):

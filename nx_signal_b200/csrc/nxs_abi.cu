@@ -35,6 +35,23 @@ static int grow(nxs_ctx* ctx, void** p, size_t* have, size_t need, bool host) {
   return NXS_OK;
 }
 
+void prof_begin(nxs_ctx* ctx, cudaStream_t st) {
+  if (!ctx->prof_enabled) return;
+  if (ctx->prof_used + 2 > ctx->prof_events.size()) {
+    cudaEvent_t a = nullptr, b = nullptr;
+    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+    ctx->prof_events.push_back(a);
+    ctx->prof_events.push_back(b);
+  }
+  cudaEventRecord(ctx->prof_events[ctx->prof_used], st);
+}
+
+void prof_end(nxs_ctx* ctx, cudaStream_t st) {
+  if (!ctx->prof_enabled || ctx->prof_used + 2 > ctx->prof_events.size()) return;
+  cudaEventRecord(ctx->prof_events[ctx->prof_used + 1], st);
+  ctx->prof_used += 2;
+}
+
 int ensure_coef(nxs_ctx* ctx, size_t bytes) {
   void* p = ctx->d_coef;
   int rc = grow(ctx, &p, &ctx->d_coef_bytes, bytes < 4096 ? 4096 : bytes, false);
@@ -73,7 +90,8 @@ int64_t frames_for(int64_t length, int64_t window_length, int64_t stride, const 
   return padded < window_length ? 0 : (padded - window_length) / stride + 1;
 }
 
-static cudaStream_t pick(nxs_ctx* ctx, void* stream) { return stream ? (cudaStream_t)stream : ctx->stream; }
+// _dev entries run on the caller's stream; NULL is CUDA's (legacy) default stream, as everywhere in CUDA
+static cudaStream_t pick(nxs_ctx*, void* stream) { return (cudaStream_t)stream; }
 
 struct DeviceGuard {
   int prev = -1;
@@ -176,6 +194,7 @@ int nxs_ctx_destroy(nxs_ctx* ctx) {
   cudaFree(ctx->d_stage_out);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+  for (auto& e : ctx->prof_events) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
   cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
@@ -192,6 +211,28 @@ int nxs_ctx_synchronize(nxs_ctx* ctx) {
 }
 
 uint64_t nxs_ctx_launch_count(const nxs_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int nxs_ctx_profile(nxs_ctx* ctx, int enable) {
+  if (!ctx) return NXS_EINVAL;
+  ctx->prof_enabled = enable != 0;
+  return NXS_OK;
+}
+
+int nxs_ctx_profile_read(nxs_ctx* ctx, double* total_ms, int64_t* launches) {
+  if (!ctx || !total_ms || !launches) return NXS_EINVAL;
+  DeviceGuard guard(ctx->device);
+  double sum = 0.0;
+  for (size_t i = 0; i + 1 < ctx->prof_used; i += 2) {
+    NXS_CUDA(ctx, cudaEventSynchronize(ctx->prof_events[i + 1]));
+    float ms = 0.f;
+    NXS_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->prof_events[i], ctx->prof_events[i + 1]));
+    sum += ms;
+  }
+  *total_ms = sum;
+  *launches = (int64_t)(ctx->prof_used / 2);
+  ctx->prof_used = 0;
+  return NXS_OK;
+}
 
 // ---- STFT -----------------------------------------------------------------------------------
 static int stft_check(int64_t channels, int64_t length, int64_t x_ld, int64_t frame_length, int64_t hop,

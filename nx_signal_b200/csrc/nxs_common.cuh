@@ -41,6 +41,10 @@ struct nxs_ctx {
   size_t d_stage_out_bytes = 0;
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  // optional per-kernel timing (nxs_ctx_profile)
+  bool prof_enabled = false;
+  std::vector<cudaEvent_t> prof_events;  // start/stop pairs
+  size_t prof_used = 0;
   // twiddle tables keyed by (kind << 32 | N)
   std::unordered_map<uint64_t, nxs::PlanTables> tables;
   std::unordered_map<uint64_t, float2*> dft_tables;  // generic DFT: exp(-2 pi i m / n), m < n
@@ -55,6 +59,8 @@ int set_cuda_error(nxs_ctx* ctx, cudaError_t e, const char* where);
     if (e__ != cudaSuccess) return nxs::set_cuda_error(ctx, e__, #call); \
   } while (0)
 
+void prof_begin(nxs_ctx* ctx, cudaStream_t st);
+void prof_end(nxs_ctx* ctx, cudaStream_t st);
 int ensure_coef(nxs_ctx* ctx, size_t bytes);
 int ensure_scratch(nxs_ctx* ctx, size_t bytes);
 

@@ -165,6 +165,202 @@ __global__ void __launch_bounds__(THREADS) stft_r2c_kernel(const StftArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Staged variant (the hot path): a CTA walks tiles of G consecutive frames of one channel.
+// The contiguous span a tile needs, (G-1)*hop + nfft samples, is brought into shared memory
+// by ONE cp.async.bulk (TMA, 1-D) signalled through an mbarrier, double-buffered so the
+// next tile's span lands while this tile's FFTs run: every input sample crosses HBM/L2 once
+// per tile although nfft/hop frames use it, and no thread ever waits on a global load.
+// Groups synchronise on their own named barrier, so the G frames of a tile drift apart and
+// overlap their FP and shared-memory phases.  Tiles that touch the padding region (or are
+// not 16-byte aligned) take the per-thread load path instead.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+template <int T>
+struct GroupSync {
+  int id;
+  __device__ __forceinline__ void operator()() const {
+    if constexpr (T >= 32) asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(T) : "memory");
+    else __syncwarp();
+  }
+};
+
+template <class PL, int THREADS>
+struct StagedCfg {
+  static constexpr int G = THREADS / PL::T, NFFT = 2 * PL::N;
+  static constexpr int STAGE = NFFT + (G - 1) * (NFFT / 2);  // floats per stage: hop <= nfft/2
+  static constexpr size_t BUF_BYTES = size_t(G) * 2 * PL::BUF * sizeof(cpx);
+  static constexpr size_t WIN_OFF = BUF_BYTES;
+  static constexpr size_t STAGE_OFF = WIN_OFF + size_t(NFFT) * sizeof(float);
+  static constexpr size_t BAR_OFF = STAGE_OFF + 2 * size_t(STAGE) * sizeof(float);
+  static constexpr size_t SMEM = BAR_OFF + 16;
+};
+
+template <class PL, class TW, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) stft_r2c_staged_kernel(const StftArgs a, const int tpc,
+                                                                        const int total_tiles) {
+  using CF = StagedCfg<PL, THREADS>;
+  constexpr int N = PL::N, T = PL::T, P = PL::P, G = CF::G, NFFT = 2 * N;
+  constexpr int R0 = PL::R(0), B0 = P / R0;
+  constexpr int RL = PL::R(PL::NP - 1), BL = P / RL;
+  static_assert(THREADS % T == 0 && P >= 2 && G <= 15, "bad plan");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tid = threadIdx.x, g = tid / T, t = tid % T;
+  cpx* bufA = reinterpret_cast<cpx*>(smem_raw) + (size_t)(2 * g) * PL::BUF;
+  cpx* bufB = bufA + PL::BUF;
+  float* wsm = reinterpret_cast<float*>(smem_raw + CF::WIN_OFF);
+  float* stage0 = reinterpret_cast<float*>(smem_raw + CF::STAGE_OFF);
+  const uint32_t bar0 = smem_u32(smem_raw + CF::BAR_OFF);
+
+  for (int i = tid; i < NFFT; i += THREADS) wsm[i] = a.wprep[i];
+  if (tid == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  TW tw;
+  tw.init(a.tw, t);
+  cpx wpost[P / 2];
+#pragma unroll
+  for (int i = 0; i < P / 2; ++i) wpost[i] = __ldg(a.post + t + i * T);
+  const GroupSync<T> sync{1 + g};
+  const int hop = (int)a.hop;
+
+  // is this tile fully interior (no padding) -> staged through TMA
+  auto tile_geom = [&](int tile, int& c, int& m0, int& gact, int64_t& src0) {
+    c = tile / tpc;
+    m0 = (tile - c * tpc) * G;
+    const int64_t left = a.M - m0;
+    gact = left < G ? (int)left : G;
+    src0 = (int64_t)m0 * hop - a.pad_lo;
+    return src0 >= 0 && src0 + (int64_t)(gact - 1) * hop + NFFT <= a.L;
+  };
+  auto issue = [&](int tile, int stage) {
+    int c, m0, gact;
+    int64_t src0;
+    if (tile_geom(tile, c, m0, gact, src0)) {
+      const uint32_t bytes = (uint32_t)(((gact - 1) * hop + NFFT) * sizeof(float));
+      const uint32_t bar = bar0 + 8 * stage;
+      mbar_expect_tx(bar, bytes);
+      tma_load_1d(smem_u32(stage0 + (size_t)stage * CF::STAGE), a.x + (int64_t)c * a.x_ld + src0, bytes, bar);
+    }
+  };
+
+  uint32_t phase_bits = 0;  // bit s = parity to wait for on stage s
+  int tile = blockIdx.x;
+  if (tile < total_tiles && tid == 0) issue(tile, 0);
+  for (int it = 0; tile < total_tiles; tile += gridDim.x, ++it) {
+    const int stage = it & 1;
+    __syncthreads();  // every thread is done reading stage^1 (tile it-1)
+    if (tid == 0 && tile + (int)gridDim.x < total_tiles) issue(tile + gridDim.x, stage ^ 1);
+
+    int c, m0, gact;
+    int64_t src0;
+    const bool staged = tile_geom(tile, c, m0, gact, src0);
+    const int m = m0 + g;
+    const bool active = g < gact;
+    const int64_t f = (int64_t)c * a.M + m;
+    cpx v[P];
+    if (staged) {
+      mbar_wait(bar0 + 8 * stage, (phase_bits >> stage) & 1);
+      phase_bits ^= (1u << stage);
+      if (active) {
+        const float2* __restrict__ xp =
+            reinterpret_cast<const float2*>(stage0 + (size_t)stage * CF::STAGE + (size_t)g * hop);
+        const float2* __restrict__ wp = reinterpret_cast<const float2*>(wsm);
+#pragma unroll
+        for (int b = 0; b < B0; ++b)
+#pragma unroll
+          for (int q = 0; q < R0; ++q) {
+            const int i = fft_in_index<PL>(t, b, q);
+            const float2 xx = xp[i], ww = wp[i];
+            v[b * R0 + q] = make_float2(xx.x * ww.x, xx.y * ww.y);
+          }
+      } else {
+#pragma unroll
+        for (int i = 0; i < P; ++i) v[i] = make_float2(0.f, 0.f);
+      }
+    } else if (active) {
+      const float* __restrict__ xrow = a.x + (int64_t)c * a.x_ld;
+      const int64_t s0 = src0 + (int64_t)g * hop;
+#pragma unroll
+      for (int b = 0; b < B0; ++b)
+#pragma unroll
+        for (int q = 0; q < R0; ++q) {
+          const int s = 2 * fft_in_index<PL>(t, b, q);
+          const float re = load_padded(xrow, s0 + s, a.L, a.reflect) * wsm[s];
+          const float im = load_padded(xrow, s0 + s + 1, a.L, a.reflect) * wsm[s + 1];
+          v[b * R0 + q] = make_float2(re, im);
+        }
+    } else {
+#pragma unroll
+      for (int i = 0; i < P; ++i) v[i] = make_float2(0.f, 0.f);
+    }
+
+    block_fft<PL>(v, t, bufA, bufB, tw, sync);
+
+    cpx* pb = ((PL::NP - 1) & 1) ? bufB : bufA;
+#pragma unroll
+    for (int b = 0; b < BL; ++b)
+#pragma unroll
+      for (int q = 0; q < RL; ++q) pb[fft_out_index<PL>(t, b, q)] = v[fft_out_reg<PL>(b, q)];
+    sync();
+    if (active) {
+      float2* __restrict__ zf = a.z + f * NFFT;
+#pragma unroll
+      for (int i = 0; i < P / 2; ++i) {
+        const int kk = t + i * T;
+        const cpx A = pb[kk];
+        const cpx Bc = cconj(pb[(N - kk) & (N - 1)]);
+        const cpx E = cadd(A, Bc), O = csub(A, Bc);
+        const cpx Tm = cmul(wpost[i], O);
+        const cpx X0 = cadd(E, Tm), X1 = csub(E, Tm);
+        __stcs(zf + kk, X0);
+        __stcs(zf + N + kk, X1);
+        if (kk > 0) {
+          __stcs(zf + N - kk, cconj(X1));
+          __stcs(zf + NFFT - kk, cconj(X0));
+        } else {
+          const cpx Zh = pb[N / 2];
+          __stcs(zf + N / 2, make_float2(2.f * Zh.x, -2.f * Zh.y));
+          __stcs(zf + N + N / 2, make_float2(2.f * Zh.x, 2.f * Zh.y));
+        }
+      }
+    }
+    if constexpr (PL::NP & 1) {
+      cpx* tmp = bufA;
+      bufA = bufB;
+      bufB = tmp;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // generic path: direct DFT, any fft_length >= 1.  One CTA per frame.
 //   tab[m] = exp(-2 pi i m / nfft) (double-computed), X[k] = sum_s xw[s] * tab[(k*s) mod nfft]
 // ------------------------------------------------------------------------------------------
@@ -271,10 +467,47 @@ static int run_r2c(nxs_ctx* ctx, StftArgs a, cudaStream_t st) {
   int64_t grid = int64_t(ctx->sm_count) * occ;
   if (grid > tiles) grid = tiles;
   if (grid < 1) grid = 1;
+  prof_begin(ctx, st);
   kern<<<(unsigned)grid, THREADS, smem, st>>>(a);
+  prof_end(ctx, st);
   ctx->launches++;
   NXS_CUDA(ctx, cudaGetLastError());
   return NXS_OK;
+}
+
+template <class PL, class TW, int THREADS, int MINB>
+static int run_r2c_staged(nxs_ctx* ctx, StftArgs a, int64_t channels, cudaStream_t st) {
+  using CF = StagedCfg<PL, THREADS>;
+  PlanTables tabs;
+  int rc = get_tables<PL>(ctx, &tabs);
+  if (rc) return rc;
+  a.tw = tabs.tw;
+  a.post = tabs.post;
+  const int64_t tpc = (a.M + CF::G - 1) / CF::G;
+  const int64_t tiles = tpc * channels;
+  auto kern = stft_r2c_staged_kernel<PL, TW, THREADS, MINB>;
+  NXS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF::SMEM));
+  int occ = 1;
+  NXS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, CF::SMEM));
+  if (occ < 1) occ = 1;
+  int64_t grid = int64_t(ctx->sm_count) * occ;
+  if (grid > tiles) grid = tiles;
+  prof_begin(ctx, st);
+  kern<<<(unsigned)grid, THREADS, CF::SMEM, st>>>(a, (int)tpc, (int)tiles);
+  prof_end(ctx, st);
+  ctx->launches++;
+  NXS_CUDA(ctx, cudaGetLastError());
+  return NXS_OK;
+}
+
+// can the staged (TMA) kernel serve this call?  (16-byte alignment of every tile span, hop <= nfft/2)
+template <class PL, int THREADS>
+static bool staged_ok(const StftArgs& a, int64_t channels) {
+  using CF = StagedCfg<PL, THREADS>;
+  const int64_t tiles = ((a.M + CF::G - 1) / CF::G) * channels;
+  return a.nload == CF::NFFT && a.hop % 4 == 0 && a.hop <= CF::NFFT / 2 && a.pad_lo % 4 == 0 && a.x_ld % 4 == 0 &&
+         (reinterpret_cast<uintptr_t>(a.x) & 15) == 0 && tiles < (int64_t(1) << 30) &&
+         CF::SMEM <= 227 * 1024;
 }
 
 int launch_prep_window(nxs_ctx* ctx, const float* window, int64_t n, int64_t nfft, int scaling,
@@ -323,7 +556,11 @@ int launch_stft(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, 
       case 128: return run_r2c<Plan<64, 8, 8, 8>, TwTable<Plan<64, 8, 8, 8>>, 256>(ctx, a, st);
       case 256: return run_r2c<Plan<128, 16, 8, 8, 2>, TwTable<Plan<128, 16, 8, 8, 2>>, 256>(ctx, a, st);
       case 512: return run_r2c<Plan<256, 32, 8, 8, 4>, TwTable<Plan<256, 32, 8, 8, 4>>, 256>(ctx, a, st);
-      case 1024: return run_r2c<Plan<512, 64, 8, 8, 8>, TwRegs<Plan<512, 64, 8, 8, 8>>, 512>(ctx, a, st);
+      case 1024: {
+        using PL = Plan<512, 64, 8, 8, 8>;
+        if (staged_ok<PL, 512>(a, channels)) return run_r2c_staged<PL, TwRegs<PL>, 512, 1>(ctx, a, channels, st);
+        return run_r2c<PL, TwRegs<PL>, 512>(ctx, a, st);
+      }
       case 2048: return run_r2c<Plan<1024, 64, 16, 8, 8>, TwTable<Plan<1024, 64, 16, 8, 8>>, 512>(ctx, a, st);
       case 4096: return run_r2c<Plan<2048, 128, 16, 16, 8>, TwTable<Plan<2048, 128, 16, 16, 8>>, 512>(ctx, a, st);
       case 8192: return run_r2c<Plan<4096, 256, 16, 16, 16>, TwTable<Plan<4096, 256, 16, 16, 16>>, 512>(ctx, a, st);
