@@ -12,6 +12,9 @@
 // Any fft_length that is not a supported power of two falls back to a direct O(n^2)
 // DFT kernel on the GPU (the reference does the same for odd lengths).
 #include <math.h>
+#include <stdlib.h>
+
+#include <type_traits>
 
 #include "nxs_common.cuh"
 #include "nxs_fft.cuh"
@@ -73,7 +76,7 @@ __global__ void __launch_bounds__(THREADS) stft_r2c_kernel(const StftArgs a) {
   constexpr int R0 = PL::R(0), B0 = P / R0;
   constexpr int RL = PL::R(PL::NP - 1), BL = P / RL;
   static_assert(THREADS % T == 0 && P >= 2, "bad plan");
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, g = tid / T, t = tid % T;
   cpx* bufA = reinterpret_cast<cpx*>(smem_raw) + (size_t)(2 * g) * PL::BUF;
   cpx* bufB = bufA + PL::BUF;
@@ -208,21 +211,29 @@ struct GroupSync {
   }
 };
 
-template <class PL, int THREADS>
+// HOPDIV: the stage holds spans for hop <= nfft / HOPDIV; TWREG: twiddles in registers, else a
+// shared-memory copy of the per-pass table.
+template <class PL_, int THREADS_, int HOPDIV_, bool TWREG_>
 struct StagedCfg {
+  using PL = PL_;
+  static constexpr int THREADS = THREADS_, HOPDIV = HOPDIV_;
+  static constexpr bool TWREG = TWREG_;
   static constexpr int G = THREADS / PL::T, NFFT = 2 * PL::N;
-  static constexpr int STAGE = NFFT + (G - 1) * (NFFT / 2);  // floats per stage: hop <= nfft/2
+  static constexpr int STAGE = NFFT + (G - 1) * (NFFT / HOPDIV);  // floats per stage
   static constexpr size_t BUF_BYTES = size_t(G) * 2 * PL::BUF * sizeof(cpx);
   static constexpr size_t WIN_OFF = BUF_BYTES;
   static constexpr size_t STAGE_OFF = WIN_OFF + size_t(NFFT) * sizeof(float);
-  static constexpr size_t BAR_OFF = STAGE_OFF + 2 * size_t(STAGE) * sizeof(float);
+  static constexpr size_t TW_OFF = STAGE_OFF + 2 * size_t(STAGE) * sizeof(float);
+  static constexpr size_t BAR_OFF = TW_OFF + (TWREG ? 0 : size_t(PL::TW_TOTAL) * sizeof(cpx));
   static constexpr size_t SMEM = BAR_OFF + 16;
 };
 
-template <class PL, class TW, int THREADS, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB) stft_r2c_staged_kernel(const StftArgs a, const int tpc,
-                                                                        const int total_tiles) {
-  using CF = StagedCfg<PL, THREADS>;
+template <class CF, int MINB>
+__global__ void __launch_bounds__(CF::THREADS, MINB) stft_r2c_staged_kernel(const StftArgs a, const int tpc,
+                                                                            const int total_tiles) {
+  using PL = typename CF::PL;
+  using TW = typename std::conditional<CF::TWREG, TwRegs<PL>, TwTable<PL>>::type;
+  constexpr int THREADS = CF::THREADS;
   constexpr int N = PL::N, T = PL::T, P = PL::P, G = CF::G, NFFT = 2 * N;
   constexpr int R0 = PL::R(0), B0 = P / R0;
   constexpr int RL = PL::R(PL::NP - 1), BL = P / RL;
@@ -236,6 +247,10 @@ __global__ void __launch_bounds__(THREADS, MINB) stft_r2c_staged_kernel(const St
   const uint32_t bar0 = smem_u32(smem_raw + CF::BAR_OFF);
 
   for (int i = tid; i < NFFT; i += THREADS) wsm[i] = a.wprep[i];
+  if constexpr (!CF::TWREG) {
+    cpx* twsm = reinterpret_cast<cpx*>(smem_raw + CF::TW_OFF);
+    for (int i = tid; i < PL::TW_TOTAL; i += THREADS) twsm[i] = a.tw[i];
+  }
   if (tid == 0) {
     mbar_init(bar0, 1);
     mbar_init(bar0 + 8, 1);
@@ -244,7 +259,8 @@ __global__ void __launch_bounds__(THREADS, MINB) stft_r2c_staged_kernel(const St
   __syncthreads();
 
   TW tw;
-  tw.init(a.tw, t);
+  if constexpr (CF::TWREG) tw.init(a.tw, t);
+  else tw.init(reinterpret_cast<const cpx*>(smem_raw + CF::TW_OFF), t);
   cpx wpost[P / 2];
 #pragma unroll
   for (int i = 0; i < P / 2; ++i) wpost[i] = __ldg(a.post + t + i * T);
@@ -475,9 +491,10 @@ static int run_r2c(nxs_ctx* ctx, StftArgs a, cudaStream_t st) {
   return NXS_OK;
 }
 
-template <class PL, class TW, int THREADS, int MINB>
+template <class CF, int MINB>
 static int run_r2c_staged(nxs_ctx* ctx, StftArgs a, int64_t channels, cudaStream_t st) {
-  using CF = StagedCfg<PL, THREADS>;
+  using PL = typename CF::PL;
+  constexpr int THREADS = CF::THREADS;
   PlanTables tabs;
   int rc = get_tables<PL>(ctx, &tabs);
   if (rc) return rc;
@@ -485,7 +502,7 @@ static int run_r2c_staged(nxs_ctx* ctx, StftArgs a, int64_t channels, cudaStream
   a.post = tabs.post;
   const int64_t tpc = (a.M + CF::G - 1) / CF::G;
   const int64_t tiles = tpc * channels;
-  auto kern = stft_r2c_staged_kernel<PL, TW, THREADS, MINB>;
+  auto kern = stft_r2c_staged_kernel<CF, MINB>;
   NXS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF::SMEM));
   int occ = 1;
   NXS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, CF::SMEM));
@@ -501,13 +518,12 @@ static int run_r2c_staged(nxs_ctx* ctx, StftArgs a, int64_t channels, cudaStream
 }
 
 // can the staged (TMA) kernel serve this call?  (16-byte alignment of every tile span, hop <= nfft/2)
-template <class PL, int THREADS>
+template <class CF>
 static bool staged_ok(const StftArgs& a, int64_t channels) {
-  using CF = StagedCfg<PL, THREADS>;
   const int64_t tiles = ((a.M + CF::G - 1) / CF::G) * channels;
-  return a.nload == CF::NFFT && a.hop % 4 == 0 && a.hop <= CF::NFFT / 2 && a.pad_lo % 4 == 0 && a.x_ld % 4 == 0 &&
+  return a.nload == CF::NFFT && a.hop % 4 == 0 && a.hop <= CF::NFFT / CF::HOPDIV && a.pad_lo % 4 == 0 && a.x_ld % 4 == 0 &&
          (reinterpret_cast<uintptr_t>(a.x) & 15) == 0 && tiles < (int64_t(1) << 30) &&
-         CF::SMEM <= 227 * 1024;
+         CF::SMEM <= 231424;
 }
 
 int launch_prep_window(nxs_ctx* ctx, const float* window, int64_t n, int64_t nfft, int scaling,
@@ -551,18 +567,34 @@ int launch_stft(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, 
   if (rc) return rc;
 
   if (fast) {
+    // staged (TMA) configurations first; each falls back to the general kernel when the call
+    // does not meet its alignment / hop conditions
+#define NXS_TRY_STAGED(CF, MINB) \
+  if (staged_ok<CF>(a, channels)) return run_r2c_staged<CF, MINB>(ctx, a, channels, st)
     switch (nfft) {
       case 64: return run_r2c<Plan<32, 4, 8, 4>, TwTable<Plan<32, 4, 8, 4>>, 256>(ctx, a, st);
       case 128: return run_r2c<Plan<64, 8, 8, 8>, TwTable<Plan<64, 8, 8, 8>>, 256>(ctx, a, st);
       case 256: return run_r2c<Plan<128, 16, 8, 8, 2>, TwTable<Plan<128, 16, 8, 8, 2>>, 256>(ctx, a, st);
-      case 512: return run_r2c<Plan<256, 32, 8, 8, 4>, TwTable<Plan<256, 32, 8, 8, 4>>, 256>(ctx, a, st);
+      case 512: {
+        using PL = Plan<256, 32, 8, 8, 4>;
+        { using CF = StagedCfg<PL, 256, 2, true>; NXS_TRY_STAGED(CF, 2); }
+        return run_r2c<PL, TwTable<PL>, 256>(ctx, a, st);
+      }
       case 1024: {
         using PL = Plan<512, 64, 8, 8, 8>;
-        if (staged_ok<PL, 512>(a, channels)) return run_r2c_staged<PL, TwRegs<PL>, 512, 1>(ctx, a, channels, st);
+        { using CF = StagedCfg<PL, 256, 2, true>; NXS_TRY_STAGED(CF, 2); }
         return run_r2c<PL, TwRegs<PL>, 512>(ctx, a, st);
       }
-      case 2048: return run_r2c<Plan<1024, 64, 16, 8, 8>, TwTable<Plan<1024, 64, 16, 8, 8>>, 512>(ctx, a, st);
-      case 4096: return run_r2c<Plan<2048, 128, 16, 16, 8>, TwTable<Plan<2048, 128, 16, 16, 8>>, 512>(ctx, a, st);
+      case 2048: {
+        using PL = Plan<1024, 64, 16, 8, 8>;
+        { using CF = StagedCfg<PL, 512, 2, false>; NXS_TRY_STAGED(CF, 1); }
+        return run_r2c<PL, TwTable<PL>, 512>(ctx, a, st);
+      }
+      case 4096: {
+        using PL = Plan<2048, 128, 16, 16, 8>;
+        { using CF = StagedCfg<PL, 512, 4, false>; NXS_TRY_STAGED(CF, 1); }
+        return run_r2c<PL, TwTable<PL>, 512>(ctx, a, st);
+      }
       case 8192: return run_r2c<Plan<4096, 256, 16, 16, 16>, TwTable<Plan<4096, 256, 16, 16, 16>>, 512>(ctx, a, st);
       case 16384:
         return run_r2c<Plan<8192, 512, 16, 16, 16, 2>, TwTable<Plan<8192, 512, 16, 16, 16, 2>>, 512>(ctx, a, st);
