@@ -1,0 +1,255 @@
+// nxs_fir.cu -- FIR filtering by overlap-save FFT convolution for sm_100a.
+//
+// Replaces NxSignal.Convolution.convolve(x, taps, mode:, method:) for the batched-FIR form
+// x {C, L} * h {1, K} (lib/nx_signal/convolution.ex:38-58; direct :95-211, fft :252-329).  The
+// reference's :fft method transforms the whole row at length L + K - 1 (:260-284); here the
+// row is cut into blocks of V = F - K + 1 outputs and each block is circularly convolved at a
+// fixed power-of-two F (overlap-save), which yields the same linear-convolution values.
+//
+// Two consecutive blocks of a channel ride one complex FFT: z = blk0 + i*blk1, Y = FFT(z) * H,
+// y = IFFT(Y); because h is real, Re(y) is blk0's result and Im(y) blk1's -- no split pass.
+// The plans are palindromic (first radix == last radix), so the forward transform's output
+// registers are exactly the inverse transform's input registers: forward FFT, multiply by
+// H / F, inverse FFT (re/im swap identity) and the store all happen without leaving the
+// register file except for the in-FFT exchanges.  `mode` only shifts the output window:
+// full 0, same (K-1)/2, valid min(L,K)-1 (convolution.ex:300-329).
+#include <math.h>
+
+#include "nxs_common.cuh"
+#include "nxs_fft.cuh"
+
+namespace nxs {
+
+struct FirArgs {
+  const float* x;
+  int64_t L, x_ld;
+  float* y;
+  int64_t out_len, y_ld;
+  int64_t start;  // y[o] = full[o + start]
+  int K;
+  int V;  // valid outputs per block = F - K + 1
+  int64_t b_lo;
+  int pairs_per_channel;
+  int total_tiles;
+  const float2* H;  // [F], already divided by F
+  const float2* tw;
+};
+
+// H[k] = (1/F) sum_j h[j] exp(-2 pi i j k / F), accumulated in double
+__global__ void __launch_bounds__(256) fir_spectrum_kernel(const float* __restrict__ taps, int K, int F,
+                                                           float2* __restrict__ H) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= F) return;
+  double re = 0.0, im = 0.0;
+  for (int j = 0; j < K; ++j) {
+    const int r = (int)(((int64_t)j * k) % F);
+    double s, c;
+    sincospi(-2.0 * (double)r / (double)F, &s, &c);
+    const double h = (double)taps[j];
+    re += h * c;
+    im += h * s;
+  }
+  H[k] = make_float2((float)(re / F), (float)(im / F));
+}
+
+template <class PL, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) fir_ols_kernel(const FirArgs a) {
+  constexpr int F = PL::N, T = PL::T, P = PL::P, G = THREADS / T;
+  constexpr int R0 = PL::R(0), B0 = P / R0;
+  constexpr int RL = PL::R(PL::NP - 1);
+  static_assert(R0 == RL, "FIR plans must be palindromic (first radix == last radix)");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tid = threadIdx.x, g = tid / T, t = tid % T;
+  cpx* const bufA = reinterpret_cast<cpx*>(smem_raw) + (size_t)(2 * g) * PL::BUF;
+  cpx* const bufB = bufA + PL::BUF;
+  cpx* twsm = reinterpret_cast<cpx*>(smem_raw + size_t(G) * 2 * PL::BUF * sizeof(cpx));
+  for (int i = tid; i < PL::TW_TOTAL; i += THREADS) twsm[i] = a.tw[i];
+  __syncthreads();
+  TwTable<PL> tw;
+  tw.init(twsm, t);
+  const SyncBlock sync;
+  const int K1 = a.K - 1;
+
+  const int iters = (a.total_tiles + G - 1) / G;
+  for (int it = blockIdx.x; it < iters; it += gridDim.x) {
+    const int tile = it * G + g;
+    const bool active = tile < a.total_tiles;
+    int c = 0, pi = 0;
+    if (active) {
+      c = tile / a.pairs_per_channel;
+      pi = tile - c * a.pairs_per_channel;
+    }
+    const float* __restrict__ xrow = a.x + (int64_t)c * a.x_ld;
+    const int64_t n0 = (a.b_lo + 2 * (int64_t)pi) * a.V;  // first full-convolution index of block 0
+    const int64_t s0 = n0 - K1, s1 = s0 + a.V;           // input segment starts of the two blocks
+    cpx v[P];
+#pragma unroll
+    for (int b = 0; b < B0; ++b)
+#pragma unroll
+      for (int q = 0; q < R0; ++q) {
+        const int i = fft_in_index<PL>(t, b, q);
+        float re = 0.f, im = 0.f;
+        if (active) {
+          const int64_t i0 = s0 + i, i1 = s1 + i;
+          if (i0 >= 0 && i0 < a.L) re = __ldg(xrow + i0);
+          if (i1 >= 0 && i1 < a.L) im = __ldg(xrow + i1);
+        }
+        v[b * R0 + q] = make_float2(re, im);
+      }
+    __syncthreads();  // the previous iteration's exchange reads are complete
+    block_fft<PL>(v, t, bufA, bufB, tw, sync);
+    // pointwise multiply by H / F; palindromic plan: output register (b, q) is input register (b, q)
+    cpx u[P];
+#pragma unroll
+    for (int b = 0; b < B0; ++b)
+#pragma unroll
+      for (int q = 0; q < R0; ++q) {
+        const int k = fft_out_index<PL>(t, b, q);
+        const cpx yk = cmul(v[fft_out_reg<PL>(b, q)], __ldg(a.H + k));
+        u[b * R0 + q] = make_float2(yk.y, yk.x);  // swap for the inverse transform
+      }
+    __syncthreads();  // forward exchanges fully consumed before the inverse reuses the buffers
+    block_fft<PL>(u, t, bufA, bufB, tw, sync);
+    if (active) {
+      float* __restrict__ yrow = a.y + (int64_t)c * a.y_ld;
+#pragma unroll
+      for (int b = 0; b < B0; ++b)
+#pragma unroll
+        for (int q = 0; q < R0; ++q) {
+          const int i = fft_out_index<PL>(t, b, q);
+          if (i >= K1) {
+            const cpx r = u[fft_out_reg<PL>(b, q)];
+            const int64_t o0 = n0 + (i - K1) - a.start, o1 = o0 + a.V;
+            if (o0 >= 0 && o0 < a.out_len) __stcs(yrow + o0, r.y);  // Re(y): block 0
+            if (o1 >= 0 && o1 < a.out_len) __stcs(yrow + o1, r.x);  // Im(y): block 1
+          }
+        }
+    }
+  }
+}
+
+template <class PL>
+static int fir_tw_table(nxs_ctx* ctx, float2** out) {
+  const uint64_t key = (uint64_t(PL::N) << 32) | (uint64_t(PL::T) << 8) | uint64_t(PL::NP) | (uint64_t(2) << 62) |
+                       (uint64_t(PL::R(0)) << 20);
+  auto it = ctx->tables.find(key);
+  if (it != ctx->tables.end()) {
+    *out = it->second.tw;
+    return NXS_OK;
+  }
+  std::vector<float2> tw(PL::TW_TOTAL > 0 ? PL::TW_TOTAL : 1);
+  for (int p = 1; p < PL::NP; ++p) {
+    const int R = PL::R(p), NS = PL::NS(p);
+    for (int q = 1; q < R; ++q)
+      for (int k = 0; k < NS; ++k) {
+        const double ang = -2.0 * M_PI * double(q) * double(k) / double(NS * R);
+        tw[PL::twOffset(p) + (q - 1) * NS + k] = make_float2((float)cos(ang), (float)sin(ang));
+      }
+  }
+  PlanTables t;
+  NXS_CUDA(ctx, cudaMalloc(&t.tw, tw.size() * sizeof(float2)));
+  NXS_CUDA(ctx, cudaMemcpy(t.tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+  ctx->tables[key] = t;
+  *out = t.tw;
+  return NXS_OK;
+}
+
+template <class PL, int THREADS, int MINB>
+static int run_fir(nxs_ctx* ctx, FirArgs a, int64_t channels, const float* taps, cudaStream_t st) {
+  constexpr int F = PL::N, G = THREADS / PL::T;
+  float2* tw = nullptr;
+  int rc = fir_tw_table<PL>(ctx, &tw);
+  if (rc) return rc;
+  a.tw = tw;
+  rc = ensure_scratch(ctx, size_t(F) * sizeof(float2));
+  if (rc) return rc;
+  fir_spectrum_kernel<<<(F + 255) / 256, 256, 0, st>>>(taps, a.K, F, (float2*)ctx->d_scratch);
+  ctx->launches++;
+  NXS_CUDA(ctx, cudaGetLastError());
+  a.H = (const float2*)ctx->d_scratch;
+  a.V = F - a.K + 1;
+  a.b_lo = a.start / a.V;
+  const int64_t b_hi = (a.start + a.out_len - 1) / a.V;
+  const int64_t nblocks = b_hi - a.b_lo + 1;
+  const int64_t pairs = (nblocks + 1) / 2;
+  const int64_t tiles = pairs * channels;
+  if (tiles >= (int64_t(1) << 31)) return NXS_EUNSUPPORTED;
+  a.pairs_per_channel = (int)pairs;
+  a.total_tiles = (int)tiles;
+  const size_t smem = size_t(G) * 2 * PL::BUF * sizeof(cpx) + size_t(PL::TW_TOTAL) * sizeof(cpx);
+  auto kern = fir_ols_kernel<PL, THREADS, MINB>;
+  NXS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 1;
+  NXS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
+  if (occ < 1) occ = 1;
+  const int64_t iters = (tiles + G - 1) / G;
+  int64_t grid = int64_t(ctx->sm_count) * occ;
+  if (grid > iters) grid = iters;
+  prof_begin(ctx, st);
+  kern<<<(unsigned)grid, THREADS, smem, st>>>(a);
+  prof_end(ctx, st);
+  ctx->launches++;
+  NXS_CUDA(ctx, cudaGetLastError());
+  return NXS_OK;
+}
+
+// short filters / very long filters: direct summation, one thread per output (fp32 FMA chain in
+// ascending tap order)
+__global__ void __launch_bounds__(256) fir_direct_kernel(const float* __restrict__ x, int64_t channels, int64_t L,
+                                                         int64_t x_ld, const float* __restrict__ taps, int K,
+                                                         int64_t start, int64_t out_len, int64_t y_ld,
+                                                         float* __restrict__ y) {
+  const int64_t total = channels * out_len;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t o = i % out_len, c = i / out_len;
+    const int64_t n = o + start;
+    const float* __restrict__ xr = x + c * x_ld;
+    int64_t k_lo = n - (L - 1);
+    if (k_lo < 0) k_lo = 0;
+    int64_t k_hi = n < K - 1 ? n : K - 1;
+    float acc = 0.f;
+    for (int64_t k = k_lo; k <= k_hi; ++k) acc = fmaf(__ldg(taps + k), __ldg(xr + (n - k)), acc);
+    y[c * y_ld + o] = acc;
+  }
+}
+
+int launch_fir(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, int64_t x_ld, const float* taps,
+               int64_t num_taps, int mode, float* y, int64_t y_ld, cudaStream_t st) {
+  if (channels <= 0) return NXS_OK;
+  int64_t out_len = 0;
+  int rc = nxs_fir_out_len(length, num_taps, mode, &out_len);
+  if (rc) return rc;
+  FirArgs a;
+  a.x = x;
+  a.L = length;
+  a.x_ld = x_ld;
+  a.y = y;
+  a.out_len = out_len;
+  a.y_ld = y_ld;
+  a.K = (int)num_taps;
+  a.start = mode == NXS_MODE_FULL ? 0
+            : mode == NXS_MODE_SAME ? (num_taps - 1) / 2
+                                    : (length < num_taps ? length : num_taps) - 1;
+  a.V = 0;
+  a.b_lo = 0;
+  a.pairs_per_channel = a.total_tiles = 0;
+  a.H = nullptr;
+  a.tw = nullptr;
+  const int64_t K = num_taps;
+  if (K >= 16 && K <= 129) return run_fir<Plan<256, 16, 16, 16>, 256, 2>(ctx, a, channels, taps, st);
+  if (K > 129 && K <= 513) return run_fir<Plan<1024, 64, 8, 16, 8>, 256, 2>(ctx, a, channels, taps, st);
+  if (K > 513 && K <= 3585) return run_fir<Plan<4096, 256, 16, 16, 16>, 256, 2>(ctx, a, channels, taps, st);
+  // K < 16 or K > 3585: direct
+  if (K > (int64_t(1) << 30)) return NXS_EUNSUPPORTED;
+  const int64_t total = channels * out_len;
+  int64_t grid = (total + 255) / 256;
+  if (grid > int64_t(ctx->sm_count) * 16) grid = int64_t(ctx->sm_count) * 16;
+  prof_begin(ctx, st);
+  fir_direct_kernel<<<(unsigned)grid, 256, 0, st>>>(x, channels, length, x_ld, taps, (int)K, a.start, out_len, y_ld, y);
+  prof_end(ctx, st);
+  ctx->launches++;
+  NXS_CUDA(ctx, cudaGetLastError());
+  return NXS_OK;
+}
+
+}  // namespace nxs

@@ -1,0 +1,448 @@
+// nxs_istft.cu -- fused inverse STFT for sm_100a.
+//
+// Replaces NxSignal.istft/3 (lib/nx_signal.ex:582-638): Nx.ifft(length:) (:609) -> rescale
+// (:611-625) -> * window (:628) -> overlap_and_add (:627-628, :684-735) -> divide by the
+// overlap-added |window|^2 with the `> 1e-10 else 1` guard (:630-637), returning c64.
+//
+// A CTA owns a segment of consecutive frames of one channel and walks it in batches of G
+// frames.  Each group of T threads inverse-transforms one frame (full complex FFT through the
+// re/im swap identity), multiplies by the prepared window w * S / nfft and leaves the frame in
+// shared memory; then the whole CTA gathers the batch's overlap-add: every output sample sums
+// its covering frames in ascending frame order plus a carry kept in shared memory from the
+// previous batch, so there are no atomics and the result is deterministic.  The normaliser is
+// accumulated the same way from |w|^2, which reproduces the reference's edge behaviour (fewer
+// covering frames at both ends) exactly.  Segments after the first recompute the few frames
+// that overlap their start (warm-up batches) instead of exchanging partial sums.
+#include <math.h>
+
+#include <type_traits>
+
+#include "nxs_common.cuh"
+#include "nxs_fft.cuh"
+
+namespace nxs {
+
+int launch_prep_window(nxs_ctx* ctx, const float* window, int64_t n, int64_t nfft, int scaling,
+                       double sampling_rate, float prescale, int invert, float* out, cudaStream_t st);
+int get_dft_table(nxs_ctx* ctx, int64_t n, int sign, float2** out);
+
+struct IstftArgs {
+  const float2* z;  // [C][M][z_len]
+  int64_t M, z_len;
+  const float* wprep;  // [nfft] = w * S / nfft
+  const float* w;      // [nfft] raw window (for |w|^2)
+  float2* y;           // [C][M*hop + nfft - hop]
+  int64_t out_len;
+  int hop;
+  int seg_frames;  // frames per segment (multiple of G)
+  int segs_per_channel;
+  int total_segs;
+  int warm_batches;  // batches recomputed before a segment that does not start at frame 0
+  const float2* tw;
+};
+
+template <class PL, int THREADS>
+struct IstftCfg {
+  static constexpr int G = THREADS / PL::T, NFFT = PL::N;
+  static constexpr size_t BUF_BYTES = size_t(G) * 2 * PL::BUF * sizeof(cpx);
+  static constexpr size_t WIN_OFF = BUF_BYTES;                              // w' [NFFT]
+  static constexpr size_t W2_OFF = WIN_OFF + size_t(NFFT) * sizeof(float);  // |w|^2 [NFFT]
+  static constexpr size_t CARRY_OFF = W2_OFF + size_t(NFFT) * sizeof(float);
+  // carry: 2 x (NFFT complex + NFFT float) (OV <= NFFT - 1 entries used)
+  static constexpr size_t CARRY_ONE = size_t(NFFT) * (sizeof(cpx) + sizeof(float));
+  static constexpr size_t TW_OFF = CARRY_OFF + 2 * CARRY_ONE;
+  static constexpr size_t SMEM = TW_OFF + size_t(PL::TW_TOTAL) * sizeof(cpx) + 16;
+};
+
+template <class PL, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) istft_kernel(const IstftArgs a) {
+  using CF = IstftCfg<PL, THREADS>;
+  constexpr int N = PL::N, T = PL::T, P = PL::P, G = CF::G;
+  constexpr int R0 = PL::R(0), B0 = P / R0;
+  constexpr int RL = PL::R(PL::NP - 1), BL = P / RL;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tid = threadIdx.x, g = tid / T, t = tid % T;
+  cpx* const buf_base = reinterpret_cast<cpx*>(smem_raw);
+  cpx* const bufA = buf_base + (size_t)(2 * g) * PL::BUF;
+  cpx* const bufB = bufA + PL::BUF;
+  float* wsm = reinterpret_cast<float*>(smem_raw + CF::WIN_OFF);
+  float* w2sm = reinterpret_cast<float*>(smem_raw + CF::W2_OFF);
+  cpx* twsm = reinterpret_cast<cpx*>(smem_raw + CF::TW_OFF);
+
+  for (int i = tid; i < N; i += THREADS) {
+    wsm[i] = a.wprep[i];
+    const float w = a.w[i];
+    w2sm[i] = (float)((double)fabsf(w) * (double)fabsf(w));  // Nx.abs(window) ** 2, f32
+  }
+  for (int i = tid; i < PL::TW_TOTAL; i += THREADS) twsm[i] = a.tw[i];
+  __syncthreads();
+  TwTable<PL> tw;
+  tw.init(twsm, t);
+  const SyncBlock sync;
+
+  const int hop = a.hop;
+  const int OV = N - hop;
+  const int span = (G - 1) * hop + N;
+
+  for (int seg = blockIdx.x; seg < a.total_segs; seg += gridDim.x) {
+    const int c = seg / a.segs_per_channel;
+    const int si = seg - c * a.segs_per_channel;
+    const int64_t ms = (int64_t)si * a.seg_frames;
+    int64_t me = ms + a.seg_frames;
+    if (me > a.M) me = a.M;
+    int64_t mb = ms - (int64_t)a.warm_batches * G;
+    if (mb < 0) mb = 0;
+    const float2* __restrict__ zc = a.z + (int64_t)c * a.M * a.z_len;
+    float2* __restrict__ yc = a.y + (int64_t)c * a.out_len;
+
+    int cur = 0;  // carry buffer in use
+    {
+      cpx* cc = reinterpret_cast<cpx*>(smem_raw + CF::CARRY_OFF);
+      float* cn = reinterpret_cast<float*>(smem_raw + CF::CARRY_OFF + size_t(N) * sizeof(cpx));
+      for (int i = tid; i < N; i += THREADS) {
+        cc[i] = make_float2(0.f, 0.f);
+        cn[i] = 0.f;
+      }
+    }
+    __syncthreads();
+
+    for (int64_t m0 = mb; m0 < me; m0 += G) {
+      const int64_t m = m0 + g;
+      const bool active = m < me;  // frames beyond this segment belong to the next one
+      cpx v[P];
+      if (active) {
+        const float2* __restrict__ zf = zc + m * a.z_len;
+#pragma unroll
+        for (int b = 0; b < B0; ++b)
+#pragma unroll
+          for (int q = 0; q < R0; ++q) {
+            const int i = fft_in_index<PL>(t, b, q);
+            float2 val = make_float2(0.f, 0.f);
+            if (i < a.z_len) val = __ldg(zf + i);
+            v[b * R0 + q] = make_float2(val.y, val.x);  // swap: ifft(x) = swap(fft(swap(x))) / n
+          }
+      } else {
+#pragma unroll
+        for (int i = 0; i < P; ++i) v[i] = make_float2(0.f, 0.f);
+      }
+      block_fft<PL>(v, t, bufA, bufB, tw, sync);
+      // windowed time-domain frame -> this group's frame buffer (unpadded)
+      cpx* fb = ((PL::NP - 1) & 1) ? bufB : bufA;
+#pragma unroll
+      for (int b = 0; b < BL; ++b)
+#pragma unroll
+        for (int q = 0; q < RL; ++q) {
+          const int n = fft_out_index<PL>(t, b, q);
+          const cpx r = v[fft_out_reg<PL>(b, q)];
+          const float w = wsm[n];
+          fb[n] = make_float2(r.y * w, r.x * w);
+        }
+      __syncthreads();
+
+      // gather overlap-add of this batch
+      int64_t gl = me - m0;  // active frames in this batch
+      const int gact = gl < G ? (int)gl : G;
+      const bool last = (m0 + G >= me) && (me == a.M);  // flush the tail of the channel
+      const bool emit = m0 >= ms;                       // warm-up batches only build the carry
+      const cpx* cold = reinterpret_cast<const cpx*>(smem_raw + CF::CARRY_OFF + size_t(cur) * CF::CARRY_ONE);
+      const float* nold = reinterpret_cast<const float*>(smem_raw + CF::CARRY_OFF + size_t(cur) * CF::CARRY_ONE +
+                                                         size_t(N) * sizeof(cpx));
+      cpx* cnew = reinterpret_cast<cpx*>(smem_raw + CF::CARRY_OFF + size_t(cur ^ 1) * CF::CARRY_ONE);
+      float* nnew = reinterpret_cast<float*>(smem_raw + CF::CARRY_OFF + size_t(cur ^ 1) * CF::CARRY_ONE +
+                                             size_t(N) * sizeof(cpx));
+      const int done = gact * hop;  // positions completed by this batch
+      const int64_t pos0 = m0 * hop;
+      const int fb_rel = ((PL::NP - 1) & 1) ? PL::BUF : 0;  // every group keeps its frame at the same offset
+      const int emit_end = !emit ? 0 : (last ? done + OV : done);
+      for (int j = tid; j < span; j += THREADS) {
+        float re = 0.f, im = 0.f, nr = 0.f;
+        if (j < OV) {
+          const cpx cv = cold[j];
+          re = cv.x;
+          im = cv.y;
+          nr = nold[j];
+        }
+        const int g_lo = j - N + 1 <= 0 ? 0 : (j - N + hop) / hop;
+        int g_hi = j / hop;
+        if (g_hi > gact - 1) g_hi = gact - 1;
+        for (int gg = g_lo; gg <= g_hi; ++gg) {
+          const int n = j - gg * hop;
+          const cpx fv = buf_base[(size_t)(2 * gg) * PL::BUF + fb_rel + n];
+          re += fv.x;
+          im += fv.y;
+          nr += w2sm[n];
+        }
+        if (j < emit_end) {
+          const float d = nr > 1.0e-10f ? nr : 1.0f;  // select(norm > 1e-10, norm, 1.0)
+          yc[pos0 + j] = make_float2(re / d, im / d);
+        }
+        if (j >= done && j < done + OV) {
+          cnew[j - done] = make_float2(re, im);
+          nnew[j - done] = nr;
+        }
+      }
+      cur ^= 1;
+      __syncthreads();  // frame buffers and the old carry are free again
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// large fft_length (shared memory cannot hold frames + carry): inverse-transform frames with the
+// same engine into a scratch frame tensor; istft_ola_norm_kernel finishes.
+// ------------------------------------------------------------------------------------------
+template <class PL, int THREADS>
+__global__ void __launch_bounds__(THREADS) ifft_frames_kernel(const float2* __restrict__ z, int64_t total_frames,
+                                                              int64_t z_len, const float* __restrict__ wprep,
+                                                              const float2* __restrict__ twg,
+                                                              float2* __restrict__ frames) {
+  constexpr int N = PL::N, T = PL::T, P = PL::P, G = THREADS / T;
+  constexpr int R0 = PL::R(0), B0 = P / R0;
+  constexpr int RL = PL::R(PL::NP - 1), BL = P / RL;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tid = threadIdx.x, g = tid / T, t = tid % T;
+  cpx* const bufA = reinterpret_cast<cpx*>(smem_raw) + (size_t)(2 * g) * PL::BUF;
+  cpx* const bufB = bufA + PL::BUF;
+  TwTable<PL> tw;
+  tw.init(twg, t);
+  const SyncBlock sync;
+  const int64_t tiles = (total_frames + G - 1) / G;
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int64_t f = tile * G + g;
+    const bool active = f < total_frames;
+    cpx v[P];
+#pragma unroll
+    for (int b = 0; b < B0; ++b)
+#pragma unroll
+      for (int q = 0; q < R0; ++q) {
+        const int i = fft_in_index<PL>(t, b, q);
+        float2 val = make_float2(0.f, 0.f);
+        if (active && i < z_len) val = __ldg(z + f * z_len + i);
+        v[b * R0 + q] = make_float2(val.y, val.x);
+      }
+    __syncthreads();  // previous tile's exchange reads are complete
+    block_fft<PL>(v, t, bufA, bufB, tw, sync);
+    if (active) {
+#pragma unroll
+      for (int b = 0; b < BL; ++b)
+#pragma unroll
+        for (int q = 0; q < RL; ++q) {
+          const int n = fft_out_index<PL>(t, b, q);
+          const cpx r = v[fft_out_reg<PL>(b, q)];
+          const float w = __ldg(wprep + n);
+          frames[f * N + n] = make_float2(r.y * w, r.x * w);
+        }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// generic path (any fft_length): direct inverse DFT of every frame into a scratch frame
+// tensor, then a gather overlap-add + normalise kernel.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) istft_dft_frames_kernel(const float2* __restrict__ z, int64_t total_frames,
+                                                               int z_len, int nfft, const float* __restrict__ wprep,
+                                                               const float2* __restrict__ tab,
+                                                               float2* __restrict__ frames) {
+  extern __shared__ float2 zs[];
+  const int nin = z_len < nfft ? z_len : nfft;
+  for (int64_t f = blockIdx.x; f < total_frames; f += gridDim.x) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < nin; i += blockDim.x) zs[i] = z[f * z_len + i];
+    __syncthreads();
+    for (int n = threadIdx.x; n < nfft; n += blockDim.x) {
+      float re = 0.f, im = 0.f;
+      int idx = 0;
+      for (int k = 0; k < nin; ++k) {
+        const float2 w = __ldg(tab + idx);  // exp(+2 pi i k n / nfft)
+        const float2 x = zs[k];
+        re += x.x * w.x - x.y * w.y;
+        im += x.x * w.y + x.y * w.x;
+        idx += n;
+        if (idx >= nfft) idx -= nfft;
+      }
+      const float w = wprep[n];
+      frames[f * nfft + n] = make_float2(re * w, im * w);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) istft_ola_norm_kernel(const float2* __restrict__ frames, int64_t channels,
+                                                             int64_t M, int nfft, int hop, int64_t out_len,
+                                                             const float* __restrict__ w, float2* __restrict__ y) {
+  const int64_t total = channels * out_len;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = i % out_len, c = i / out_len;
+    int64_t m_hi = n / hop;
+    if (m_hi > M - 1) m_hi = M - 1;
+    const int64_t m_lo = n - nfft + 1 <= 0 ? 0 : (n - nfft + hop) / hop;
+    float re = 0.f, im = 0.f, nr = 0.f;
+    for (int64_t m = m_lo; m <= m_hi; ++m) {
+      const int k = (int)(n - m * hop);
+      const float2 v = frames[(c * M + m) * nfft + k];
+      re += v.x;
+      im += v.y;
+      const float a = fabsf(w[k]);
+      nr += (float)((double)a * (double)a);
+    }
+    const float d = nr > 1.0e-10f ? nr : 1.0f;
+    y[i] = make_float2(re / d, im / d);
+  }
+}
+
+template <class PL>
+static int get_tw_table(nxs_ctx* ctx, float2** out) {
+  const uint64_t key = (uint64_t(PL::N) << 32) | (uint64_t(PL::T) << 8) | uint64_t(PL::NP) | (uint64_t(1) << 62);
+  auto it = ctx->tables.find(key);
+  if (it != ctx->tables.end()) {
+    *out = it->second.tw;
+    return NXS_OK;
+  }
+  std::vector<float2> tw(PL::TW_TOTAL > 0 ? PL::TW_TOTAL : 1);
+  for (int p = 1; p < PL::NP; ++p) {
+    const int R = PL::R(p), NS = PL::NS(p);
+    for (int q = 1; q < R; ++q)
+      for (int k = 0; k < NS; ++k) {
+        const double ang = -2.0 * M_PI * double(q) * double(k) / double(NS * R);
+        tw[PL::twOffset(p) + (q - 1) * NS + k] = make_float2((float)cos(ang), (float)sin(ang));
+      }
+  }
+  PlanTables t;
+  NXS_CUDA(ctx, cudaMalloc(&t.tw, tw.size() * sizeof(float2)));
+  NXS_CUDA(ctx, cudaMemcpy(t.tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+  ctx->tables[key] = t;
+  *out = t.tw;
+  return NXS_OK;
+}
+
+template <class PL, int THREADS, int MINB>
+static int run_istft(nxs_ctx* ctx, IstftArgs a, int64_t channels, cudaStream_t st) {
+  using CF = IstftCfg<PL, THREADS>;
+  float2* tw = nullptr;
+  int rc = get_tw_table<PL>(ctx, &tw);
+  if (rc) return rc;
+  a.tw = tw;
+  const int G = CF::G;
+  const int OV = PL::N - a.hop;
+  const int warm_frames = (OV + a.hop - 1) / a.hop;
+  a.warm_batches = (warm_frames + G - 1) / G;
+  int64_t seg = 256;
+  if (seg < int64_t(8) * a.warm_batches * G) seg = int64_t(8) * a.warm_batches * G;
+  seg = (seg + G - 1) / G * G;
+  if (seg > a.M) seg = (a.M + G - 1) / G * G;
+  a.seg_frames = (int)seg;
+  a.segs_per_channel = (int)((a.M + seg - 1) / seg);
+  const int64_t total = int64_t(a.segs_per_channel) * channels;
+  if (total >= (int64_t(1) << 31)) return NXS_EUNSUPPORTED;
+  a.total_segs = (int)total;
+  auto kern = istft_kernel<PL, THREADS, MINB>;
+  if (CF::SMEM > 231424) return NXS_EUNSUPPORTED;
+  NXS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF::SMEM));
+  int occ = 1;
+  NXS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, CF::SMEM));
+  if (occ < 1) occ = 1;
+  int64_t grid = int64_t(ctx->sm_count) * occ;
+  if (grid > total) grid = total;
+  prof_begin(ctx, st);
+  kern<<<(unsigned)grid, THREADS, CF::SMEM, st>>>(a);
+  prof_end(ctx, st);
+  ctx->launches++;
+  NXS_CUDA(ctx, cudaGetLastError());
+  return NXS_OK;
+}
+
+static int run_ola_norm(nxs_ctx* ctx, const float2* frames, int64_t channels, int64_t M, int64_t nfft, int64_t hop,
+                        int64_t out_len, const float* window, float2* y, cudaStream_t st) {
+  const int64_t total = channels * out_len;
+  int64_t grid = (total + 255) / 256;
+  if (grid > int64_t(ctx->sm_count) * 16) grid = int64_t(ctx->sm_count) * 16;
+  istft_ola_norm_kernel<<<(unsigned)grid, 256, 0, st>>>(frames, channels, M, (int)nfft, (int)hop, out_len, window, y);
+  ctx->launches++;
+  NXS_CUDA(ctx, cudaGetLastError());
+  return NXS_OK;
+}
+
+template <class PL, int THREADS>
+static int run_istft_two_kernels(nxs_ctx* ctx, const IstftArgs& a, int64_t channels, cudaStream_t st) {
+  float2* tw = nullptr;
+  int rc = get_tw_table<PL>(ctx, &tw);
+  if (rc) return rc;
+  const int64_t total_frames = channels * a.M;
+  rc = ensure_scratch(ctx, size_t(total_frames) * PL::N * sizeof(float2));
+  if (rc) return rc;
+  constexpr int G = THREADS / PL::T;
+  const size_t smem = size_t(G) * 2 * PL::BUF * sizeof(cpx);
+  auto kern = ifft_frames_kernel<PL, THREADS>;
+  NXS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t tiles = (total_frames + G - 1) / G;
+  int64_t grid = tiles < int64_t(ctx->sm_count) ? tiles : int64_t(ctx->sm_count);
+  prof_begin(ctx, st);
+  kern<<<(unsigned)grid, THREADS, smem, st>>>(a.z, total_frames, a.z_len, a.wprep, tw, (float2*)ctx->d_scratch);
+  prof_end(ctx, st);
+  ctx->launches++;
+  NXS_CUDA(ctx, cudaGetLastError());
+  return run_ola_norm(ctx, (const float2*)ctx->d_scratch, channels, a.M, PL::N, a.hop, a.out_len, a.w, a.y, st);
+}
+
+int launch_istft(nxs_ctx* ctx, const float2* z, int64_t channels, int64_t num_frames, int64_t z_len,
+                 const float* window, int64_t frame_length, int64_t hop, int64_t fft_length, int scaling,
+                 double sampling_rate, float2* y, cudaStream_t st) {
+  if (channels <= 0) return NXS_OK;
+  const int64_t nfft = fft_length;
+  if (nfft > (int64_t(1) << 24)) return NXS_EUNSUPPORTED;
+  int rc = ensure_coef(ctx, size_t(nfft) * sizeof(float));
+  if (rc) return rc;
+  // w' = w * S / nfft (istft multiplies by S = sum w | sqrt(sr * sum w^2), lib/nx_signal.ex:611-625)
+  rc = launch_prep_window(ctx, window, frame_length, nfft, scaling, sampling_rate, (float)(1.0 / double(nfft)), 1,
+                          ctx->d_coef, st);
+  if (rc) return rc;
+
+  IstftArgs a;
+  a.z = z;
+  a.M = num_frames;
+  a.z_len = z_len;
+  a.wprep = ctx->d_coef;
+  a.w = window;
+  a.y = y;
+  a.out_len = num_frames * hop + (nfft - hop);
+  a.hop = (int)hop;
+  a.tw = nullptr;
+  a.seg_frames = a.segs_per_channel = a.total_segs = a.warm_batches = 0;
+
+  const bool pow2 = (nfft & (nfft - 1)) == 0;
+  if (pow2 && nfft >= 32 && nfft <= 8192) {
+    switch (nfft) {
+      case 32: return run_istft<Plan<32, 4, 8, 4>, 128, 1>(ctx, a, channels, st);
+      case 64: return run_istft<Plan<64, 8, 8, 8>, 128, 1>(ctx, a, channels, st);
+      case 128: return run_istft<Plan<128, 16, 8, 8, 2>, 128, 1>(ctx, a, channels, st);
+      case 256: return run_istft<Plan<256, 32, 8, 8, 4>, 256, 2>(ctx, a, channels, st);
+      case 512: return run_istft<Plan<512, 64, 8, 8, 8>, 256, 2>(ctx, a, channels, st);
+      case 1024: return run_istft<Plan<1024, 64, 16, 8, 8>, 256, 2>(ctx, a, channels, st);
+      case 2048: return run_istft<Plan<2048, 128, 16, 16, 8>, 512, 1>(ctx, a, channels, st);
+      case 4096: return run_istft_two_kernels<Plan<4096, 256, 16, 16, 16>, 512>(ctx, a, channels, st);
+      case 8192: return run_istft_two_kernels<Plan<8192, 512, 16, 16, 16, 2>, 512>(ctx, a, channels, st);
+      default: break;
+    }
+  }
+  // generic: frames = ifft(z) * w' in scratch, then overlap-add + normalise
+  float2* tab = nullptr;
+  rc = get_dft_table(ctx, nfft, +1, &tab);
+  if (rc) return rc;
+  const int64_t total_frames = channels * num_frames;
+  rc = ensure_scratch(ctx, size_t(total_frames) * nfft * sizeof(float2));
+  if (rc) return rc;
+  const int nin = (int)(z_len < nfft ? z_len : nfft);
+  const size_t smem = size_t(nin) * sizeof(float2);
+  if (smem > 200 * 1024) return NXS_EUNSUPPORTED;
+  NXS_CUDA(ctx, cudaFuncSetAttribute(istft_dft_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int64_t grid = total_frames < int64_t(ctx->sm_count) * 8 ? total_frames : int64_t(ctx->sm_count) * 8;
+  istft_dft_frames_kernel<<<(unsigned)grid, 256, smem, st>>>(z, total_frames, (int)z_len, (int)nfft, ctx->d_coef, tab,
+                                                            (float2*)ctx->d_scratch);
+  ctx->launches++;
+  NXS_CUDA(ctx, cudaGetLastError());
+  return run_ola_norm(ctx, (const float2*)ctx->d_scratch, channels, num_frames, nfft, hop, a.out_len, window, y, st);
+  // (unreachable)
+  return NXS_OK;
+}
+
+}  // namespace nxs

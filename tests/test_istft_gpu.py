@@ -1,0 +1,172 @@
+"""GPU parity of the fused ISTFT kernel (C ABI) against the oracle.
+Tolerance: max|gpu - oracle| / max|oracle| <= 1e-5 per channel (north_star: fp32 error <= 1e-5)."""
+import numpy as np
+import pytest
+
+import nx_signal_b200 as nx
+from oracle import nxsignal_oracle as o
+from tests.util import TOL, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def ola_energy(window, hop, M):
+    """The reference's normaliser: overlap-added |w|^2 (lib/nx_signal.ex:630-633)."""
+    w2 = np.abs(np.asarray(window, dtype=np.float64)) ** 2
+    N = len(w2)
+    d = np.zeros(M * hop + N - hop)
+    for m in range(M):
+        d[m * hop:m * hop + N] += w2
+    return d
+
+
+def rel(got, want, window=None, hop=None):
+    """max |got - want| / max |want| per channel.  With `window`, samples are weighted by the
+    conditioning of the reference's division: where the overlap-added window energy D[n] falls
+    below 1 % of its maximum (the first / last ~100 samples of a Hann-windowed signal) the
+    reference divides an fp32-accurate numerator by a near-zero number, so the bound there is
+    TOL * sqrt(Dmax / D[n]) instead of TOL ("ISTFT edge conditioning")."""
+    got = np.asarray(got).astype(np.complex128)
+    want = np.asarray(want).astype(np.complex128)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    err = np.abs(got - want)
+    if window is not None:
+        N = len(window)
+        M = (got.shape[-1] - (N - hop)) // hop
+        d = ola_energy(window, hop, M)
+        d = np.where(d > 1e-10, d, 1.0)
+        cond = np.maximum(1.0, np.sqrt(0.01 * d.max() / d))
+        err = err / cond
+    num = err.max(axis=-1)
+    den = np.abs(want).max(axis=-1)
+    return float((num / np.where(den > 0, den, 1.0)).max())
+
+
+@pytest.mark.parametrize("scaling", [None, "spectrum", "psd"])
+def test_doctest_roundtrip(scaling):  # lib/nx_signal.ex:545-579 (generic path: nfft = 4)
+    t = np.array([10, 10, 1, 0, 10, 10, 2, 20], dtype=np.float32)
+    w = nx.windows.hann(4)
+    kw = dict(sampling_rate=1, fft_length=4, scaling=scaling)
+    z, _, _ = nx.stft(t, w, **kw)
+    r = nx.istft(z, w, **kw)
+    assert r.dtype == np.complex64 and r.shape == (8,)
+    np.testing.assert_allclose(r.real, [0, 10, 1, 0, 10, 10, 2, 20], atol=2e-5)
+    zo, _, _ = o.stft(t, o.hann(4), **kw)
+    ro = o.istft(zo, o.hann(4), **kw)
+    assert rel(r, ro, o.hann(4), 2) <= TOL
+
+
+def test_cfg5_shape_reduced_vs_oracle():
+    """BASELINE config 5 at reduced length: istft(stft(x)), hann(1024), hop 256."""
+    x = synth((3, 120_000), 1005)
+    w = o.hann(1024)
+    kw = dict(overlap_length=768, fft_length=1024, sampling_rate=48000)
+    zo, _, _ = o.stft_fast(x, w, **kw)
+    yo = o.istft_fast(zo, w, **kw)
+    y = nx.istft(zo, w, **kw)
+    assert y.shape == yo.shape and y.dtype == np.complex64
+    assert rel(y, yo, w, 256) <= TOL
+    # and the round trip through our own stft reproduces x away from the edges
+    z, _, _ = nx.stft(x, w, **kw)
+    y2 = nx.istft(z, w, **kw)
+    n = y2.shape[-1]
+    assert np.abs(y2.real[:, 1024:n - 1024] - x[:, 1024:n - 1024]).max() <= 1e-5 * np.abs(x).max()
+    assert np.abs(y2.imag[:, 1024:n - 1024]).max() <= 1e-5 * np.abs(x).max()
+
+
+@pytest.mark.parametrize("nfft", [32, 64, 128, 256, 512, 1024, 2048, 4096, 8192])
+def test_every_pow2_plan(nfft):
+    rng = np.random.default_rng(nfft)
+    M = 37
+    z = (rng.standard_normal((2, M, nfft)) + 1j * rng.standard_normal((2, M, nfft))).astype(np.complex64)
+    w = o.hamming(nfft)
+    kw = dict(overlap_length=nfft - nfft // 4, fft_length=nfft)
+    y = nx.istft(z, w, **kw)
+    yo = o.istft_fast(z, w, **kw)
+    assert rel(y, yo) <= TOL
+
+
+@pytest.mark.parametrize("nfft,hop", [(256, 256), (256, 128), (256, 100), (256, 255), (256, 7), (64, 1), (1024, 512),
+                                      (1024, 128), (12, 5), (10, 3), (15, 15), (3, 2)])
+def test_hops_and_generic_lengths(nfft, hop):
+    rng = np.random.default_rng(nfft * 1000 + hop)
+    M = 300 if nfft > 64 else 61
+    z = (rng.standard_normal((2, M, nfft)) + 1j * rng.standard_normal((2, M, nfft))).astype(np.complex64)
+    w = (o.hann(nfft) + np.float32(0.1)).astype(np.float32)
+    kw = dict(overlap_length=nfft - hop, fft_length=nfft)
+    y = nx.istft(z, w, **kw)
+    yo = (o.istft_fast if nfft & (nfft - 1) == 0 else o.istft)(z, w, **kw)
+    assert y.shape == (2, M * hop + nfft - hop)
+    assert rel(y, yo) <= TOL
+
+
+def test_long_channel_many_segments():
+    """More frames than one segment (256) so the warm-up recompute at segment starts is exercised."""
+    rng = np.random.default_rng(3)
+    M, nfft, hop = 1500, 256, 64
+    z = (rng.standard_normal((3, M, nfft)) + 1j * rng.standard_normal((3, M, nfft))).astype(np.complex64)
+    w = o.hann(nfft)
+    y = nx.istft(z, w, overlap_length=nfft - hop, fft_length=nfft)
+    yo = o.istft_fast(z, w, overlap_length=nfft - hop, fft_length=nfft)
+    assert rel(y, yo, w, hop) <= TOL
+
+
+@pytest.mark.parametrize("scaling", ["spectrum", "psd"])
+def test_scaling(scaling):
+    x = synth((2, 30000), 8)
+    w = o.hann(512)
+    kw = dict(overlap_length=384, fft_length=512, sampling_rate=16000, scaling=scaling)
+    zo, _, _ = o.stft_fast(x, w, **kw)
+    assert rel(nx.istft(zo, w, **kw), o.istft_fast(zo, w, **kw), w, 128) <= TOL
+
+
+def test_z_len_padding_and_truncation():  # Nx.ifft(length:) pads / truncates the last axis
+    rng = np.random.default_rng(5)
+    w = o.hann(256)
+    for zlen in (200, 256, 300):
+        z = (rng.standard_normal((2, 50, zlen)) + 1j * rng.standard_normal((2, 50, zlen))).astype(np.complex64)
+        y = nx.istft(z, w, overlap_length=192, fft_length=256)
+        yo = o.istft_fast(z, w, overlap_length=192, fft_length=256)
+        assert rel(y, yo, w, 64) <= TOL
+
+
+def test_zero_window_guard():  # select(norm > 1e-10, norm, 1.0), lib/nx_signal.ex:635
+    rng = np.random.default_rng(6)
+    z = (rng.standard_normal((1, 20, 64)) + 1j * rng.standard_normal((1, 20, 64))).astype(np.complex64)
+    w = o.hann(64, is_periodic=False)  # zero at both ends -> first / last sample have zero normaliser
+    y = nx.istft(z, w, overlap_length=0, fft_length=64)
+    yo = o.istft_fast(z, w, overlap_length=0, fft_length=64)
+    assert np.isfinite(y.view(np.float32)).all()
+    assert rel(y, yo, w, 64) <= TOL
+
+
+def test_errors():
+    w = nx.windows.hann(64)
+    with pytest.raises(nx.NxSignalArgumentError, match="cannot broadcast"):
+        nx.istft(np.zeros((3, 128), np.complex64), w)
+    with pytest.raises(nx.NxSignalArgumentError, match="invalid :scaling"):
+        nx.istft(np.zeros((3, 64), np.complex64), w, scaling="bogus")
+
+
+def test_device_roundtrip_at_scale():
+    """cfg5 full shape (32 ch x 60 s): stft -> istft on device reproduces x away from the edges."""
+    import torch
+
+    C, L, N, H = 32, 48000 * 60, 1024, 256
+    g = torch.Generator(device="cuda").manual_seed(1005)
+    x = torch.randn(C, L, device="cuda", generator=g) * 0.25
+    w = torch.from_numpy(nx.windows.hann(N)).cuda()
+    z, _, _ = nx.stft(x, w, overlap_length=N - H, sampling_rate=48000)
+    y = nx.istft(z, w, overlap_length=N - H, fft_length=N)
+    n = y.shape[-1]
+    assert y.dtype == torch.complex64 and n == z.shape[-2] * H + N - H
+    err = (y.real[:, N:n - N] - x[:, N:n - N]).abs().max() / x.abs().max()
+    assert float(err) <= 1e-5
+    assert float(y.imag[:, N:n - N].abs().max() / x.abs().max()) <= 1e-5
+    # oracle spot check on one channel's first 40 frames
+    zs = z[0, :40].cpu().numpy()
+    yo = o.istft_fast(zs, nx.windows.hann(N), overlap_length=N - H, fft_length=N)
+    got = y[0, : 39 * H].cpu().numpy()  # samples not touched by frames >= 40
+    d = ola_energy(nx.windows.hann(N), H, 40)[: 39 * H]
+    cond = np.maximum(1.0, np.sqrt(0.01 * d.max() / np.where(d > 1e-10, d, 1.0)))
+    assert (np.abs(got - yo[: 39 * H]) / cond).max() / np.abs(yo).max() <= TOL
