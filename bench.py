@@ -106,7 +106,9 @@ def cpu_port_rate(seconds_target, nthreads=0):
     from tests.util import synth
 
     w = o.hann(NFFT)
-    cores = c_port.threads() if nthreads <= 0 else nthreads
+    if nthreads <= 0:  # torchrun exports OMP_NUM_THREADS=1: use every core this process may run on
+        nthreads = len(os.sched_getaffinity(0))
+    cores = nthreads
     cal_frames = 2048 * max(cores // 8, 1)
     x = synth((1, cal_frames * HOP + NFFT - HOP), 1002)
     t = time.perf_counter()

@@ -197,6 +197,7 @@ int nxs_ctx_destroy(nxs_ctx* ctx) {
   for (auto& e : ctx->prof_events) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
   cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->out_stream) cudaStreamDestroy(ctx->out_stream);
   delete ctx;
   return NXS_OK;
 }
@@ -275,14 +276,43 @@ int nxs_stft_f32_host(nxs_ctx* ctx, const float* x, int64_t channels, int64_t le
                       scaling, sampling_rate, &g, &M);
   if (rc) return rc;
   DeviceGuard guard(ctx->device);
-  const size_t in_bytes = size_t(channels > 0 ? (channels - 1) * x_ld + length : 0) * sizeof(float);
-  const size_t out_bytes = size_t(channels) * size_t(M) * size_t(fft_length) * sizeof(float2);
-  return host_roundtrip(ctx, x, in_bytes, window, size_t(frame_length) * sizeof(float), z, out_bytes,
-                        [&](void* dx, void* dw, void* dz) {
-                          return launch_stft(ctx, (const float*)dx, channels, length, x_ld, (const float*)dw,
-                                             frame_length, hop, fft_length, g, M, scaling, sampling_rate,
-                                             (float2*)dz, ctx->stream);
-                        });
+  if (channels == 0 || M == 0) return NXS_OK;
+  // Chunked pipeline over channels: H2D(chunk i+1) | kernels(chunk i) | D2H(chunk i-1) on three
+  // streams.  The D2H of the 8x larger spectrum dominates, so overlapping it with the H2D and
+  // the kernels hides everything but PCIe's D2H time.
+  const size_t in_bytes = size_t((channels - 1) * x_ld + length) * sizeof(float);
+  const size_t out_per_ch = size_t(M) * size_t(fft_length) * sizeof(float2);
+  int rc2 = grow(ctx, &ctx->d_stage_in, &ctx->d_stage_in_bytes, in_bytes + size_t(frame_length) * sizeof(float) + 512, false);
+  if (rc2) return rc2;
+  rc2 = grow(ctx, &ctx->d_stage_out, &ctx->d_stage_out_bytes, out_per_ch * size_t(channels) + 256, false);
+  if (rc2) return rc2;
+  if (!ctx->out_stream) NXS_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->out_stream, cudaStreamNonBlocking));
+  float* d_x = (float*)ctx->d_stage_in;
+  float* d_w = (float*)((char*)ctx->d_stage_in + (in_bytes + 255) / 256 * 256);
+  float2* d_z = (float2*)ctx->d_stage_out;
+  int64_t cc = int64_t((size_t(256) << 20) / (out_per_ch ? out_per_ch : 1));
+  if (cc < 1) cc = 1;
+  if (cc > channels) cc = channels;
+  NXS_CUDA(ctx, cudaMemcpyAsync(d_w, window, size_t(frame_length) * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_stream));
+  int i = 0;
+  for (int64_t c0 = 0; c0 < channels; c0 += cc, ++i) {
+    const int64_t n = channels - c0 < cc ? channels - c0 : cc;
+    const size_t xb = size_t((n - 1) * x_ld + length) * sizeof(float);
+    NXS_CUDA(ctx, cudaMemcpyAsync(d_x + c0 * x_ld, x + c0 * x_ld, xb, cudaMemcpyHostToDevice, ctx->copy_stream));
+    NXS_CUDA(ctx, cudaEventRecord(ctx->ev[i & 1], ctx->copy_stream));
+    NXS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev[i & 1], 0));
+    rc = launch_stft(ctx, d_x + c0 * x_ld, n, length, x_ld, d_w, frame_length, hop, fft_length, g, M, scaling,
+                     sampling_rate, d_z + size_t(c0) * M * fft_length, ctx->stream);
+    if (rc) return rc;
+    NXS_CUDA(ctx, cudaEventRecord(ctx->ev[2 + (i & 1)], ctx->stream));
+    NXS_CUDA(ctx, cudaStreamWaitEvent(ctx->out_stream, ctx->ev[2 + (i & 1)], 0));
+    NXS_CUDA(ctx, cudaMemcpyAsync(reinterpret_cast<float2*>(z) + size_t(c0) * M * fft_length,
+                                  d_z + size_t(c0) * M * fft_length, out_per_ch * size_t(n), cudaMemcpyDeviceToHost,
+                                  ctx->out_stream));
+  }
+  NXS_CUDA(ctx, cudaStreamSynchronize(ctx->out_stream));
+  NXS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return NXS_OK;
 }
 
 // ---- ISTFT ----------------------------------------------------------------------------------

@@ -40,6 +40,7 @@ struct nxs_ctx {
   void* d_stage_out = nullptr;
   size_t d_stage_out_bytes = 0;
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t out_stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   // optional per-kernel timing (nxs_ctx_profile)
   bool prof_enabled = false;

@@ -213,19 +213,22 @@ struct GroupSync {
 
 // HOPDIV: the stage holds spans for hop <= nfft / HOPDIV; TWREG: twiddles in registers, else a
 // shared-memory copy of the per-pass table.
-template <class PL_, int THREADS_, int HOPDIV_, bool TWREG_>
+// PERGROUP: every frame group stages its own frame (nfft floats, its own mbarrier pair) and
+// free-runs with no CTA-wide barrier; the nfft/hop-fold re-read of the input is served by L2.
+template <class PL_, int THREADS_, int HOPDIV_, bool TWREG_, bool PERGROUP_ = false>
 struct StagedCfg {
   using PL = PL_;
   static constexpr int THREADS = THREADS_, HOPDIV = HOPDIV_;
-  static constexpr bool TWREG = TWREG_;
+  static constexpr bool TWREG = TWREG_, PERGROUP = PERGROUP_;
   static constexpr int G = THREADS / PL::T, NFFT = 2 * PL::N;
-  static constexpr int STAGE = NFFT + (G - 1) * (NFFT / HOPDIV);  // floats per stage
+  // floats per stage: one tile span, or G private frames
+  static constexpr int STAGE = PERGROUP ? G * NFFT : NFFT + (G - 1) * (NFFT / HOPDIV);
   static constexpr size_t BUF_BYTES = size_t(G) * 2 * PL::BUF * sizeof(cpx);
   static constexpr size_t WIN_OFF = BUF_BYTES;
   static constexpr size_t STAGE_OFF = WIN_OFF + size_t(NFFT) * sizeof(float);
   static constexpr size_t TW_OFF = STAGE_OFF + 2 * size_t(STAGE) * sizeof(float);
   static constexpr size_t BAR_OFF = TW_OFF + (TWREG ? 0 : size_t(PL::TW_TOTAL) * sizeof(cpx));
-  static constexpr size_t SMEM = BAR_OFF + 16;
+  static constexpr size_t SMEM = BAR_OFF + 16 * (PERGROUP ? G : 1);
 };
 
 template <class CF, int MINB>
@@ -252,8 +255,7 @@ __global__ void __launch_bounds__(CF::THREADS, MINB) stft_r2c_staged_kernel(cons
     for (int i = tid; i < PL::TW_TOTAL; i += THREADS) twsm[i] = a.tw[i];
   }
   if (tid == 0) {
-    mbar_init(bar0, 1);
-    mbar_init(bar0 + 8, 1);
+    for (int i = 0; i < 2 * (CF::PERGROUP ? G : 1); ++i) mbar_init(bar0 + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -267,33 +269,46 @@ __global__ void __launch_bounds__(CF::THREADS, MINB) stft_r2c_staged_kernel(cons
   const GroupSync<T> sync{1 + g};
   const int hop = (int)a.hop;
 
-  // is this tile fully interior (no padding) -> staged through TMA
+  // is this tile (PERGROUP: this group's frame) fully interior (no padding) -> staged through TMA
   auto tile_geom = [&](int tile, int& c, int& m0, int& gact, int64_t& src0) {
     c = tile / tpc;
     m0 = (tile - c * tpc) * G;
     const int64_t left = a.M - m0;
     gact = left < G ? (int)left : G;
     src0 = (int64_t)m0 * hop - a.pad_lo;
-    return src0 >= 0 && src0 + (int64_t)(gact - 1) * hop + NFFT <= a.L;
+    if constexpr (CF::PERGROUP) {
+      const int64_t s = src0 + (int64_t)g * hop;
+      return g < gact && s >= 0 && s + NFFT <= a.L;
+    } else {
+      return src0 >= 0 && src0 + (int64_t)(gact - 1) * hop + NFFT <= a.L;
+    }
   };
+  // mbarrier / stage buffer of (stage) for this thread's group
+  const uint32_t mybar = CF::PERGROUP ? bar0 + 16 * g : bar0;
+  float* const mystage = CF::PERGROUP ? stage0 + (size_t)g * NFFT : stage0;
   auto issue = [&](int tile, int stage) {
     int c, m0, gact;
     int64_t src0;
     if (tile_geom(tile, c, m0, gact, src0)) {
-      const uint32_t bytes = (uint32_t)(((gact - 1) * hop + NFFT) * sizeof(float));
-      const uint32_t bar = bar0 + 8 * stage;
+      const uint32_t bytes =
+          (uint32_t)((CF::PERGROUP ? NFFT : (gact - 1) * hop + NFFT) * sizeof(float));
+      const uint32_t bar = mybar + 8 * stage;
+      const int64_t s = CF::PERGROUP ? src0 + (int64_t)g * hop : src0;
       mbar_expect_tx(bar, bytes);
-      tma_load_1d(smem_u32(stage0 + (size_t)stage * CF::STAGE), a.x + (int64_t)c * a.x_ld + src0, bytes, bar);
+      tma_load_1d(smem_u32(mystage + (size_t)stage * CF::STAGE), a.x + (int64_t)c * a.x_ld + s, bytes, bar);
     }
   };
+  const bool issuer = CF::PERGROUP ? (t == 0) : (tid == 0);
 
   uint32_t phase_bits = 0;  // bit s = parity to wait for on stage s
   int tile = blockIdx.x;
-  if (tile < total_tiles && tid == 0) issue(tile, 0);
+  if (tile < total_tiles && issuer) issue(tile, 0);
   for (int it = 0; tile < total_tiles; tile += gridDim.x, ++it) {
     const int stage = it & 1;
-    __syncthreads();  // every thread is done reading stage^1 (tile it-1)
-    if (tid == 0 && tile + (int)gridDim.x < total_tiles) issue(tile + gridDim.x, stage ^ 1);
+    // stage^1 was last read in iteration it-1: PERGROUP -- this group's threads all passed that
+    // iteration's barriers before the issuer gets here; else a CTA-wide barrier says so
+    if constexpr (!CF::PERGROUP) __syncthreads();
+    if (issuer && tile + (int)gridDim.x < total_tiles) issue(tile + gridDim.x, stage ^ 1);
 
     int c, m0, gact;
     int64_t src0;
@@ -303,11 +318,11 @@ __global__ void __launch_bounds__(CF::THREADS, MINB) stft_r2c_staged_kernel(cons
     const int64_t f = (int64_t)c * a.M + m;
     cpx v[P];
     if (staged) {
-      mbar_wait(bar0 + 8 * stage, (phase_bits >> stage) & 1);
+      mbar_wait(mybar + 8 * stage, (phase_bits >> stage) & 1);
       phase_bits ^= (1u << stage);
       if (active) {
-        const float2* __restrict__ xp =
-            reinterpret_cast<const float2*>(stage0 + (size_t)stage * CF::STAGE + (size_t)g * hop);
+        const float2* __restrict__ xp = reinterpret_cast<const float2*>(
+            mystage + (size_t)stage * CF::STAGE + (CF::PERGROUP ? (size_t)0 : (size_t)g * hop));
         const float2* __restrict__ wp = reinterpret_cast<const float2*>(wsm);
 #pragma unroll
         for (int b = 0; b < B0; ++b)
@@ -518,6 +533,11 @@ static int run_r2c_staged(nxs_ctx* ctx, StftArgs a, int64_t channels, cudaStream
 }
 
 // can the staged (TMA) kernel serve this call?  (16-byte alignment of every tile span, hop <= nfft/2)
+static int variant_env() {
+  const char* var = getenv("NXS_STFT_VARIANT");
+  return var ? atoi(var) : 0;
+}
+
 template <class CF>
 static bool staged_ok(const StftArgs& a, int64_t channels) {
   const int64_t tiles = ((a.M + CF::G - 1) / CF::G) * channels;
@@ -577,22 +597,30 @@ int launch_stft(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, 
       case 256: return run_r2c<Plan<128, 16, 8, 8, 2>, TwTable<Plan<128, 16, 8, 8, 2>>, 256>(ctx, a, st);
       case 512: {
         using PL = Plan<256, 32, 8, 8, 4>;
-        { using CF = StagedCfg<PL, 256, 2, true>; NXS_TRY_STAGED(CF, 2); }
+        { using CF = StagedCfg<PL, 256, 2, true, true>; NXS_TRY_STAGED(CF, 2); }
         return run_r2c<PL, TwTable<PL>, 256>(ctx, a, st);
       }
       case 1024: {
         using PL = Plan<512, 64, 8, 8, 8>;
-        { using CF = StagedCfg<PL, 256, 2, true>; NXS_TRY_STAGED(CF, 2); }
+        // tuning variants (tests/test_stft_variants_gpu.py); default = per-group staging, 256 x 2
+        const char* var = getenv("NXS_STFT_VARIANT");
+        const int variant = var ? atoi(var) : 0;
+        if (variant == 1) { using CF = StagedCfg<PL, 256, 2, true, false>; NXS_TRY_STAGED(CF, 2); }
+        if (variant == 2) { using CF = StagedCfg<PL, 512, 2, true, true>; NXS_TRY_STAGED(CF, 1); }
+        if (variant == 3) { using CF = StagedCfg<PL, 128, 2, true, true>; NXS_TRY_STAGED(CF, 4); }
+        { using CF = StagedCfg<PL, 256, 2, true, true>; NXS_TRY_STAGED(CF, 2); }
         return run_r2c<PL, TwRegs<PL>, 512>(ctx, a, st);
       }
       case 2048: {
         using PL = Plan<1024, 64, 16, 8, 8>;
-        { using CF = StagedCfg<PL, 512, 2, false>; NXS_TRY_STAGED(CF, 1); }
+        if (variant_env() == 1) { using CF = StagedCfg<PL, 512, 2, false, false>; NXS_TRY_STAGED(CF, 1); }
+        { using CF = StagedCfg<PL, 256, 2, false, true>; NXS_TRY_STAGED(CF, 2); }
         return run_r2c<PL, TwTable<PL>, 512>(ctx, a, st);
       }
       case 4096: {
         using PL = Plan<2048, 128, 16, 16, 8>;
-        { using CF = StagedCfg<PL, 512, 4, false>; NXS_TRY_STAGED(CF, 1); }
+        if (variant_env() == 1) { using CF = StagedCfg<PL, 512, 4, false, false>; NXS_TRY_STAGED(CF, 1); }
+        { using CF = StagedCfg<PL, 256, 4, false, true>; NXS_TRY_STAGED(CF, 1); }
         return run_r2c<PL, TwTable<PL>, 512>(ctx, a, st);
       }
       case 8192: return run_r2c<Plan<4096, 256, 16, 16, 16>, TwTable<Plan<4096, 256, 16, 16, 16>>, 512>(ctx, a, st);
