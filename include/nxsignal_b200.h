@@ -126,6 +126,15 @@ int nxs_stft_f32_host(nxs_ctx* ctx, const float* x, int64_t channels, int64_t le
                       int pad_mode, int64_t pad_lo, int64_t pad_hi, int scaling, double sampling_rate,
                       float* z);
 
+/* One-sided variant (opt-in): only bins 0 .. fft_length/2 of every frame are
+ * stored, z [channels][num_frames][z_ld] c64 with z_ld >= fft_length/2 + 1.  The remaining
+ * bins of the reference's two-sided result (lib/nx_signal.ex:49) are conj(z[fft_length-k]);
+ * nxs_stft_f32_host uses this form on the wire and mirrors on the host. */
+int nxs_stft_onesided_f32_dev(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length,
+                              int64_t x_ld, const float* window, int64_t frame_length, int64_t hop,
+                              int64_t fft_length, int pad_mode, int64_t pad_lo, int64_t pad_hi,
+                              int scaling, double sampling_rate, float* z, int64_t z_ld, void* stream);
+
 /* ---- ISTFT: NxSignal.istft(data, window, opts)  lib/nx_signal.ex:582-638 ---
  * z      [channels][num_frames][z_len] c64; Nx.ifft(length: fft_length) pads /
  *        truncates the last axis to fft_length, which must equal frame_length

@@ -2,6 +2,7 @@
 // include/nxsignal_b200.h.  Argument checking mirrors the reference's ArgumentError
 // conditions (cited per entry); no entry point ever falls back to the CPU.
 #include <dlfcn.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "nxs_common.cuh"
@@ -195,6 +196,8 @@ int nxs_ctx_destroy(nxs_ctx* ctx) {
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
   for (auto& e : ctx->prof_events) cudaEventDestroy(e);
+  for (auto& e : ctx->slab_events) cudaEventDestroy(e);
+  delete ctx->pool;
   cudaStreamDestroy(ctx->stream);
   cudaStreamDestroy(ctx->copy_stream);
   if (ctx->out_stream) cudaStreamDestroy(ctx->out_stream);
@@ -262,7 +265,23 @@ int nxs_stft_f32_dev(nxs_ctx* ctx, const float* x, int64_t channels, int64_t len
   if (rc) return rc;
   DeviceGuard guard(ctx->device);
   return launch_stft(ctx, x, channels, length, x_ld, window, frame_length, hop, fft_length, g, M, scaling,
-                     sampling_rate, reinterpret_cast<float2*>(z), pick(ctx, stream));
+                     sampling_rate, reinterpret_cast<float2*>(z), fft_length, 0, pick(ctx, stream));
+}
+
+int nxs_stft_onesided_f32_dev(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, int64_t x_ld,
+                              const float* window, int64_t frame_length, int64_t hop, int64_t fft_length,
+                              int pad_mode, int64_t pad_lo, int64_t pad_hi, int scaling, double sampling_rate,
+                              float* z, int64_t z_ld, void* stream) {
+  if (!ctx || !x || !window || !z) return NXS_EINVAL;
+  PadGeom g;
+  int64_t M = 0;
+  int rc = stft_check(channels, length, x_ld, frame_length, hop, fft_length, pad_mode, pad_lo, pad_hi,
+                      scaling, sampling_rate, &g, &M);
+  if (rc) return rc;
+  if (z_ld < fft_length / 2 + 1) return NXS_ESHAPE;
+  DeviceGuard guard(ctx->device);
+  return launch_stft(ctx, x, channels, length, x_ld, window, frame_length, hop, fft_length, g, M, scaling,
+                     sampling_rate, reinterpret_cast<float2*>(z), z_ld, 1, pick(ctx, stream));
 }
 
 int nxs_stft_f32_host(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, int64_t x_ld,
@@ -279,20 +298,32 @@ int nxs_stft_f32_host(nxs_ctx* ctx, const float* x, int64_t channels, int64_t le
   if (channels == 0 || M == 0) return NXS_OK;
   // Chunked pipeline over channels: H2D(chunk i+1) | kernels(chunk i) | D2H(chunk i-1) on three
   // streams.  The D2H of the 8x larger spectrum dominates, so overlapping it with the H2D and
-  // the kernels hides everything but PCIe's D2H time.
+  // the kernels hides everything but PCIe's D2H time -- and that time is halved by moving only
+  // bins 0 .. nfft/2 of each frame (a pitched copy straight into the caller's rows) and letting
+  // host threads write the conjugate-mirror half while later slabs are still in flight.
+  const bool mirror = stft_has_exact_mirror(fft_length) && !getenv("NXS_HOST_NO_MIRROR");
+  const int64_t nout = mirror ? fft_length / 2 + 1 : fft_length;
+  const int64_t z_ld = mirror ? (nout + 3) / 4 * 4 : fft_length;  // device row stride (32-byte multiple)
   const size_t in_bytes = size_t((channels - 1) * x_ld + length) * sizeof(float);
-  const size_t out_per_ch = size_t(M) * size_t(fft_length) * sizeof(float2);
+  const size_t dev_per_ch = size_t(M) * size_t(z_ld) * sizeof(float2);
   int rc2 = grow(ctx, &ctx->d_stage_in, &ctx->d_stage_in_bytes, in_bytes + size_t(frame_length) * sizeof(float) + 512, false);
   if (rc2) return rc2;
-  rc2 = grow(ctx, &ctx->d_stage_out, &ctx->d_stage_out_bytes, out_per_ch * size_t(channels) + 256, false);
+  rc2 = grow(ctx, &ctx->d_stage_out, &ctx->d_stage_out_bytes, dev_per_ch * size_t(channels) + 256, false);
   if (rc2) return rc2;
   if (!ctx->out_stream) NXS_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->out_stream, cudaStreamNonBlocking));
+  if (mirror && !ctx->pool) ctx->pool = new HostPool(HostPool::default_threads());
   float* d_x = (float*)ctx->d_stage_in;
   float* d_w = (float*)((char*)ctx->d_stage_in + (in_bytes + 255) / 256 * 256);
   float2* d_z = (float2*)ctx->d_stage_out;
-  int64_t cc = int64_t((size_t(256) << 20) / (out_per_ch ? out_per_ch : 1));
+  float2* hz = reinterpret_cast<float2*>(z);
+  int64_t cc = int64_t((size_t(128) << 20) / (dev_per_ch ? dev_per_ch : 1));
   if (cc < 1) cc = 1;
   if (cc > channels) cc = channels;
+  // D2H slabs: whole frames, about 16 MiB on the wire each
+  int64_t slab_rows = int64_t((size_t(16) << 20) / (size_t(nout) * sizeof(float2)));
+  if (slab_rows < 1) slab_rows = 1;
+  struct Slab { int64_t row0, row1; };
+  std::vector<Slab> slabs;
   NXS_CUDA(ctx, cudaMemcpyAsync(d_w, window, size_t(frame_length) * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_stream));
   int i = 0;
   for (int64_t c0 = 0; c0 < channels; c0 += cc, ++i) {
@@ -302,13 +333,44 @@ int nxs_stft_f32_host(nxs_ctx* ctx, const float* x, int64_t channels, int64_t le
     NXS_CUDA(ctx, cudaEventRecord(ctx->ev[i & 1], ctx->copy_stream));
     NXS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev[i & 1], 0));
     rc = launch_stft(ctx, d_x + c0 * x_ld, n, length, x_ld, d_w, frame_length, hop, fft_length, g, M, scaling,
-                     sampling_rate, d_z + size_t(c0) * M * fft_length, ctx->stream);
+                     sampling_rate, d_z + size_t(c0) * M * z_ld, z_ld, mirror ? 1 : 0, ctx->stream);
     if (rc) return rc;
     NXS_CUDA(ctx, cudaEventRecord(ctx->ev[2 + (i & 1)], ctx->stream));
     NXS_CUDA(ctx, cudaStreamWaitEvent(ctx->out_stream, ctx->ev[2 + (i & 1)], 0));
-    NXS_CUDA(ctx, cudaMemcpyAsync(reinterpret_cast<float2*>(z) + size_t(c0) * M * fft_length,
-                                  d_z + size_t(c0) * M * fft_length, out_per_ch * size_t(n), cudaMemcpyDeviceToHost,
-                                  ctx->out_stream));
+    const int64_t r_end = (c0 + n) * M;
+    for (int64_t r0 = c0 * M; r0 < r_end; r0 += slab_rows) {
+      const int64_t r1 = r0 + slab_rows < r_end ? r0 + slab_rows : r_end;
+      if (mirror) {
+        NXS_CUDA(ctx, cudaMemcpy2DAsync(hz + size_t(r0) * fft_length, size_t(fft_length) * sizeof(float2),
+                                        d_z + size_t(r0) * z_ld, size_t(z_ld) * sizeof(float2),
+                                        size_t(nout) * sizeof(float2), size_t(r1 - r0), cudaMemcpyDeviceToHost,
+                                        ctx->out_stream));
+        if (slabs.size() >= ctx->slab_events.size()) {
+          cudaEvent_t e = nullptr;
+          NXS_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+          ctx->slab_events.push_back(e);
+        }
+        NXS_CUDA(ctx, cudaEventRecord(ctx->slab_events[slabs.size()], ctx->out_stream));
+        slabs.push_back(Slab{r0, r1});
+      } else {
+        NXS_CUDA(ctx, cudaMemcpyAsync(hz + size_t(r0) * fft_length, d_z + size_t(r0) * fft_length,
+                                      size_t(r1 - r0) * fft_length * sizeof(float2), cudaMemcpyDeviceToHost,
+                                      ctx->out_stream));
+      }
+    }
+  }
+  // host threads: as each slab lands, write its mirror half (blocks of 64 frames per work item)
+  struct Job { float* z; int64_t nfft, row0, row1; };
+  for (size_t s = 0; s < slabs.size(); ++s) {
+    NXS_CUDA(ctx, cudaEventSynchronize(ctx->slab_events[s]));
+    Job job{z, fft_length, slabs[s].row0, slabs[s].row1};
+    const int64_t blocks = (job.row1 - job.row0 + 63) / 64;
+    ctx->pool->parallel_for(blocks, [](void* p, int64_t b) {
+      const Job* j = static_cast<const Job*>(p);
+      const int64_t a0 = j->row0 + b * 64;
+      const int64_t a1 = a0 + 64 < j->row1 ? a0 + 64 : j->row1;
+      mirror_rows_c64(j->z, j->nfft, a0, a1);
+    }, &job);
   }
   NXS_CUDA(ctx, cudaStreamSynchronize(ctx->out_stream));
   NXS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

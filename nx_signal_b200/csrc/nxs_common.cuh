@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../include/nxsignal_b200.h"
+#include "nxs_hostpool.h"
 
 namespace nxs {
 
@@ -42,6 +43,9 @@ struct nxs_ctx {
   cudaStream_t copy_stream = nullptr;
   cudaStream_t out_stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  // _host STFT: one event per device->host slab, and the threads that mirror the slabs
+  std::vector<cudaEvent_t> slab_events;
+  nxs::HostPool* pool = nullptr;
   // optional per-kernel timing (nxs_ctx_profile)
   bool prof_enabled = false;
   std::vector<cudaEvent_t> prof_events;  // start/stop pairs
@@ -78,7 +82,10 @@ int64_t frames_for(int64_t length, int64_t window_length, int64_t stride, const 
 int launch_stft(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, int64_t x_ld,
                 const float* window, int64_t frame_length, int64_t hop, int64_t fft_length,
                 const PadGeom& g, int64_t num_frames, int scaling, double sampling_rate, float2* z,
-                cudaStream_t st);
+                int64_t z_ld, int onesided, cudaStream_t st);
+// true when launch_stft serves fft_length with a kernel whose upper half-spectrum is the exact
+// conjugate mirror of the lower half (the r2c kernels; not the generic DFT)
+bool stft_has_exact_mirror(int64_t fft_length);
 int launch_istft(nxs_ctx* ctx, const float2* z, int64_t channels, int64_t num_frames, int64_t z_len,
                  const float* window, int64_t frame_length, int64_t hop, int64_t fft_length, int scaling,
                  double sampling_rate, float2* y, cudaStream_t st);

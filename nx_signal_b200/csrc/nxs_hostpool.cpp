@@ -1,0 +1,137 @@
+// nxs_hostpool.cpp -- host-side worker threads of the "_host" entry points.
+//
+// The reference returns the full two-sided spectrum of a real signal (lib/nx_signal.ex:49,
+// :102, :129), whose bins nfft/2+1 .. nfft-1 are the exact conjugate mirror of bins
+// nfft/2-1 .. 1.  The GPU computes the spectrum; moving that redundant half over PCIe would
+// double the device->host time, which is what bounds an NIF call.  nxs_stft_f32_host therefore
+// copies only bins 0 .. nfft/2 of every frame into the caller's rows and these threads fill in
+// z[f][nfft-k] = conj(z[f][k]) (a bit copy with one sign flip -- no arithmetic), slab by slab
+// while later slabs are still in flight.  The result is bit-identical to the two-sided device
+// output (tests/test_stft_gpu.py::test_host_mirror_bit_identical).
+#include <emmintrin.h>
+#include <sched.h>
+#include <stdlib.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "nxs_hostpool.h"
+
+namespace nxs {
+
+struct HostPool::Impl {
+  std::vector<std::thread> workers;
+  std::mutex mu;
+  std::condition_variable cv_work, cv_done;
+  uint64_t generation = 0;
+  bool stop = false;
+  // current job
+  void (*fn)(void*, int64_t) = nullptr;
+  void* arg = nullptr;
+  int64_t n = 0;
+  std::atomic<int64_t> next{0};
+  int pending = 0;  // workers still inside the current job
+
+  void drain() {
+    for (;;) {
+      const int64_t i = next.fetch_add(1, std::memory_order_relaxed);
+      if (i >= n) break;
+      fn(arg, i);
+    }
+  }
+
+  void worker_main() {
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv_work.wait(lk, [&] { return stop || generation != seen; });
+        if (stop) return;
+        seen = generation;
+      }
+      drain();
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        if (--pending == 0) cv_done.notify_one();
+      }
+    }
+  }
+};
+
+int HostPool::default_threads() {
+  const char* e = getenv("NXS_HOST_THREADS");
+  if (e && atoi(e) > 0) return atoi(e);
+  cpu_set_t set;
+  int n = 0;
+  if (sched_getaffinity(0, sizeof(set), &set) == 0) n = CPU_COUNT(&set);
+  if (n <= 0) n = (int)std::thread::hardware_concurrency();
+  if (n <= 0) n = 1;
+  return n > 32 ? 32 : n;
+}
+
+HostPool::HostPool(int nthreads) : impl_(new Impl()), nthreads_(nthreads < 1 ? 1 : nthreads) {
+  for (int i = 1; i < nthreads_; ++i) impl_->workers.emplace_back([this] { impl_->worker_main(); });
+}
+
+HostPool::~HostPool() {
+  {
+    std::lock_guard<std::mutex> lk(impl_->mu);
+    impl_->stop = true;
+  }
+  impl_->cv_work.notify_all();
+  for (auto& t : impl_->workers) t.join();
+  delete impl_;
+}
+
+void HostPool::parallel_for(int64_t n, void (*fn)(void*, int64_t), void* arg) {
+  if (n <= 0) return;
+  Impl& s = *impl_;
+  if (s.workers.empty() || n == 1) {
+    for (int64_t i = 0; i < n; ++i) fn(arg, i);
+    return;
+  }
+  {
+    std::lock_guard<std::mutex> lk(s.mu);
+    s.fn = fn;
+    s.arg = arg;
+    s.n = n;
+    s.next.store(0, std::memory_order_relaxed);
+    s.pending = (int)s.workers.size();
+    ++s.generation;
+  }
+  s.cv_work.notify_all();
+  s.drain();
+  std::unique_lock<std::mutex> lk(s.mu);
+  s.cv_done.wait(lk, [&] { return s.pending == 0; });
+}
+
+// z[nfft - k] = conj(z[k]) for k = 1 .. nfft - (nfft/2 + 1), rows [row0, row1) of a
+// [rows][nfft] interleaved c64 matrix.
+void mirror_rows_c64(float* z, int64_t nfft, int64_t row0, int64_t row1) {
+  const int64_t nout = nfft / 2 + 1;
+  const int64_t kmax = nfft - nout;  // last k whose mirror lies outside the stored half
+  const __m128 sign = _mm_castsi128_ps(_mm_set_epi32((int)0x80000000u, 0, (int)0x80000000u, 0));
+  for (int64_t r = row0; r < row1; ++r) {
+    float* row = z + 2 * r * nfft;
+    int64_t k = 1;
+    if ((reinterpret_cast<uintptr_t>(row) & 15) == 0 && (nfft & 1) == 0) {
+      // pairs (k, k+1), k odd: destination index nfft-k-1 is even -> 16-byte aligned, streamed
+      for (; k + 1 <= kmax; k += 2) {
+        __m128 v = _mm_loadu_ps(row + 2 * k);              // [re k, im k, re k+1, im k+1]
+        v = _mm_shuffle_ps(v, v, _MM_SHUFFLE(1, 0, 3, 2));  // [re k+1, im k+1, re k, im k]
+        v = _mm_xor_ps(v, sign);
+        _mm_stream_ps(row + 2 * (nfft - k - 1), v);
+      }
+    }
+    for (; k <= kmax; ++k) {
+      row[2 * (nfft - k)] = row[2 * k];
+      row[2 * (nfft - k) + 1] = -row[2 * k + 1];
+    }
+  }
+  _mm_sfence();
+}
+
+}  // namespace nxs

@@ -1,0 +1,29 @@
+// nxs_hostpool.h -- host worker threads used by the "_host" entry points (see nxs_hostpool.cpp).
+#pragma once
+#include <stdint.h>
+
+namespace nxs {
+
+class HostPool {
+ public:
+  explicit HostPool(int nthreads);
+  ~HostPool();
+  HostPool(const HostPool&) = delete;
+  HostPool& operator=(const HostPool&) = delete;
+  // fn(arg, i) for every i in [0, n), on the workers and the calling thread; returns when done
+  void parallel_for(int64_t n, void (*fn)(void*, int64_t), void* arg);
+  int threads() const { return nthreads_; }
+  // NXS_HOST_THREADS, else the CPUs this process may run on (capped at 32)
+  static int default_threads();
+
+ private:
+  struct Impl;
+  Impl* impl_;
+  int nthreads_;
+};
+
+// z[r][nfft - k] = conj(z[r][k]) for the bins above nfft/2, rows [row0, row1) of a
+// [rows][nfft] interleaved c64 matrix (bit copy + sign flip)
+void mirror_rows_c64(float* z, int64_t nfft, int64_t row0, int64_t row1);
+
+}  // namespace nxs

@@ -55,7 +55,9 @@ struct StftArgs {
   const float* x;
   int64_t x_ld, L;
   const float* wprep;  // [nfft], scaled, zero-extended
-  float2* z;           // [total_frames][nfft]
+  float2* z;           // [total_frames][z_ld]; nfft bins per frame, or nfft/2 + 1 when onesided
+  int64_t z_ld;
+  int onesided;        // 1: only bins 0 .. nfft/2 are stored (the rest is their conjugate mirror)
   int64_t M, total_frames, hop, pad_lo;
   int nload;           // min(frame_length, nfft)
   int reflect;
@@ -138,7 +140,8 @@ __global__ void __launch_bounds__(THREADS) stft_r2c_kernel(const StftArgs a) {
       for (int q = 0; q < RL; ++q) pb[fft_out_index<PL>(t, b, q)] = v[fft_out_reg<PL>(b, q)];
     sync();
     if (active) {
-      float2* __restrict__ zf = a.z + f * NFFT;
+      float2* __restrict__ zf = a.z + f * a.z_ld;
+      const bool two = !a.onesided;
 #pragma unroll
       for (int i = 0; i < P / 2; ++i) {
         const int kk = t + i * T;
@@ -148,14 +151,14 @@ __global__ void __launch_bounds__(THREADS) stft_r2c_kernel(const StftArgs a) {
         const cpx Tm = cmul(wpost[i], O);
         const cpx X0 = cadd(E, Tm), X1 = csub(E, Tm);
         zf[kk] = X0;
-        zf[N + kk] = X1;
+        if (two || kk == 0) zf[N + kk] = X1;
         if (kk > 0) {
           zf[N - kk] = cconj(X1);
-          zf[NFFT - kk] = cconj(X0);
+          if (two) zf[NFFT - kk] = cconj(X0);
         } else {
           const cpx Zh = pb[N / 2];
           zf[N / 2] = make_float2(2.f * Zh.x, -2.f * Zh.y);
-          zf[N + N / 2] = make_float2(2.f * Zh.x, 2.f * Zh.y);
+          if (two) zf[N + N / 2] = make_float2(2.f * Zh.x, 2.f * Zh.y);
         }
       }
     }
@@ -231,7 +234,7 @@ struct StagedCfg {
   static constexpr size_t SMEM = BAR_OFF + 16 * (PERGROUP ? G : 1);
 };
 
-template <class CF, int MINB>
+template <class CF, int MINB, bool ONESIDED>
 __global__ void __launch_bounds__(CF::THREADS, MINB) stft_r2c_staged_kernel(const StftArgs a, const int tpc,
                                                                             const int total_tiles) {
   using PL = typename CF::PL;
@@ -362,7 +365,7 @@ __global__ void __launch_bounds__(CF::THREADS, MINB) stft_r2c_staged_kernel(cons
       for (int q = 0; q < RL; ++q) pb[fft_out_index<PL>(t, b, q)] = v[fft_out_reg<PL>(b, q)];
     sync();
     if (active) {
-      float2* __restrict__ zf = a.z + f * NFFT;
+      float2* __restrict__ zf = a.z + f * (ONESIDED ? a.z_ld : (int64_t)NFFT);
 #pragma unroll
       for (int i = 0; i < P / 2; ++i) {
         const int kk = t + i * T;
@@ -372,14 +375,14 @@ __global__ void __launch_bounds__(CF::THREADS, MINB) stft_r2c_staged_kernel(cons
         const cpx Tm = cmul(wpost[i], O);
         const cpx X0 = cadd(E, Tm), X1 = csub(E, Tm);
         __stcs(zf + kk, X0);
-        __stcs(zf + N + kk, X1);
+        if (!ONESIDED || kk == 0) __stcs(zf + N + kk, X1);
         if (kk > 0) {
           __stcs(zf + N - kk, cconj(X1));
-          __stcs(zf + NFFT - kk, cconj(X0));
+          if constexpr (!ONESIDED) __stcs(zf + NFFT - kk, cconj(X0));
         } else {
           const cpx Zh = pb[N / 2];
           __stcs(zf + N / 2, make_float2(2.f * Zh.x, -2.f * Zh.y));
-          __stcs(zf + N + N / 2, make_float2(2.f * Zh.x, 2.f * Zh.y));
+          if constexpr (!ONESIDED) __stcs(zf + N + N / 2, make_float2(2.f * Zh.x, 2.f * Zh.y));
         }
       }
     }
@@ -405,7 +408,8 @@ __global__ void __launch_bounds__(256) stft_dft_kernel(const StftArgs a, int nff
     for (int s = threadIdx.x; s < a.nload; s += blockDim.x)
       xw[s] = load_padded(xrow, src0 + s, a.L, a.reflect) * a.wprep[s];
     __syncthreads();
-    for (int k = threadIdx.x; k < nfft; k += blockDim.x) {
+    const int nout = a.onesided ? nfft / 2 + 1 : nfft;
+    for (int k = threadIdx.x; k < nout; k += blockDim.x) {
       float re = 0.f, im = 0.f;
       int idx = 0;
       for (int s = 0; s < a.nload; ++s) {
@@ -417,7 +421,7 @@ __global__ void __launch_bounds__(256) stft_dft_kernel(const StftArgs a, int nff
         if (idx >= nfft) idx -= nfft;
       }
       // Nx.fft snaps |re|, |im| <= eps (1e-10) to zero
-      a.z[f * nfft + k] = make_float2(fabsf(re) <= 1e-10f ? 0.f : re, fabsf(im) <= 1e-10f ? 0.f : im);
+      a.z[f * a.z_ld + k] = make_float2(fabsf(re) <= 1e-10f ? 0.f : re, fabsf(im) <= 1e-10f ? 0.f : im);
     }
   }
 }
@@ -517,7 +521,7 @@ static int run_r2c_staged(nxs_ctx* ctx, StftArgs a, int64_t channels, cudaStream
   a.post = tabs.post;
   const int64_t tpc = (a.M + CF::G - 1) / CF::G;
   const int64_t tiles = tpc * channels;
-  auto kern = stft_r2c_staged_kernel<CF, MINB>;
+  auto kern = a.onesided ? stft_r2c_staged_kernel<CF, MINB, true> : stft_r2c_staged_kernel<CF, MINB, false>;
   NXS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF::SMEM));
   int occ = 1;
   NXS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, CF::SMEM));
@@ -555,10 +559,14 @@ int launch_prep_window(nxs_ctx* ctx, const float* window, int64_t n, int64_t nff
   return NXS_OK;
 }
 
+bool stft_has_exact_mirror(int64_t nfft) {
+  return (nfft & (nfft - 1)) == 0 && nfft >= 64 && nfft <= 16384;
+}
+
 int launch_stft(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, int64_t x_ld,
                 const float* window, int64_t frame_length, int64_t hop, int64_t fft_length,
                 const PadGeom& g, int64_t num_frames, int scaling, double sampling_rate, float2* z,
-                cudaStream_t st) {
+                int64_t z_ld, int onesided, cudaStream_t st) {
   if (num_frames <= 0 || channels <= 0) return NXS_OK;
   if (fft_length > (int64_t(1) << 24) || frame_length > (int64_t(1) << 24)) return NXS_EUNSUPPORTED;
   const int64_t nfft = fft_length;
@@ -571,6 +579,8 @@ int launch_stft(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, 
   a.L = length;
   a.wprep = ctx->d_coef;
   a.z = z;
+  a.z_ld = z_ld;
+  a.onesided = onesided;
   a.M = num_frames;
   a.total_frames = num_frames * channels;
   a.hop = hop;
@@ -580,8 +590,7 @@ int launch_stft(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, 
   a.tw = nullptr;
   a.post = nullptr;
 
-  const bool pow2 = (nfft & (nfft - 1)) == 0;
-  const bool fast = pow2 && nfft >= 64 && nfft <= 16384;
+  const bool fast = stft_has_exact_mirror(nfft);
   rc = launch_prep_window(ctx, window, frame_length, nfft, scaling, sampling_rate, fast ? 0.5f : 1.0f, 0,
                           ctx->d_coef, st);
   if (rc) return rc;
