@@ -284,12 +284,24 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             e2e_s = float(tt.item())
         e2e = {"value": world * FRAMES_PER_GPU / e2e_s, "unit": "frames/s",
-               "h2d_bytes_per_step": int(xh.numel() * 4 + NFFT * 4), "d2h_bytes_per_step": int(zh.numel() * 8),
+               "h2d_bytes_per_step": int(xh.numel() * 4 + NFFT * 4),
+               "d2h_bytes_per_step": int(CHANNELS * M * (NFFT // 2 + 1) * 8),
+               "host_result_bytes_per_step": int(zh.numel() * 8),
                "steps": args.e2e_steps, "ms_per_step": 1e3 * e2e_s,
-               "path": "nxs_stft_f32_host on pinned host buffers (wall clock, max over ranks)"}
+               "path": "nxs_stft_f32_host on pinned host buffers (wall clock, max over ranks): H2D | kernel | "
+                       "D2H of bins 0..nfft/2 | host threads write the conjugate-mirror bins; result = the "
+                       "reference's two-sided c64 tensor, bit-identical to the device entry"}
         if rank == 0:
             got = zh[0, :16].numpy()
             e2e["parity"] = float((np.abs(got - zo).max(-1) / np.abs(zo).max(-1)).max())
+            # the host result must equal the device result bit for bit (checked on the last 4096 frames)
+            step_dev2 = torch.empty((4096, NFFT), dtype=torch.complex64, device=dev)
+            x_tail = x[CHANNELS - 1, L - (4095 * HOP + NFFT) - ((L - NFFT) % HOP):].contiguous()
+            _lib.check(lib.nxs_stft_f32_dev(ctx, A.ptr(x_tail), 1, x_tail.numel(), x_tail.numel(), A.ptr(w), NFFT, HOP,
+                                            NFFT, _lib.PAD_VALID, 0, 0, _lib.SCALE_NONE, float(FS), A.ptr(step_dev2), sptr), ctx)
+            torch.cuda.synchronize(dev)
+            e2e["host_equals_device_bitwise"] = bool(torch.equal(torch.view_as_real(step_dev2).cpu(),
+                                                                 torch.view_as_real(zh[CHANNELS - 1, M - 4096:])))
     except Exception as ex:  # report, never fake
         e2e = {"value": None, "unit": "frames/s", "error": repr(ex)[:200]}
 
@@ -321,7 +333,7 @@ def main():
         "config": {"workload": WORKLOAD, "channels_per_gpu": CHANNELS, "fft_length": NFFT, "hop": HOP,
                    "l2": "inputs larger than L2 (0.92 GB in, 7.37 GB out per step)", "parity_frame_rel_err": parity},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "kernel": "stft_r2c_staged_kernel<StagedCfg<Plan<512,64,8,8,8>,256,2,regs>,2>",
+                     "traffic": traffic, "peak_source": peak_src, "kernel": "stft_r2c_staged_kernel<StagedCfg<Plan<512,64,8,8,8>,256,2,tw-regs,per-group TMA>,2,two-sided>",
                      "kernel_ms": kern_avg_ms, "kernel_launches_timed": kern_n, "algorithmic_bytes": ALGO_BYTES},
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }

@@ -83,6 +83,11 @@ uint64_t nxs_ctx_launch_count(const nxs_ctx* ctx);
 int nxs_ctx_profile(nxs_ctx* ctx, int enable);
 int nxs_ctx_profile_read(nxs_ctx* ctx, double* total_ms, int64_t* launches);
 
+/* phases of the last nxs_stft_f32_host call on this context, seconds since the call began:
+ * [0] all copies/kernels enqueued, [1] first result slab in host memory, [2] last slab in host
+ * memory, [3] host mirror threads done (= result complete).  bench.py reports them. */
+int nxs_ctx_host_timeline(const nxs_ctx* ctx, double out_seconds[4]);
+
 /* ---- host-side closed forms (O(n); no GPU needed) ----------------------- */
 /* NxSignal.Windows.{rectangular,bartlett,triangular,blackman,hamming,hann,kaiser}(n, opts)
  * lib/nx_signal/windows.ex:33,57,98,160,225,278,341 -- f32 output, `periodic`

@@ -92,13 +92,17 @@ def stft_times(frame_length, sampling_rate, num_frames):
 
 
 def stft(data, window, overlap_length=None, fft_length="power_of_two", window_padding="valid",
-         sampling_rate=100, scaling=None, **ignored):
+         sampling_rate=100, scaling=None, onesided=False, **ignored):
     """NxSignal.stft/3 (lib/nx_signal.ex:68-130).
 
     data [..., L], window [N] -> (z c64 [..., M, fft_length], times f32 [M], frequencies f32
     [fft_length]).  Defaults as the reference: overlap_length = N // 2, fft_length =
     next power of two >= N, window_padding = 'valid', sampling_rate = 100 (sic, :77).
-    The reference's unused ``:window`` option is accepted and ignored (:74)."""
+    The reference's unused ``:window`` option is accepted and ignored (:74).
+
+    ``onesided=True`` is an opt-in extension (not in the reference): CUDA tensors
+    only, z holds bins 0 .. fft_length // 2 ([..., M, fft_length // 2 + 1]), frequencies
+    likewise; the dropped bins are conj(z[..., fft_length - k])."""
     for k in ignored:
         if k != "window":
             raise NxSignalArgumentError(f"unknown keys [{k!r}] in options")
@@ -121,11 +125,19 @@ def stft(data, window, overlap_length=None, fft_length="power_of_two", window_pa
     batch_shape = tuple(x.shape[:-1])
     Cn = int(np.prod(batch_shape, dtype=np.int64)) if batch_shape else 1
     M = _num_frames(L, N, hop, mode, lo, hi)
-    z = A.empty_like_kind(x, batch_shape + (M, nfft), "c64")
+    if onesided and not A.is_cuda(x):
+        raise NotImplementedError("onesided=True takes CUDA tensors (the host entry already moves the one-sided "
+                                  "form over PCIe and returns the reference's two-sided result)")
+    nout = nfft // 2 + 1 if onesided else nfft
+    z = A.empty_like_kind(x, batch_shape + (M, nout), "c64")
     if M > 0 and Cn > 0:
         dev = A.device_index(x)
         ctx = _lib.context(dev)
-        if A.is_cuda(x):
+        if onesided:
+            rc = _lib.lib().nxs_stft_onesided_f32_dev(ctx, A.ptr(x), Cn, L, L, A.ptr(w), N, hop, nfft, mode, lo,
+                                                      hi, scale, float(sampling_rate), A.ptr(z), nout,
+                                                      A.stream_of(x))
+        elif A.is_cuda(x):
             rc = _lib.lib().nxs_stft_f32_dev(ctx, A.ptr(x), Cn, L, L, A.ptr(w), N, hop, nfft, mode, lo, hi,
                                              scale, float(sampling_rate), A.ptr(z), A.stream_of(x))
         else:
@@ -133,7 +145,7 @@ def stft(data, window, overlap_length=None, fft_length="power_of_two", window_pa
                                               scale, float(sampling_rate), A.ptr(z))
         _lib.check(rc, ctx, "stft")
     times = A.from_host(x, stft_times(N, sampling_rate, M))
-    freqs = A.from_host(x, fft_frequencies(sampling_rate, nfft))
+    freqs = A.from_host(x, fft_frequencies(sampling_rate, nfft)[:nout])
     return z, times, freqs
 
 

@@ -37,6 +37,7 @@ SIGNATURES = {
     "nxs_ctx_launch_count": (C.c_uint64, [vp]),
     "nxs_ctx_profile": (i32, [vp, i32]),
     "nxs_ctx_profile_read": (i32, [vp, C.POINTER(f64), C.POINTER(i64)]),
+    "nxs_ctx_host_timeline": (i32, [vp, C.POINTER(f64 * 4)]),
     "nxs_window_f32": (i32, [i32, i64, i32, f64, f64, vp]),
     "nxs_firwin_f32": (i32, [i64, C.POINTER(f64), i32, i32, f64, i32, i32, f64, vp]),
     "nxs_fft_frequencies_f32": (i32, [f64, i64, vp]),
@@ -137,3 +138,11 @@ def profile_read(device=0):
 
 def synchronize(device=0):
     check(lib().nxs_ctx_synchronize(context(device)), context(device))
+
+
+def host_timeline(device=0):
+    """Phases of the last nxs_stft_f32_host call (seconds since its start): enqueued, first slab
+    landed, last slab landed, mirror done."""
+    t = (f64 * 4)()
+    check(lib().nxs_ctx_host_timeline(context(device), C.byref(t)))
+    return [float(v) for v in t]

@@ -5,6 +5,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+#include <chrono>
+
 #include "nxs_common.cuh"
 
 namespace nxs {
@@ -89,6 +92,10 @@ int resolve_padding(int64_t length, int64_t window_length, int pad_mode, int64_t
 int64_t frames_for(int64_t length, int64_t window_length, int64_t stride, const PadGeom& g) {
   const int64_t padded = length + g.lo + g.hi;
   return padded < window_length ? 0 : (padded - window_length) / stride + 1;
+}
+
+static double wall_seconds() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
 // _dev entries run on the caller's stream; NULL is CUDA's (legacy) default stream, as everywhere in CUDA
@@ -238,6 +245,12 @@ int nxs_ctx_profile_read(nxs_ctx* ctx, double* total_ms, int64_t* launches) {
   return NXS_OK;
 }
 
+int nxs_ctx_host_timeline(const nxs_ctx* ctx, double out_seconds[4]) {
+  if (!ctx || !out_seconds) return NXS_EINVAL;
+  for (int i = 0; i < 4; ++i) out_seconds[i] = ctx->host_t[i];
+  return NXS_OK;
+}
+
 // ---- STFT -----------------------------------------------------------------------------------
 static int stft_check(int64_t channels, int64_t length, int64_t x_ld, int64_t frame_length, int64_t hop,
                       int64_t fft_length, int pad_mode, int64_t pad_lo, int64_t pad_hi, int scaling,
@@ -296,6 +309,8 @@ int nxs_stft_f32_host(nxs_ctx* ctx, const float* x, int64_t channels, int64_t le
   if (rc) return rc;
   DeviceGuard guard(ctx->device);
   if (channels == 0 || M == 0) return NXS_OK;
+  const double t_start = wall_seconds();
+  for (double& t : ctx->host_t) t = 0.0;
   // Chunked pipeline over channels: H2D(chunk i+1) | kernels(chunk i) | D2H(chunk i-1) on three
   // streams.  The D2H of the 8x larger spectrum dominates, so overlapping it with the H2D and
   // the kernels hides everything but PCIe's D2H time -- and that time is halved by moving only
@@ -319,58 +334,88 @@ int nxs_stft_f32_host(nxs_ctx* ctx, const float* x, int64_t channels, int64_t le
   int64_t cc = int64_t((size_t(128) << 20) / (dev_per_ch ? dev_per_ch : 1));
   if (cc < 1) cc = 1;
   if (cc > channels) cc = channels;
-  // D2H slabs: whole frames, about 16 MiB on the wire each
-  int64_t slab_rows = int64_t((size_t(16) << 20) / (size_t(nout) * sizeof(float2)));
-  if (slab_rows < 1) slab_rows = 1;
-  struct Slab { int64_t row0, row1; };
-  std::vector<Slab> slabs;
-  NXS_CUDA(ctx, cudaMemcpyAsync(d_w, window, size_t(frame_length) * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_stream));
-  int i = 0;
-  for (int64_t c0 = 0; c0 < channels; c0 += cc, ++i) {
-    const int64_t n = channels - c0 < cc ? channels - c0 : cc;
-    const size_t xb = size_t((n - 1) * x_ld + length) * sizeof(float);
-    NXS_CUDA(ctx, cudaMemcpyAsync(d_x + c0 * x_ld, x + c0 * x_ld, xb, cudaMemcpyHostToDevice, ctx->copy_stream));
-    NXS_CUDA(ctx, cudaEventRecord(ctx->ev[i & 1], ctx->copy_stream));
-    NXS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev[i & 1], 0));
-    rc = launch_stft(ctx, d_x + c0 * x_ld, n, length, x_ld, d_w, frame_length, hop, fft_length, g, M, scaling,
-                     sampling_rate, d_z + size_t(c0) * M * z_ld, z_ld, mirror ? 1 : 0, ctx->stream);
-    if (rc) return rc;
-    NXS_CUDA(ctx, cudaEventRecord(ctx->ev[2 + (i & 1)], ctx->stream));
-    NXS_CUDA(ctx, cudaStreamWaitEvent(ctx->out_stream, ctx->ev[2 + (i & 1)], 0));
-    const int64_t r_end = (c0 + n) * M;
-    for (int64_t r0 = c0 * M; r0 < r_end; r0 += slab_rows) {
-      const int64_t r1 = r0 + slab_rows < r_end ? r0 + slab_rows : r_end;
-      if (mirror) {
-        NXS_CUDA(ctx, cudaMemcpy2DAsync(hz + size_t(r0) * fft_length, size_t(fft_length) * sizeof(float2),
-                                        d_z + size_t(r0) * z_ld, size_t(z_ld) * sizeof(float2),
-                                        size_t(nout) * sizeof(float2), size_t(r1 - r0), cudaMemcpyDeviceToHost,
+  // D2H slabs: whole frames, a few MiB on the wire each (small enough that the mirror threads
+  // read a slab while it is still cache-resident, large enough to keep the copy engine busy)
+  size_t slab_bytes = size_t(8) << 20;
+  if (const char* e = getenv("NXS_HOST_SLAB_KB")) {
+    if (atol(e) > 0) slab_bytes = size_t(atol(e)) << 10;
+  }
+  int64_t slab_rows = int64_t(slab_bytes / (size_t(nout) * sizeof(float2)));
+  slab_rows = slab_rows < 64 ? 64 : slab_rows / 64 * 64;  // whole mirror work items (64 frames)
+  // host threads: work item b mirrors frames [64 b, 64 b + 64); it may start once its slab landed
+  struct Job { float* z; int64_t nfft, rows; };
+  Job job{z, fft_length, channels * M};
+  std::atomic<int64_t> gate{0};
+  const int64_t items = (job.rows + 63) / 64;
+  std::vector<int64_t> slab_end;  // frames landed once slab s is complete
+  if (mirror) {
+    ctx->pool->begin(items, [](void* p, int64_t b) {
+      const Job* j = static_cast<const Job*>(p);
+      const int64_t a0 = b * 64;
+      const int64_t a1 = a0 + 64 < j->rows ? a0 + 64 : j->rows;
+      mirror_rows_c64(j->z, j->nfft, a0, a1);
+    }, &job, &gate);
+  }
+  // from here on every exit must join the workers
+  auto enqueue = [&]() -> int {
+    NXS_CUDA(ctx, cudaMemcpyAsync(d_w, window, size_t(frame_length) * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_stream));
+    int i = 0;
+    for (int64_t c0 = 0; c0 < channels; c0 += cc, ++i) {
+      const int64_t n = channels - c0 < cc ? channels - c0 : cc;
+      const size_t xb = size_t((n - 1) * x_ld + length) * sizeof(float);
+      NXS_CUDA(ctx, cudaMemcpyAsync(d_x + c0 * x_ld, x + c0 * x_ld, xb, cudaMemcpyHostToDevice, ctx->copy_stream));
+      NXS_CUDA(ctx, cudaEventRecord(ctx->ev[i & 1], ctx->copy_stream));
+      NXS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev[i & 1], 0));
+      int rcl = launch_stft(ctx, d_x + c0 * x_ld, n, length, x_ld, d_w, frame_length, hop, fft_length, g, M, scaling,
+                            sampling_rate, d_z + size_t(c0) * M * z_ld, z_ld, mirror ? 1 : 0, ctx->stream);
+      if (rcl) return rcl;
+      NXS_CUDA(ctx, cudaEventRecord(ctx->ev[2 + (i & 1)], ctx->stream));
+      NXS_CUDA(ctx, cudaStreamWaitEvent(ctx->out_stream, ctx->ev[2 + (i & 1)], 0));
+      const int64_t r_end = (c0 + n) * M;
+      int64_t r0 = c0 * M;
+      while (r0 < r_end) {
+        // slabs end on multiples of 64 frames (work-item boundaries) except at the chunk's end
+        int64_t r1 = (r0 / 64 + slab_rows / 64) * 64;
+        if (r1 > r_end) r1 = r_end;
+        if (mirror) {
+          NXS_CUDA(ctx, cudaMemcpy2DAsync(hz + size_t(r0) * fft_length, size_t(fft_length) * sizeof(float2),
+                                          d_z + size_t(r0) * z_ld, size_t(z_ld) * sizeof(float2),
+                                          size_t(nout) * sizeof(float2), size_t(r1 - r0), cudaMemcpyDeviceToHost,
+                                          ctx->out_stream));
+          if (slab_end.size() >= ctx->slab_events.size()) {
+            cudaEvent_t e = nullptr;
+            NXS_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ctx->slab_events.push_back(e);
+          }
+          NXS_CUDA(ctx, cudaEventRecord(ctx->slab_events[slab_end.size()], ctx->out_stream));
+          slab_end.push_back(r1);
+        } else {
+          NXS_CUDA(ctx, cudaMemcpyAsync(hz + size_t(r0) * fft_length, d_z + size_t(r0) * fft_length,
+                                        size_t(r1 - r0) * fft_length * sizeof(float2), cudaMemcpyDeviceToHost,
                                         ctx->out_stream));
-        if (slabs.size() >= ctx->slab_events.size()) {
-          cudaEvent_t e = nullptr;
-          NXS_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-          ctx->slab_events.push_back(e);
         }
-        NXS_CUDA(ctx, cudaEventRecord(ctx->slab_events[slabs.size()], ctx->out_stream));
-        slabs.push_back(Slab{r0, r1});
-      } else {
-        NXS_CUDA(ctx, cudaMemcpyAsync(hz + size_t(r0) * fft_length, d_z + size_t(r0) * fft_length,
-                                      size_t(r1 - r0) * fft_length * sizeof(float2), cudaMemcpyDeviceToHost,
-                                      ctx->out_stream));
+        r0 = r1;
       }
     }
-  }
-  // host threads: as each slab lands, write its mirror half (blocks of 64 frames per work item)
-  struct Job { float* z; int64_t nfft, row0, row1; };
-  for (size_t s = 0; s < slabs.size(); ++s) {
-    NXS_CUDA(ctx, cudaEventSynchronize(ctx->slab_events[s]));
-    Job job{z, fft_length, slabs[s].row0, slabs[s].row1};
-    const int64_t blocks = (job.row1 - job.row0 + 63) / 64;
-    ctx->pool->parallel_for(blocks, [](void* p, int64_t b) {
-      const Job* j = static_cast<const Job*>(p);
-      const int64_t a0 = j->row0 + b * 64;
-      const int64_t a1 = a0 + 64 < j->row1 ? a0 + 64 : j->row1;
-      mirror_rows_c64(j->z, j->nfft, a0, a1);
-    }, &job);
+    // raise the gate as slabs land: item b is runnable once frames [64 b, 64 b + 64) are in host memory
+    ctx->host_t[0] = wall_seconds() - t_start;  // everything enqueued
+    for (size_t s = 0; s < slab_end.size(); ++s) {
+      NXS_CUDA(ctx, cudaEventSynchronize(ctx->slab_events[s]));
+      if (s == 0) ctx->host_t[1] = wall_seconds() - t_start;  // first slab landed
+      const int64_t landed = slab_end[s];
+      gate.store(landed == job.rows ? items : landed / 64, std::memory_order_release);
+    }
+    return NXS_OK;
+  };
+  rc = enqueue();
+  ctx->host_t[2] = wall_seconds() - t_start;  // last slab landed
+  if (mirror) ctx->pool->finish(rc != NXS_OK);
+  ctx->host_t[3] = wall_seconds() - t_start;  // mirror complete
+  if (rc) {
+    cudaStreamSynchronize(ctx->out_stream);  // nothing of ours may still write the caller's buffer
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->copy_stream);
+    return rc;
   }
   NXS_CUDA(ctx, cudaStreamSynchronize(ctx->out_stream));
   NXS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

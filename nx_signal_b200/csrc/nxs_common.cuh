@@ -46,6 +46,7 @@ struct nxs_ctx {
   // _host STFT: one event per device->host slab, and the threads that mirror the slabs
   std::vector<cudaEvent_t> slab_events;
   nxs::HostPool* pool = nullptr;
+  double host_t[4] = {0, 0, 0, 0};  // nxs_ctx_host_timeline
   // optional per-kernel timing (nxs_ctx_profile)
   bool prof_enabled = false;
   std::vector<cudaEvent_t> prof_events;  // start/stop pairs

@@ -35,10 +35,25 @@ struct HostPool::Impl {
   std::atomic<int64_t> next{0};
   int pending = 0;  // workers still inside the current job
 
+  // gated jobs: item i may run only once *gate > i (the caller raises the gate as data lands)
+  const std::atomic<int64_t>* gate = nullptr;
+  std::atomic<bool> abort{false};
+
   void drain() {
     for (;;) {
       const int64_t i = next.fetch_add(1, std::memory_order_relaxed);
       if (i >= n) break;
+      if (gate) {
+        int spins = 0;
+        while (gate->load(std::memory_order_acquire) <= i && !abort.load(std::memory_order_relaxed)) {
+          _mm_pause();
+          if (++spins == 4096) {
+            spins = 0;
+            sched_yield();
+          }
+        }
+      }
+      if (abort.load(std::memory_order_relaxed)) continue;
       fn(arg, i);
     }
   }
@@ -86,26 +101,35 @@ HostPool::~HostPool() {
   delete impl_;
 }
 
-void HostPool::parallel_for(int64_t n, void (*fn)(void*, int64_t), void* arg) {
-  if (n <= 0) return;
+void HostPool::begin(int64_t n, void (*fn)(void*, int64_t), void* arg, const std::atomic<int64_t>* gate) {
   Impl& s = *impl_;
-  if (s.workers.empty() || n == 1) {
-    for (int64_t i = 0; i < n; ++i) fn(arg, i);
-    return;
-  }
   {
     std::lock_guard<std::mutex> lk(s.mu);
     s.fn = fn;
     s.arg = arg;
-    s.n = n;
+    s.n = n < 0 ? 0 : n;
+    s.gate = gate;
+    s.abort.store(false, std::memory_order_relaxed);
     s.next.store(0, std::memory_order_relaxed);
     s.pending = (int)s.workers.size();
     ++s.generation;
   }
   s.cv_work.notify_all();
-  s.drain();
+}
+
+void HostPool::finish(bool abort) {
+  Impl& s = *impl_;
+  if (abort) s.abort.store(true, std::memory_order_relaxed);
+  s.drain();  // the caller helps (and is the only runner when there are no workers)
   std::unique_lock<std::mutex> lk(s.mu);
   s.cv_done.wait(lk, [&] { return s.pending == 0; });
+  s.gate = nullptr;
+}
+
+void HostPool::parallel_for(int64_t n, void (*fn)(void*, int64_t), void* arg) {
+  if (n <= 0) return;
+  begin(n, fn, arg, nullptr);
+  finish(false);
 }
 
 // z[nfft - k] = conj(z[k]) for k = 1 .. nfft - (nfft/2 + 1), rows [row0, row1) of a

@@ -2,6 +2,8 @@
 #pragma once
 #include <stdint.h>
 
+#include <atomic>
+
 namespace nxs {
 
 class HostPool {
@@ -12,6 +14,12 @@ class HostPool {
   HostPool& operator=(const HostPool&) = delete;
   // fn(arg, i) for every i in [0, n), on the workers and the calling thread; returns when done
   void parallel_for(int64_t n, void (*fn)(void*, int64_t), void* arg);
+  // gated form: begin() starts the workers on items 0 .. n-1 in order, item i waiting until
+  // *gate > i (gate == nullptr: no waiting); the caller raises the gate as data becomes ready
+  // and then calls finish(), which joins the work and returns when every item is done.
+  // finish(true) makes the remaining items no-ops (error paths).
+  void begin(int64_t n, void (*fn)(void*, int64_t), void* arg, const std::atomic<int64_t>* gate);
+  void finish(bool abort);
   int threads() const { return nthreads_; }
   // NXS_HOST_THREADS, else the CPUs this process may run on (capped at 32)
   static int default_threads();

@@ -137,3 +137,83 @@ def test_properties_at_scale():
     assert float(((e_t - e_f).abs() / e_t).max()) < 1e-5
     herm = (za[..., 1:] - za[..., 1:].flip(-1).conj()).abs().amax(dim=-1) / za.abs().amax(dim=-1)
     assert float(herm.max()) < 1e-6
+
+
+# ---- one-sided device form and the host entry's mirror pipeline ---------------------------------
+@pytest.mark.parametrize("nfft", [64, 256, 512, 1024, 2048, 4096, 8192])
+@pytest.mark.parametrize("padding", ["valid", "reflect"])
+def test_onesided_is_the_lower_half_bit_for_bit(nfft, padding):
+    import torch
+
+    x = torch.from_numpy(synth((3, 9 * nfft + 13), 31 + nfft)).cuda()
+    w = torch.from_numpy(o.hann(nfft)).cuda()
+    kw = dict(overlap_length=nfft - nfft // 4, fft_length=nfft, sampling_rate=48000, window_padding=padding)
+    z2, _, f2 = nx.stft(x, w, **kw)
+    z1, _, f1 = nx.stft(x, w, onesided=True, **kw)
+    assert z1.shape == z2.shape[:-1] + (nfft // 2 + 1,)
+    assert torch.equal(torch.view_as_real(z1), torch.view_as_real(z2[..., : nfft // 2 + 1].contiguous()))
+    assert torch.equal(f1, f2[: nfft // 2 + 1])
+    # and the dropped half is the exact conjugate mirror
+    up = torch.view_as_real(z2[..., nfft // 2 + 1:].contiguous())
+    mir = torch.view_as_real(torch.conj(z2[..., 1: nfft // 2].flip(-1)).resolve_conj().contiguous())
+    assert torch.equal(up, mir)
+
+
+def test_onesided_generic_dft_length():
+    import torch
+
+    x = torch.from_numpy(synth((2, 300), 5)).cuda()
+    w = torch.from_numpy(o.hamming(20)).cuda()
+    kw = dict(overlap_length=10, fft_length=30, sampling_rate=100)
+    z2, _, _ = nx.stft(x, w, **kw)
+    z1, _, _ = nx.stft(x, w, onesided=True, **kw)
+    assert torch.equal(torch.view_as_real(z1), torch.view_as_real(z2[..., :16].contiguous()))
+
+
+@pytest.mark.parametrize("nfft,hop,C,L,padding,scaling", [
+    (1024, 256, 2, 1_300_000, "valid", None),      # > 1 D2H slab per channel chunk
+    (1024, 256, 3, 50_000, "reflect", "spectrum"),
+    (64, 16, 5, 4_001, "same", "psd"),
+    (2048, 512, 2, 70_000, "valid", None),
+    (4096, 1024, 2, 70_000, "valid", None),
+    (512, 200, 1, 30_001, "valid", None),          # hop not a multiple of 4: general r2c kernel
+    (30, 10, 2, 500, "valid", None),               # generic DFT: two-sided on the wire
+])
+def test_host_entry_is_bit_identical_to_device_entry(nfft, hop, C, L, padding, scaling):
+    """nxs_stft_f32_host moves bins 0..nfft/2 over PCIe and mirrors on the host; the result must
+    equal the two-sided device result bit for bit (pageable numpy buffers here)."""
+    import torch
+
+    x = synth((C, L), 77 + nfft)
+    w = o.hann(min(nfft, 1024)) if nfft != 30 else o.hamming(20)
+    N = len(w)
+    kw = dict(overlap_length=N - hop, fft_length=nfft, sampling_rate=48000, window_padding=padding, scaling=scaling)
+    zh, th, fh = nx.stft(x, w, **kw)
+    zd, td, fd = nx.stft(torch.from_numpy(x).cuda(), torch.from_numpy(w).cuda(), **kw)
+    assert zh.shape == tuple(zd.shape)
+    np.testing.assert_array_equal(zh.view(np.float32), torch.view_as_real(zd).cpu().numpy().reshape(zh.shape[:-1] + (-1,)))
+    np.testing.assert_array_equal(th, td.cpu().numpy())
+    zo, _, _ = o.stft_fast(x, w, **kw)
+    assert frame_rel_err(zh, zo) <= TOL
+
+
+def test_host_entry_pinned_buffers_and_repeat():
+    """Pinned caller buffers (what bench.py's e2e leg uses), called twice on one context."""
+    import torch
+
+    from nx_signal_b200 import _arrays as A
+    from nx_signal_b200 import _lib
+
+    C_, L, nfft, hop = 4, 600_000, 1024, 256
+    M = (L - nfft) // hop + 1
+    xh = torch.from_numpy(synth((C_, L), 404)).pin_memory()
+    w = o.hann(nfft)
+    zh = torch.empty((C_, M, nfft), dtype=torch.complex64).pin_memory()
+    ctx = _lib.context(0)
+    for _ in range(2):
+        zh.zero_()
+        _lib.check(_lib.lib().nxs_stft_f32_host(ctx, A.ptr(xh), C_, L, L, w.ctypes.data, nfft, hop, nfft,
+                                                _lib.PAD_VALID, 0, 0, _lib.SCALE_NONE, 48000.0, A.ptr(zh)), ctx)
+        zd, _, _ = nx.stft(xh.cuda(), torch.from_numpy(w).cuda(), overlap_length=nfft - hop, fft_length=nfft,
+                           sampling_rate=48000)
+        assert torch.equal(torch.view_as_real(zh), torch.view_as_real(zd).cpu())
