@@ -184,7 +184,9 @@ struct SyncWarp {
 // v[b*R0 + q] = x[t + b*T + q*N/R0]; the last pass leaves X[t + b*T + q*N/R] in
 // v[b*R + bitrev(q)].
 // ---------------------------------------------------------------------------------------
-template <class PL, int PASS, class TW, class SYNC>
+// SINGLE: buf0 == buf1 (one exchange buffer): a barrier separates a pass's reads from its
+// writes, at the price of one more sync per middle pass.
+template <class PL, int PASS, class TW, class SYNC, bool SINGLE = false>
 struct PassRunner {
   static __device__ __forceinline__ void run(cpx (&v)[PL::P], int t, cpx* buf0, cpx* buf1,
                                              const TW& tw, const SYNC& sync) {
@@ -206,6 +208,7 @@ struct PassRunner {
           if constexpr (split) v[b * R + q] = in[tb + pad_idx<A, C>(X)];
           else v[b * R + q] = in[pad_idx<A, C>(t + X)];
         }
+      if constexpr (SINGLE && PASS + 1 < PL::NP) sync();  // reads done before this pass overwrites the buffer
 #pragma unroll
       for (int b = 0; b < B; ++b) {
         const int k = (t + b * T) % NS;
@@ -229,7 +232,7 @@ struct PassRunner {
         for (int q = 0; q < R; ++q) out[base + q * NS] = v[b * R + bitrev(q, ilog2(R))];
       }
       sync();
-      PassRunner<PL, PASS + 1, TW, SYNC>::run(v, t, buf0, buf1, tw, sync);
+      PassRunner<PL, PASS + 1, TW, SYNC, SINGLE>::run(v, t, buf0, buf1, tw, sync);
     }
   }
 };
@@ -241,6 +244,11 @@ template <class PL, class TW, class SYNC>
 __device__ __forceinline__ void block_fft(cpx (&v)[PL::P], int t, cpx* buf0, cpx* buf1, const TW& tw,
                                           const SYNC& sync) {
   PassRunner<PL, 0, TW, SYNC>::run(v, t, buf0, buf1, tw, sync);
+}
+// one exchange buffer of PL::BUF complex (see PassRunner's SINGLE)
+template <class PL, class TW, class SYNC>
+__device__ __forceinline__ void block_fft_single(cpx (&v)[PL::P], int t, cpx* buf, const TW& tw, const SYNC& sync) {
+  PassRunner<PL, 0, TW, SYNC, true>::run(v, t, buf, buf, tw, sync);
 }
 
 // logical index of the element the caller must preload into v[b*R0 + q]

@@ -14,11 +14,13 @@
 // covering frames at both ends) exactly.  Segments after the first recompute the few frames
 // that overlap their start (warm-up batches) instead of exchanging partial sums.
 #include <math.h>
+#include <stdlib.h>
 
 #include <type_traits>
 
 #include "nxs_common.cuh"
 #include "nxs_fft.cuh"
+#include "nxs_tma.cuh"
 
 namespace nxs {
 
@@ -188,6 +190,177 @@ __global__ void __launch_bounds__(THREADS, MINB) istft_kernel(const IstftArgs a)
 }
 
 // ------------------------------------------------------------------------------------------
+// Register overlap-add variant (the hot path): hop = N / HOPDIV with hop a multiple of the
+// group width T.  A group of T threads walks a segment of consecutive frames of one channel on
+// its own -- no CTA-wide barrier anywhere.  After the last FFT pass thread t holds the frame's
+// samples n = t + j*T (j < P), so the running overlap-add lives in P complex registers per
+// thread: acc[j] += frame[t + j*T] * w'; the first hop samples are then final (emit acc[j],
+// j < hop/T, divided by the overlap-added |w|^2) and the accumulators shift down by hop/T --
+// a compile-time register renaming.  Each frame's spectrum (N complex, contiguous) arrives by
+// one cp.async.bulk (TMA 1-D) into the group's stage buffer, issued as soon as the previous
+// frame has been read out of it, so the load of frame m+1 overlaps the FFT of frame m.
+// Segments after the first recompute the HOPDIV-1 frames that overlap their start.
+// ------------------------------------------------------------------------------------------
+template <class PL, int THREADS>
+struct RolaCfg {
+  static constexpr int G = THREADS / PL::T, N = PL::N;
+  static constexpr size_t GROUP_BYTES = (size_t(N) + size_t(PL::BUF)) * sizeof(cpx);  // stage + exchange
+  static constexpr size_t WIN_OFF = size_t(G) * GROUP_BYTES;
+  static constexpr size_t W2_OFF = WIN_OFF + size_t(N) * sizeof(float);
+  static constexpr size_t TW_OFF = W2_OFF + size_t(N) * sizeof(float);
+  static constexpr size_t BAR_OFF = TW_OFF + size_t(PL::TW_TOTAL) * sizeof(cpx);
+  static constexpr size_t SMEM = BAR_OFF + 8 * size_t(G) + 8;
+};
+
+template <class PL, int THREADS, int MINB, int HOPDIV>
+__global__ void __launch_bounds__(THREADS, MINB) istft_rola_kernel(const IstftArgs a) {
+  using CF = RolaCfg<PL, THREADS>;
+  constexpr int N = PL::N, T = PL::T, P = PL::P, G = CF::G;
+  constexpr int R0 = PL::R(0), B0 = P / R0;
+  constexpr int RL = PL::R(PL::NP - 1), BL = P / RL;
+  constexpr int HOP = N / HOPDIV, S = HOP / T;  // S accumulators complete per frame
+  static_assert(HOP % T == 0 && S >= 1 && N % HOPDIV == 0, "hop must be a multiple of the group width");
+  static_assert((N / RL) % T == 0, "last pass must leave n = t (mod T) in every thread");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tid = threadIdx.x, g = tid / T, t = tid % T;
+  cpx* const stage = reinterpret_cast<cpx*>(smem_raw + size_t(g) * CF::GROUP_BYTES);
+  cpx* const xbuf = stage + N;
+  float* wsm = reinterpret_cast<float*>(smem_raw + CF::WIN_OFF);
+  float* w2sm = reinterpret_cast<float*>(smem_raw + CF::W2_OFF);
+  cpx* twsm = reinterpret_cast<cpx*>(smem_raw + CF::TW_OFF);
+  const uint32_t mybar = smem_u32(smem_raw + CF::BAR_OFF) + 8 * g;
+
+  for (int i = tid; i < N; i += THREADS) {
+    wsm[i] = a.wprep[i];
+    const float w = a.w[i];
+    w2sm[i] = (float)((double)fabsf(w) * (double)fabsf(w));  // Nx.abs(window) ** 2, f32
+  }
+  for (int i = tid; i < PL::TW_TOTAL; i += THREADS) twsm[i] = a.tw[i];
+  if (tid == 0) {
+    for (int i = 0; i < G; ++i) mbar_init(smem_u32(smem_raw + CF::BAR_OFF) + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  TwTable<PL> tw;
+  tw.init(twsm, t);
+  const GroupSync<T> sync{1 + g};
+
+  // interior normaliser of the S samples a frame completes: all HOPDIV covering frames present,
+  // summed in ascending frame order (= descending window offset)
+  float normc[S];
+#pragma unroll
+  for (int j = 0; j < S; ++j) {
+    float nr = 0.f;
+#pragma unroll
+    for (int k = HOPDIV - 1; k >= 0; --k) nr += w2sm[t + j * T + k * HOP];
+    normc[j] = nr;
+  }
+  // exact normaliser at output position p of a channel (edges: fewer covering frames)
+  auto norm_at = [&](int64_t p) {
+    int64_t m_lo = p - N + 1 <= 0 ? 0 : (p - N + HOP) / HOP;
+    int64_t m_hi = p / HOP;
+    if (m_hi > a.M - 1) m_hi = a.M - 1;
+    float nr = 0.f;
+    for (int64_t m = m_lo; m <= m_hi; ++m) nr += w2sm[(int)(p - m * HOP)];
+    return nr;
+  };
+
+  const int gid = blockIdx.x * G + g, ngroups = gridDim.x * G;
+  // frame iterator over this group's segments
+  auto seg_bounds = [&](int seg, int& c, int64_t& mb, int64_t& ms, int64_t& me) {
+    c = seg / a.segs_per_channel;
+    const int si = seg - c * a.segs_per_channel;
+    ms = (int64_t)si * a.seg_frames;
+    me = ms + a.seg_frames;
+    if (me > a.M) me = a.M;
+    mb = ms - (HOPDIV - 1);
+    if (mb < 0) mb = 0;
+  };
+  auto issue = [&](int c, int64_t m) {
+    mbar_expect_tx(mybar, (uint32_t)(N * sizeof(cpx)));
+    tma_load_1d(smem_u32(stage), a.z + ((int64_t)c * a.M + m) * N, (uint32_t)(N * sizeof(cpx)), mybar);
+  };
+
+  uint32_t parity = 0;
+  int seg = gid;
+  int c = 0;
+  int64_t mb = 0, ms = 0, me = 0;
+  if (seg < a.total_segs) {
+    seg_bounds(seg, c, mb, ms, me);
+    if (t == 0) issue(c, mb);
+  }
+  while (seg < a.total_segs) {
+    float2* __restrict__ yc = a.y + (int64_t)c * a.out_len;
+    cpx acc[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) acc[j] = make_float2(0.f, 0.f);
+    // the segment after this one (for the prefetch across the segment boundary)
+    const int nseg = seg + ngroups;
+    int nc = 0;
+    int64_t nmb = 0, nms = 0, nme = 0;
+    if (nseg < a.total_segs) seg_bounds(nseg, nc, nmb, nms, nme);
+
+    for (int64_t m = mb; m < me; ++m) {
+      cpx v[P];
+      mbar_wait(mybar, parity);
+      parity ^= 1;
+#pragma unroll
+      for (int b = 0; b < B0; ++b)
+#pragma unroll
+        for (int q = 0; q < R0; ++q) {
+          const cpx val = stage[fft_in_index<PL>(t, b, q)];
+          v[b * R0 + q] = make_float2(val.y, val.x);  // swap: ifft(x) = swap(fft(swap(x))) / n
+        }
+      sync();  // stage read out (and the previous frame's last exchange reads are done)
+      if (t == 0) {
+        if (m + 1 < me) issue(c, m + 1);
+        else if (nseg < a.total_segs) issue(nc, nmb);
+      }
+      block_fft_single<PL>(v, t, xbuf, tw, sync);
+      // window, accumulate: thread t holds n = t + j*T at v[fft_out_reg(b, q)], j = b + q*BL
+#pragma unroll
+      for (int b = 0; b < BL; ++b)
+#pragma unroll
+        for (int q = 0; q < RL; ++q) {
+          const int j = b + q * BL;
+          const cpx r = v[fft_out_reg<PL>(b, q)];
+          const float w = wsm[t + j * T];
+          acc[j].x += r.y * w;
+          acc[j].y += r.x * w;
+        }
+      if (m >= ms) {
+        const int64_t pos = m * HOP + t;
+        const bool interior = m >= HOPDIV - 1;
+#pragma unroll
+        for (int j = 0; j < S; ++j) {
+          const float nr = interior ? normc[j] : norm_at(pos + j * T);
+          const float d = nr > 1.0e-10f ? nr : 1.0f;  // select(norm > 1e-10, norm, 1.0)
+          __stcs(yc + pos + j * T, make_float2(acc[j].x / d, acc[j].y / d));
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < P - S; ++j) acc[j] = acc[j + S];
+#pragma unroll
+      for (int j = P - S; j < P; ++j) acc[j] = make_float2(0.f, 0.f);
+    }
+    if (me == a.M) {  // tail of the channel: the N - hop samples no further frame completes
+      const int64_t pos = a.M * HOP + t;
+#pragma unroll
+      for (int j = 0; j < P - S; ++j) {
+        const float nr = norm_at(pos + j * T);
+        const float d = nr > 1.0e-10f ? nr : 1.0f;
+        __stcs(yc + pos + j * T, make_float2(acc[j].x / d, acc[j].y / d));
+      }
+    }
+    seg = nseg;
+    c = nc;
+    mb = nmb;
+    ms = nms;
+    me = nme;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // large fft_length (shared memory cannot hold frames + carry): inverse-transform frames with the
 // same engine into a scratch frame tensor; istft_ola_norm_kernel finishes.
 // ------------------------------------------------------------------------------------------
@@ -351,6 +524,58 @@ static int run_istft(nxs_ctx* ctx, IstftArgs a, int64_t channels, cudaStream_t s
   return NXS_OK;
 }
 
+// register overlap-add kernel: requires z_len == N, hop * HOPDIV == N, hop % T == 0 and 16-byte aligned rows
+template <class PL, int THREADS, int MINB, int HOPDIV>
+static int run_istft_rola(nxs_ctx* ctx, IstftArgs a, int64_t channels, cudaStream_t st) {
+  using CF = RolaCfg<PL, THREADS>;
+  float2* tw = nullptr;
+  int rc = get_tw_table<PL>(ctx, &tw);
+  if (rc) return rc;
+  a.tw = tw;
+  auto kern = istft_rola_kernel<PL, THREADS, MINB, HOPDIV>;
+  NXS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF::SMEM));
+  int occ = 1;
+  NXS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, CF::SMEM));
+  if (occ < 1) occ = 1;
+  // segments: a few per group so the tail is balanced; each costs HOPDIV-1 recomputed frames
+  const int64_t groups = int64_t(ctx->sm_count) * occ * CF::G;
+  const int64_t total_frames = channels * a.M;
+  int64_t seg = (total_frames + groups * 4 - 1) / (groups * 4);
+  const int64_t seg_min = 16 * (HOPDIV - 1) > 32 ? 16 * (HOPDIV - 1) : 32;
+  if (seg < seg_min) seg = seg_min;
+  if (seg > a.M) seg = a.M;
+  a.seg_frames = (int)seg;
+  a.segs_per_channel = (int)((a.M + seg - 1) / seg);
+  const int64_t total = int64_t(a.segs_per_channel) * channels;
+  if (total >= (int64_t(1) << 31)) return NXS_EUNSUPPORTED;
+  a.total_segs = (int)total;
+  a.warm_batches = 0;
+  int64_t grid = (total + CF::G - 1) / CF::G;
+  if (grid > int64_t(ctx->sm_count) * occ) grid = int64_t(ctx->sm_count) * occ;
+  prof_begin(ctx, st);
+  kern<<<(unsigned)grid, THREADS, CF::SMEM, st>>>(a);
+  prof_end(ctx, st);
+  ctx->launches++;
+  NXS_CUDA(ctx, cudaGetLastError());
+  return NXS_OK;
+}
+
+template <class PL, int THREADS, int MINB>
+static int try_istft_rola(nxs_ctx* ctx, const IstftArgs& a, int64_t channels, cudaStream_t st, bool* done) {
+  *done = false;
+  if (getenv("NXS_ISTFT_NO_ROLA")) return NXS_OK;
+  if (a.z_len != PL::N || (reinterpret_cast<uintptr_t>(a.z) & 15) != 0 || a.hop % PL::T != 0) return NXS_OK;
+  if (a.M >= (int64_t(1) << 40)) return NXS_OK;
+  *done = true;
+  if (a.hop * 2 == PL::N) return run_istft_rola<PL, THREADS, MINB, 2>(ctx, a, channels, st);
+  if (a.hop * 4 == PL::N) return run_istft_rola<PL, THREADS, MINB, 4>(ctx, a, channels, st);
+  if constexpr (PL::P >= 8) {
+    if (a.hop * 8 == PL::N) return run_istft_rola<PL, THREADS, MINB, 8>(ctx, a, channels, st);
+  }
+  *done = false;
+  return NXS_OK;
+}
+
 static int run_ola_norm(nxs_ctx* ctx, const float2* frames, int64_t channels, int64_t M, int64_t nfft, int64_t hop,
                         int64_t out_len, const float* window, float2* y, cudaStream_t st) {
   const int64_t total = channels * out_len;
@@ -410,6 +635,18 @@ int launch_istft(nxs_ctx* ctx, const float2* z, int64_t channels, int64_t num_fr
   a.seg_frames = a.segs_per_channel = a.total_segs = a.warm_batches = 0;
 
   const bool pow2 = (nfft & (nfft - 1)) == 0;
+  if (pow2 && nfft >= 256 && nfft <= 4096) {  // register overlap-add fast path (hop = N/2, N/4, N/8)
+    bool done = false;
+    switch (nfft) {
+      case 256: rc = try_istft_rola<Plan<256, 32, 8, 8, 4>, 256, 2>(ctx, a, channels, st, &done); break;
+      case 512: rc = try_istft_rola<Plan<512, 64, 8, 8, 8>, 256, 2>(ctx, a, channels, st, &done); break;
+      case 1024: rc = try_istft_rola<Plan<1024, 64, 16, 8, 8>, 256, 2>(ctx, a, channels, st, &done); break;
+      case 2048: rc = try_istft_rola<Plan<2048, 128, 16, 16, 8>, 256, 2>(ctx, a, channels, st, &done); break;
+      case 4096: rc = try_istft_rola<Plan<4096, 256, 16, 16, 16>, 512, 1>(ctx, a, channels, st, &done); break;
+      default: break;
+    }
+    if (rc || done) return rc;
+  }
   if (pow2 && nfft >= 32 && nfft <= 8192) {
     switch (nfft) {
       case 32: return run_istft<Plan<32, 4, 8, 4>, 128, 1>(ctx, a, channels, st);

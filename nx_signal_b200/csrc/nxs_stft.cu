@@ -18,6 +18,7 @@
 
 #include "nxs_common.cuh"
 #include "nxs_fft.cuh"
+#include "nxs_tma.cuh"
 
 namespace nxs {
 
@@ -180,40 +181,6 @@ __global__ void __launch_bounds__(THREADS) stft_r2c_kernel(const StftArgs a) {
 // overlap their FP and shared-memory phases.  Tiles that touch the padding region (or are
 // not 16-byte aligned) take the per-thread load path instead.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}\n" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-
-template <int T>
-struct GroupSync {
-  int id;
-  __device__ __forceinline__ void operator()() const {
-    if constexpr (T >= 32) asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(T) : "memory");
-    else __syncwarp();
-  }
-};
-
 // HOPDIV: the stage holds spans for hop <= nfft / HOPDIV; TWREG: twiddles in registers, else a
 // shared-memory copy of the per-pass table.
 // PERGROUP: every frame group stages its own frame (nfft floats, its own mbarrier pair) and

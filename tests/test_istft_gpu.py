@@ -170,3 +170,62 @@ def test_device_roundtrip_at_scale():
     d = ola_energy(nx.windows.hann(N), H, 40)[: 39 * H]
     cond = np.maximum(1.0, np.sqrt(0.01 * d.max() / np.where(d > 1e-10, d, 1.0)))
     assert (np.abs(got - yo[: 39 * H]) / cond).max() / np.abs(yo).max() <= TOL
+
+
+# ---- register overlap-add fast path (hop = N/2, N/4, N/8; z_len == N) --------------------------
+@pytest.mark.parametrize("nfft", [256, 512, 1024, 2048, 4096])
+@pytest.mark.parametrize("hopdiv", [2, 4, 8])
+@pytest.mark.parametrize("M", [1, 2, 5, 131])
+def test_rola_plans_hops_and_short_inputs(nfft, hopdiv, M):
+    rng = np.random.default_rng(nfft + 17 * hopdiv + M)
+    hop = nfft // hopdiv
+    C = 3 if M < 100 else 2
+    z = (rng.standard_normal((C, M, nfft)) + 1j * rng.standard_normal((C, M, nfft))).astype(np.complex64)
+    w = (o.hann(nfft) + np.float32(0.05)).astype(np.float32)
+    kw = dict(overlap_length=nfft - hop, fft_length=nfft)
+    y = nx.istft(z, w, **kw)
+    yo = o.istft_fast(z, w, **kw)
+    assert y.shape == (C, M * hop + nfft - hop)
+    assert rel(y, yo) <= TOL
+
+
+def test_rola_many_segments_matches_gather_kernel(monkeypatch):
+    """Enough frames that every group walks several segments (warm-up recompute at segment
+    starts, prefetch across segment and channel boundaries); the register overlap-add kernel
+    and the shared-memory gather kernel must agree to fp32 rounding, and both with the oracle."""
+    rng = np.random.default_rng(11)
+    C, M, nfft, hop = 5, 40_000, 1024, 256
+    import torch
+
+    z = torch.randn(C, M, nfft, 2, device="cuda", generator=torch.Generator(device="cuda").manual_seed(11))
+    z = torch.view_as_complex(z)
+    w = torch.from_numpy(o.hann(nfft)).cuda()
+    kw = dict(overlap_length=nfft - hop, fft_length=nfft)
+    y1 = nx.istft(z, w, **kw)
+    torch.cuda.synchronize()
+    monkeypatch.setenv("NXS_ISTFT_NO_ROLA", "1")
+    y2 = nx.istft(z, w, **kw)
+    torch.cuda.synchronize()
+    monkeypatch.delenv("NXS_ISTFT_NO_ROLA")
+    a, b = y1.cpu().numpy(), y2.cpu().numpy()
+    assert rel(a, b, o.hann(nfft), hop) <= 2e-6
+    # oracle on a slice that spans several segment boundaries of channel 3 (interior samples only)
+    m0, m1 = 17_000, 17_600
+    zs = z[3, m0:m1].cpu().numpy()
+    yo = o.istft_fast(zs, o.hann(nfft), **kw)
+    lo, hi = nfft, (m1 - m0) * hop - nfft  # samples fully covered by frames inside the slice
+    got = a[3, m0 * hop + lo: m0 * hop + hi]
+    assert np.abs(got - yo[lo:hi]).max() / np.abs(yo).max() <= TOL
+
+
+def test_rola_zero_window_guard_and_scaling():
+    rng = np.random.default_rng(12)
+    z = (rng.standard_normal((2, 40, 256)) + 1j * rng.standard_normal((2, 40, 256))).astype(np.complex64)
+    w = np.zeros(256, np.float32)
+    w[64:192] = o.hann(128)  # zero-energy positions at both ends of every hop of 128
+    for scaling in (None, "spectrum", "psd"):
+        kw = dict(overlap_length=128, fft_length=256, scaling=scaling, sampling_rate=8000)
+        y = nx.istft(z, w, **kw)
+        yo = o.istft_fast(z, w, **kw)
+        assert np.isfinite(y.view(np.float32)).all()
+        assert rel(y, yo, w, 128) <= TOL
