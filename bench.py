@@ -98,52 +98,73 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_port_rate(seconds_target, nthreads=0):
-    """Times the oracle's C port (the reference's algorithm restated, f64 recursive radix-2)
-    on a bounded sample of the same workload; returns (frames/s, cores, sample text)."""
-    from oracle import c_port
-    from oracle import nxsignal_oracle as o
-    from tests.util import synth
+def cpu_sample(frames, seed=1002):
+    """cfg2 channel-0 style input for `frames` frames, synthesised in f32 chunks (same recipe as
+    tests.util.synth: 0.25 N(0,1) + two tones) without the f64 temporaries of the test helper."""
+    n = frames * HOP + NFFT - HOP
+    rng = np.random.default_rng(seed)
+    x = np.empty((1, n), dtype=np.float32)
+    step = 1 << 22
+    for i in range(0, n, step):
+        j = min(n, i + step)
+        t = np.arange(i, j, dtype=np.float64) / FS
+        tone = 0.5 * np.sin(2 * np.pi * 440.0 * t) + 0.5 * np.sin(2 * np.pi * 3000.0 * t)
+        x[0, i:j] = 0.25 * rng.standard_normal(j - i, dtype=np.float32) + tone.astype(np.float32)
+    return x
 
-    w = o.hann(NFFT)
-    if nthreads <= 0:  # torchrun exports OMP_NUM_THREADS=1: use every core this process may run on
-        nthreads = len(os.sched_getaffinity(0))
-    cores = nthreads
-    cal_frames = 2048 * max(cores // 8, 1)
-    x = synth((1, cal_frames * HOP + NFFT - HOP), 1002)
-    t = time.perf_counter()
-    c_port.stft(x, w, HOP, NFFT, nthreads=nthreads)
-    rate = cal_frames / (time.perf_counter() - t)
-    frames = int(max(cal_frames, min(rate * seconds_target, 8_000_000)))
-    x = synth((1, frames * HOP + NFFT - HOP), 1002)
-    t = time.perf_counter()
-    z = c_port.stft(x, w, HOP, NFFT, nthreads=nthreads)
-    dt = time.perf_counter() - t
-    assert z.shape[1] == frames
-    return frames / dt, cores, f"{frames} frames of cfg2 channel 0 ({frames * HOP / FS:.0f} s of audio), {dt:.1f} s"
+
+class CpuPort:
+    """The oracle's C port (the reference's algorithm restated: f64 recursive radix-2, OpenMP over
+    frames) timed on a bounded sample of the workload.  The sample is built once, outside the
+    timed region; every step transforms the same `frames` frames."""
+
+    def __init__(self, nthreads=0):
+        from oracle import c_port
+        from oracle import nxsignal_oracle as o
+
+        self.c_port = c_port
+        self.w = o.hann(NFFT)
+        if nthreads <= 0:  # torchrun exports OMP_NUM_THREADS=1: use every core this process may run on
+            nthreads = len(os.sched_getaffinity(0))
+        self.cores = nthreads
+        # fixed sample: 2**18 frames (67 M samples in, 2.1 GB of spectrum out per step); the rate is
+        # size-independent beyond a few thousand frames, and the run time stays bounded on any host
+        self.frames = 1 << 18
+        self.x = cpu_sample(self.frames)
+        self.sample = ""
+        self.c_port.stft(self.x[:, : 4096 * HOP + NFFT], self.w, HOP, NFFT, nthreads=nthreads)  # start the threads
+
+    def step(self):
+        t = time.perf_counter()
+        z = self.c_port.stft(self.x, self.w, HOP, NFFT, nthreads=self.cores)
+        dt = time.perf_counter() - t
+        assert z.shape[1] == self.frames
+        self.sample = (f"{self.frames} frames of cfg2 channel 0 ({self.frames * HOP / FS:.0f} s of audio), "
+                       f"{dt:.2f} s per step")
+        return self.frames / dt, dt
 
 
 def run_reference(args, rank, world):
     """Reference arm: the reference's own CPU algorithm (Nx.BinaryBackend's recursive radix-2 in
-    f64, restated in C: oracle/nxs_oracle.c -- the BEAM cannot run here) on all host threads."""
+    f64, restated in C: oracle/nxs_oracle.c -- the BEAM cannot run here) on all host threads.
+    Each step is a bounded sample sized so the whole run stays within ~2 minutes."""
     if rank != 0:
         return
-    per_step = max(1.0, min(5.0, 120.0 / max(args.steps + args.warmup, 1)))
-    for _ in range(min(args.warmup, 1)):
-        cpu_port_rate(0.5)
-    rates, sample, cores = [], "", 1
-    t0 = time.perf_counter()
+    port = CpuPort()
+    for _ in range(args.warmup):
+        port.step()
+    rates, times = [], []
     for _ in range(args.steps):
-        r, cores, sample = cpu_port_rate(per_step)
+        r, dt = port.step()
         rates.append(r)
-    total = time.perf_counter() - t0
-    value = float(np.mean(rates))
+        times.append(dt)
+    value = float(port.frames * len(times) / sum(times)) if times else 0.0
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)) if times else None,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (rounded to f32/c64)",
-        "data": "synthetic", "config": {"workload": WORKLOAD, "sample_per_step": sample},
-        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "data": "synthetic", "config": {"workload": WORKLOAD, "sample_per_step": port.sample},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": port.cores, "kind": "port", "sample": port.sample},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -200,6 +221,8 @@ def main():
 
     x = make_input(torch, dev, 1002 + rank)
     z = torch.empty((CHANNELS, M, NFFT), dtype=torch.complex64, device=dev)
+    # host mirror threads of the _host entry: share the box's cores between the ranks
+    os.environ.setdefault("NXS_HOST_THREADS", str(max(2, len(os.sched_getaffinity(0)) // max(world, 1))))
     ctx = _lib.context(local_rank)
     lib = _lib.lib()
     stream = torch.cuda.current_stream(dev)
@@ -322,8 +345,14 @@ def main():
             traffic = None
     cpu = None
     if world == 1 and not args.no_cpu:
-        r, cores, sample = cpu_port_rate(12.0)
-        cpu = {"value": r, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample,
+        port = CpuPort()
+        port.step()
+        rs, t_end = [], time.perf_counter() + 10.0
+        while len(rs) < 3 or (time.perf_counter() < t_end and len(rs) < 40):
+            rs.append(port.step())
+        r = port.frames * len(rs) / sum(dt for _, dt in rs)
+        cpu = {"value": r, "unit": "frames/s", "cores": port.cores, "kind": "port",
+               "sample": port.sample + f", {len(rs)} steps",
                "note": "oracle/nxs_oracle.c: Nx.BinaryBackend's f64 recursive radix-2 restated in C + OpenMP; "
                        "the real BEAM backend cannot run here and is far slower"}
     line = {
