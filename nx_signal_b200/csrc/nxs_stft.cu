@@ -185,18 +185,24 @@ __global__ void __launch_bounds__(THREADS) stft_r2c_kernel(const StftArgs a) {
 // shared-memory copy of the per-pass table.
 // PERGROUP: every frame group stages its own frame (nfft floats, its own mbarrier pair) and
 // free-runs with no CTA-wide barrier; the nfft/hop-fold re-read of the input is served by L2.
-template <class PL_, int THREADS_, int HOPDIV_, bool TWREG_, bool PERGROUP_ = false>
+// LEAN (PERGROUP only): one stage buffer and one exchange buffer per group -- the next frame's
+// TMA is issued as soon as the group has read the stage into registers, so it still overlaps the
+// whole FFT; halves the shared memory of the large plans (2 CTAs/SM instead of 1) for one
+// extra group barrier per middle pass.
+template <class PL_, int THREADS_, int HOPDIV_, bool TWREG_, bool PERGROUP_ = false, bool LEAN_ = false>
 struct StagedCfg {
   using PL = PL_;
   static constexpr int THREADS = THREADS_, HOPDIV = HOPDIV_;
-  static constexpr bool TWREG = TWREG_, PERGROUP = PERGROUP_;
+  static constexpr bool TWREG = TWREG_, PERGROUP = PERGROUP_, LEAN = LEAN_;
+  static_assert(!LEAN || PERGROUP, "LEAN needs per-group staging");
   static constexpr int G = THREADS / PL::T, NFFT = 2 * PL::N;
+  static constexpr int NSTAGE = LEAN ? 1 : 2, NXBUF = LEAN ? 1 : 2;
   // floats per stage: one tile span, or G private frames
   static constexpr int STAGE = PERGROUP ? G * NFFT : NFFT + (G - 1) * (NFFT / HOPDIV);
-  static constexpr size_t BUF_BYTES = size_t(G) * 2 * PL::BUF * sizeof(cpx);
+  static constexpr size_t BUF_BYTES = size_t(G) * NXBUF * PL::BUF * sizeof(cpx);
   static constexpr size_t WIN_OFF = BUF_BYTES;
   static constexpr size_t STAGE_OFF = WIN_OFF + size_t(NFFT) * sizeof(float);
-  static constexpr size_t TW_OFF = STAGE_OFF + 2 * size_t(STAGE) * sizeof(float);
+  static constexpr size_t TW_OFF = STAGE_OFF + NSTAGE * size_t(STAGE) * sizeof(float);
   static constexpr size_t BAR_OFF = TW_OFF + (TWREG ? 0 : size_t(PL::TW_TOTAL) * sizeof(cpx));
   static constexpr size_t SMEM = BAR_OFF + 16 * (PERGROUP ? G : 1);
 };
@@ -213,8 +219,8 @@ __global__ void __launch_bounds__(CF::THREADS, MINB) stft_r2c_staged_kernel(cons
   static_assert(THREADS % T == 0 && P >= 2 && G <= 15, "bad plan");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, g = tid / T, t = tid % T;
-  cpx* bufA = reinterpret_cast<cpx*>(smem_raw) + (size_t)(2 * g) * PL::BUF;
-  cpx* bufB = bufA + PL::BUF;
+  cpx* bufA = reinterpret_cast<cpx*>(smem_raw) + (size_t)(CF::NXBUF * g) * PL::BUF;
+  cpx* bufB = CF::LEAN ? bufA : bufA + PL::BUF;
   float* wsm = reinterpret_cast<float*>(smem_raw + CF::WIN_OFF);
   float* stage0 = reinterpret_cast<float*>(smem_raw + CF::STAGE_OFF);
   const uint32_t bar0 = smem_u32(smem_raw + CF::BAR_OFF);
@@ -274,11 +280,13 @@ __global__ void __launch_bounds__(CF::THREADS, MINB) stft_r2c_staged_kernel(cons
   int tile = blockIdx.x;
   if (tile < total_tiles && issuer) issue(tile, 0);
   for (int it = 0; tile < total_tiles; tile += gridDim.x, ++it) {
-    const int stage = it & 1;
+    const int stage = CF::LEAN ? 0 : (it & 1);
     // stage^1 was last read in iteration it-1: PERGROUP -- this group's threads all passed that
     // iteration's barriers before the issuer gets here; else a CTA-wide barrier says so
     if constexpr (!CF::PERGROUP) __syncthreads();
-    if (issuer && tile + (int)gridDim.x < total_tiles) issue(tile + gridDim.x, stage ^ 1);
+    if constexpr (!CF::LEAN) {
+      if (issuer && tile + (int)gridDim.x < total_tiles) issue(tile + gridDim.x, stage ^ 1);
+    }
 
     int c, m0, gact;
     int64_t src0;
@@ -323,7 +331,16 @@ __global__ void __launch_bounds__(CF::THREADS, MINB) stft_r2c_staged_kernel(cons
       for (int i = 0; i < P; ++i) v[i] = make_float2(0.f, 0.f);
     }
 
-    block_fft<PL>(v, t, bufA, bufB, tw, sync);
+    if constexpr (CF::LEAN) {
+      // the group has read its stage (and finished the previous frame's post-pass reads of the
+      // exchange buffer): refill the stage with the next frame while this one is transformed
+      sync();
+      if (issuer && tile + (int)gridDim.x < total_tiles) issue(tile + gridDim.x, 0);
+      block_fft_single<PL>(v, t, bufA, tw, sync);
+      sync();  // last pass's reads done before the post-pass reuses the buffer
+    } else {
+      block_fft<PL>(v, t, bufA, bufB, tw, sync);
+    }
 
     cpx* pb = ((PL::NP - 1) & 1) ? bufB : bufA;
 #pragma unroll
@@ -353,7 +370,7 @@ __global__ void __launch_bounds__(CF::THREADS, MINB) stft_r2c_staged_kernel(cons
         }
       }
     }
-    if constexpr (PL::NP & 1) {
+    if constexpr ((PL::NP & 1) && !CF::LEAN) {
       cpx* tmp = bufA;
       bufA = bufB;
       bufB = tmp;
@@ -512,7 +529,7 @@ static int variant_env() {
 template <class CF>
 static bool staged_ok(const StftArgs& a, int64_t channels) {
   const int64_t tiles = ((a.M + CF::G - 1) / CF::G) * channels;
-  return a.nload == CF::NFFT && a.hop % 4 == 0 && a.hop <= CF::NFFT / CF::HOPDIV && a.pad_lo % 4 == 0 && a.x_ld % 4 == 0 &&
+  return a.nload == CF::NFFT && a.hop % 4 == 0 && (CF::PERGROUP || a.hop <= CF::NFFT / CF::HOPDIV) && a.pad_lo % 4 == 0 && a.x_ld % 4 == 0 &&
          (reinterpret_cast<uintptr_t>(a.x) & 15) == 0 && tiles < (int64_t(1) << 30) &&
          CF::SMEM <= 231424;
 }
@@ -584,22 +601,30 @@ int launch_stft(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, 
         if (variant == 1) { using CF = StagedCfg<PL, 256, 2, true, false>; NXS_TRY_STAGED(CF, 2); }
         if (variant == 2) { using CF = StagedCfg<PL, 512, 2, true, true>; NXS_TRY_STAGED(CF, 1); }
         if (variant == 3) { using CF = StagedCfg<PL, 128, 2, true, true>; NXS_TRY_STAGED(CF, 4); }
+        if (variant == 4) { using CF = StagedCfg<PL, 256, 2, true, true, true>; NXS_TRY_STAGED(CF, 2); }
         { using CF = StagedCfg<PL, 256, 2, true, true>; NXS_TRY_STAGED(CF, 2); }
         return run_r2c<PL, TwRegs<PL>, 512>(ctx, a, st);
       }
       case 2048: {
         using PL = Plan<1024, 64, 16, 8, 8>;
         if (variant_env() == 1) { using CF = StagedCfg<PL, 512, 2, false, false>; NXS_TRY_STAGED(CF, 1); }
-        { using CF = StagedCfg<PL, 256, 2, false, true>; NXS_TRY_STAGED(CF, 2); }
+        if (variant_env() == 2) { using CF = StagedCfg<PL, 256, 2, false, true>; NXS_TRY_STAGED(CF, 2); }
+        { using CF = StagedCfg<PL, 256, 2, false, true, true>; NXS_TRY_STAGED(CF, 2); }
         return run_r2c<PL, TwTable<PL>, 512>(ctx, a, st);
       }
       case 4096: {
         using PL = Plan<2048, 128, 16, 16, 8>;
         if (variant_env() == 1) { using CF = StagedCfg<PL, 512, 4, false, false>; NXS_TRY_STAGED(CF, 1); }
-        { using CF = StagedCfg<PL, 256, 4, false, true>; NXS_TRY_STAGED(CF, 1); }
+        if (variant_env() == 2) { using CF = StagedCfg<PL, 256, 4, false, true>; NXS_TRY_STAGED(CF, 1); }
+        if (variant_env() == 3) { using CF = StagedCfg<PL, 512, 4, false, true, true>; NXS_TRY_STAGED(CF, 1); }
+        { using CF = StagedCfg<PL, 256, 4, false, true, true>; NXS_TRY_STAGED(CF, 2); }
         return run_r2c<PL, TwTable<PL>, 512>(ctx, a, st);
       }
-      case 8192: return run_r2c<Plan<4096, 256, 16, 16, 16>, TwTable<Plan<4096, 256, 16, 16, 16>>, 512>(ctx, a, st);
+      case 8192: {
+        using PL = Plan<4096, 256, 16, 16, 16>;
+        if (variant_env() != 1) { using CF = StagedCfg<PL, 512, 4, false, true, true>; NXS_TRY_STAGED(CF, 1); }
+        return run_r2c<PL, TwTable<PL>, 512>(ctx, a, st);
+      }
       case 16384:
         return run_r2c<Plan<8192, 512, 16, 16, 16, 2>, TwTable<Plan<8192, 512, 16, 16, 16, 2>>, 512>(ctx, a, st);
       default: break;

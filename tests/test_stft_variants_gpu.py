@@ -1,7 +1,5 @@
 """Every STFT kernel variant selectable by NXS_STFT_VARIANT gives the same results as the default
 (parity of tuning variants; the default is what ships)."""
-import os
-
 import numpy as np
 import pytest
 
@@ -12,13 +10,27 @@ from tests.util import TOL, frame_rel_err, synth
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("variant", ["0", "1", "2", "3"])
+@pytest.mark.parametrize("nfft,variant", [(1024, v) for v in "01234"] + [(2048, v) for v in "012"] +
+                         [(4096, v) for v in "0123"] + [(8192, v) for v in "01"])
 @pytest.mark.parametrize("padding", ["valid", "reflect"])
-def test_variant_parity(variant, padding, monkeypatch):
+def test_variant_parity(nfft, variant, padding, monkeypatch):
     monkeypatch.setenv("NXS_STFT_VARIANT", variant)
-    x = synth((3, 50_000), 31)
-    w = o.hann(1024)
-    kw = dict(overlap_length=768, fft_length=1024, sampling_rate=48000, window_padding=padding)
+    x = synth((3, 40 * nfft + 808), 31)
+    w = o.hann(nfft)
+    kw = dict(overlap_length=nfft - nfft // 4, fft_length=nfft, sampling_rate=48000, window_padding=padding)
+    z, _, _ = nx.stft(x, w, **kw)
+    zo, _, _ = o.stft_fast(x, w, **kw)
+    assert frame_rel_err(z, zo) <= TOL
+
+
+@pytest.mark.parametrize("nfft", [512, 1024, 2048, 4096, 8192])
+@pytest.mark.parametrize("hop_num,hop_den", [(1, 1), (1, 2), (3, 4), (1, 16)])
+def test_staged_hops(nfft, hop_num, hop_den):
+    """Per-group staging serves any hop that keeps frame starts 16-byte aligned, including no overlap."""
+    hop = nfft * hop_num // hop_den
+    x = synth((2, 23 * nfft + 4 * 77), 41 + nfft)
+    w = o.hann(nfft)
+    kw = dict(overlap_length=nfft - hop, fft_length=nfft, sampling_rate=48000)
     z, _, _ = nx.stft(x, w, **kw)
     zo, _, _ = o.stft_fast(x, w, **kw)
     assert frame_rel_err(z, zo) <= TOL
