@@ -14,6 +14,7 @@
 //   out : y[expand(j) + q*NS],  expand(j) = (j/NS)*NS*R + (j mod NS)
 #pragma once
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 
 namespace nxs {
@@ -111,6 +112,13 @@ struct Plan {
     return o;
   }
   static constexpr int TW_TOTAL = twOffset(NP);
+  // compact table (TwDeriveC): only the power-of-two rows W^(2^r k), r < log2 R, per pass
+  static constexpr int twcOffset(int p) {
+    int o = 0;
+    for (int i = 1; i < p; ++i) o += ilog2(R(i)) * NS(i);
+    return o;
+  }
+  static constexpr int TWC_TOTAL = twcOffset(NP);
   // number of distinct twiddle sets a thread needs in pass p (1 when k = t mod NS for every b)
   static constexpr int twSets(int p) { return (T_ % NS(p) == 0) ? 1 : (P / R(p)); }
   static constexpr int twRegOffset(int p) {
@@ -151,6 +159,11 @@ struct TwRegs {
     constexpr int R = PL::R(PASS), SETS = PL::twSets(PASS);
     return w[PL::twRegOffset(PASS) + (SETS == 1 ? 0 : b) * (R - 1) + q - 1];
   }
+  template <int PASS>
+  __device__ __forceinline__ void fill(int b, int k, cpx* out) const {
+#pragma unroll
+    for (int q = 1; q < PL::R(PASS); ++q) out[q] = get<PASS>(b, q, k);
+  }
 };
 
 // Twiddles read from a table (shared or global memory) on every use.
@@ -162,7 +175,86 @@ struct TwTable {
   __device__ __forceinline__ cpx get(int /*b*/, int q, int k) const {
     return tab[PL::twOffset(PASS) + (q - 1) * PL::NS(PASS) + k];
   }
+  // w[q] = W^(q k), q = 1 .. R-1
+  template <int PASS>
+  __device__ __forceinline__ void fill(int b, int k, cpx* w) const {
+#pragma unroll
+    for (int q = 1; q < PL::R(PASS); ++q) w[q] = get<PASS>(b, q, k);
+  }
 };
+
+// Twiddles derived from the table's power-of-two entries: W^k, W^2k, W^4k (and W^8k for radix
+// 16) are loaded, the other powers are their products -- 3-4 shared-memory loads per butterfly
+// instead of 7-15, paid for with complex multiplies on the (under-used) FMA pipe.  The shared-
+// memory pipe is what bounds the large plans (ncu: LSU wavefronts ~80 % of peak).
+template <class PL>
+struct TwDerive {
+  const cpx* tab;
+  __device__ __forceinline__ void init(const cpx* t_, int) { tab = t_; }
+  template <int PASS>
+  __device__ __forceinline__ void fill(int /*b*/, int k, cpx* w) const {
+    constexpr int R = PL::R(PASS), NS = PL::NS(PASS);
+    const cpx* base = tab + PL::twOffset(PASS) + k;
+    w[1] = base[0];
+    if constexpr (R >= 4) {
+      w[2] = base[1 * NS];
+      w[3] = cmul(w[1], w[2]);
+    }
+    if constexpr (R >= 8) {
+      w[4] = base[3 * NS];
+      w[5] = cmul(w[4], w[1]);
+      w[6] = cmul(w[4], w[2]);
+      w[7] = cmul(w[4], w[3]);
+    }
+    if constexpr (R >= 16) {
+      w[8] = base[7 * NS];
+#pragma unroll
+      for (int q = 1; q < 8; ++q) w[8 + q] = cmul(w[8], w[q]);
+    }
+  }
+};
+
+// TwDerive over the compact table layout [pass][r = log2 q][k] (Plan::twcOffset): a quarter of
+// the full table's shared memory for radix 16.
+template <class PL>
+struct TwDeriveC {
+  const cpx* tab;
+  __device__ __forceinline__ void init(const cpx* t_, int) { tab = t_; }
+  template <int PASS>
+  __device__ __forceinline__ void fill(int /*b*/, int k, cpx* w) const {
+    constexpr int R = PL::R(PASS), NS = PL::NS(PASS);
+    const cpx* base = tab + PL::twcOffset(PASS) + k;
+    w[1] = base[0];
+    if constexpr (R >= 4) {
+      w[2] = base[1 * NS];
+      w[3] = cmul(w[1], w[2]);
+    }
+    if constexpr (R >= 8) {
+      w[4] = base[2 * NS];
+      w[5] = cmul(w[4], w[1]);
+      w[6] = cmul(w[4], w[2]);
+      w[7] = cmul(w[4], w[3]);
+    }
+    if constexpr (R >= 16) {
+      w[8] = base[3 * NS];
+#pragma unroll
+      for (int q = 1; q < 8; ++q) w[8 + q] = cmul(w[8], w[q]);
+    }
+  }
+};
+
+// host: fills the compact table, tw[twcOffset(p) + r*NS + k] = exp(-2 pi i 2^r k / (NS R))
+template <class PL>
+inline void build_compact_twiddles(cpx* tw) {
+  for (int p = 1; p < PL::NP; ++p) {
+    const int R = PL::R(p), NS = PL::NS(p);
+    for (int r = 0; (1 << r) < R; ++r)
+      for (int k = 0; k < NS; ++k) {
+        const double ang = -2.0 * 3.14159265358979323846 * double(1 << r) * double(k) / double(NS * R);
+        tw[PL::twcOffset(p) + r * NS + k] = make_float2((float)cos(ang), (float)sin(ang));
+      }
+  }
+}
 
 struct SyncBlock {
   __device__ __forceinline__ void operator()() const { __syncthreads(); }
@@ -212,8 +304,10 @@ struct PassRunner {
 #pragma unroll
       for (int b = 0; b < B; ++b) {
         const int k = (t + b * T) % NS;
+        cpx w[R];
+        tw.template fill<PASS>(b, k, w);
 #pragma unroll
-        for (int q = 1; q < R; ++q) v[b * R + q] = cmul(v[b * R + q], tw.template get<PASS>(b, q, k));
+        for (int q = 1; q < R; ++q) v[b * R + q] = cmul(v[b * R + q], w[q]);
       }
     }
 #pragma unroll

@@ -14,9 +14,11 @@
 // register file except for the in-FFT exchanges.  `mode` only shifts the output window:
 // full 0, same (K-1)/2, valid min(L,K)-1 (convolution.ex:300-329).
 #include <math.h>
+#include <stdlib.h>
 
 #include "nxs_common.cuh"
 #include "nxs_fft.cuh"
+#include "nxs_tma.cuh"
 
 namespace nxs {
 
@@ -128,6 +130,147 @@ __global__ void __launch_bounds__(THREADS, MINB) fir_ols_kernel(const FirArgs a)
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Per-group variant (the hot path for K > 129): every group of T threads walks its own block
+// pairs with no CTA-wide barrier.  The pair's input span (V + F samples, contiguous) arrives by
+// one cp.async.bulk (TMA 1-D, from the 16-byte-aligned address below the span) into the group's
+// stage buffer, re-issued for the next pair as soon as this pair has been read into registers.
+// One exchange buffer per group, H / F and the compact twiddle table (power-of-two rows, the
+// other twiddles are products) in shared memory: the kernel is bounded by the shared-memory
+// pipe, so every table load saved is time saved.
+// ------------------------------------------------------------------------------------------
+template <class PL, int THREADS>
+struct FirPgCfg {
+  static constexpr int F = PL::N, G = THREADS / PL::T;
+  // the stage holds one pair's span: V + F samples plus alignment slack (a multiple of 4 floats)
+  static __host__ __device__ int stage_floats(int V) { return (V + F + 3 + 3) / 4 * 4 + 4; }
+  static __host__ __device__ size_t group_bytes(int V) {
+    return size_t(stage_floats(V)) * sizeof(float) + size_t(PL::BUF) * sizeof(cpx);
+  }
+  static __host__ __device__ size_t h_off(int V) { return size_t(G) * group_bytes(V); }
+  static __host__ __device__ size_t tw_off(int V) { return h_off(V) + size_t(F) * sizeof(cpx); }
+  static __host__ __device__ size_t bar_off(int V) { return tw_off(V) + size_t(PL::TWC_TOTAL) * sizeof(cpx); }
+  static __host__ __device__ size_t smem(int V) { return bar_off(V) + 8 * size_t(G) + 8; }
+};
+
+template <class PL, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) fir_ols_pg_kernel(const FirArgs a, const int aligned_rows) {
+  using CF = FirPgCfg<PL, THREADS>;
+  constexpr int F = PL::N, T = PL::T, P = PL::P, G = CF::G;
+  constexpr int R0 = PL::R(0), B0 = P / R0;
+  constexpr int RL = PL::R(PL::NP - 1);
+  static_assert(R0 == RL, "FIR plans must be palindromic (first radix == last radix)");
+  static_assert(T >= 32, "per-group barriers need whole warps");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tid = threadIdx.x, g = tid / T, t = tid % T;
+  float* const stage = reinterpret_cast<float*>(smem_raw + size_t(g) * CF::group_bytes(a.V));
+  cpx* const xbuf = reinterpret_cast<cpx*>(smem_raw + size_t(g) * CF::group_bytes(a.V) +
+                                           size_t(CF::stage_floats(a.V)) * sizeof(float));
+  cpx* const Hs = reinterpret_cast<cpx*>(smem_raw + CF::h_off(a.V));
+  cpx* const twsm = reinterpret_cast<cpx*>(smem_raw + CF::tw_off(a.V));
+  const uint32_t mybar = smem_u32(smem_raw + CF::bar_off(a.V)) + 8 * g;
+  for (int i = tid; i < F; i += THREADS) Hs[i] = a.H[i];
+  for (int i = tid; i < PL::TWC_TOTAL; i += THREADS) twsm[i] = a.tw[i];
+  if (tid == 0) {
+    for (int i = 0; i < G; ++i) mbar_init(smem_u32(smem_raw + CF::bar_off(a.V)) + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  TwDeriveC<PL> tw;
+  tw.init(twsm, t);
+  const GroupSync<T> sync{1 + g};
+  const int K1 = a.K - 1;
+
+  // geometry of a block pair; returns whether its span can be staged by TMA
+  auto geom = [&](int tile, int& c, int64_t& n0, int64_t& s0a, int& off, uint32_t& bytes) {
+    c = tile / a.pairs_per_channel;
+    const int pi = tile - c * a.pairs_per_channel;
+    n0 = (a.b_lo + 2 * (int64_t)pi) * a.V;
+    const int64_t s0 = n0 - K1;
+    s0a = s0 & ~(int64_t)3;  // floor to a multiple of 4 samples (also for negative s0)
+    off = (int)(s0 - s0a);
+    const int len4 = (off + a.V + F + 3) & ~3;
+    bytes = (uint32_t)len4 * (uint32_t)sizeof(float);
+    return aligned_rows && s0a >= 0 && s0a + len4 <= a.L;
+  };
+  auto issue = [&](int tile) {
+    int c, off;
+    int64_t n0, s0a;
+    uint32_t bytes;
+    if (geom(tile, c, n0, s0a, off, bytes)) {
+      mbar_expect_tx(mybar, bytes);
+      tma_load_1d(smem_u32(stage), a.x + (int64_t)c * a.x_ld + s0a, bytes, mybar);
+    }
+  };
+
+  const int gid = blockIdx.x * G + g, ngroups = gridDim.x * G;
+  uint32_t parity = 0;
+  int tile = gid;
+  if (tile < a.total_tiles && t == 0) issue(tile);
+  for (; tile < a.total_tiles; tile += ngroups) {
+    int c, off;
+    int64_t n0, s0a;
+    uint32_t bytes;
+    const bool staged = geom(tile, c, n0, s0a, off, bytes);
+    cpx v[P];
+    if (staged) {
+      mbar_wait(mybar, parity);
+      parity ^= 1;
+      const float* __restrict__ p0 = stage + off;
+      const float* __restrict__ p1 = p0 + a.V;
+#pragma unroll
+      for (int b = 0; b < B0; ++b)
+#pragma unroll
+        for (int q = 0; q < R0; ++q) {
+          const int i = fft_in_index<PL>(t, b, q);
+          v[b * R0 + q] = make_float2(p0[i], p1[i]);
+        }
+    } else {
+      const float* __restrict__ xrow = a.x + (int64_t)c * a.x_ld;
+      const int64_t s0 = n0 - K1, s1 = s0 + a.V;
+#pragma unroll
+      for (int b = 0; b < B0; ++b)
+#pragma unroll
+        for (int q = 0; q < R0; ++q) {
+          const int i = fft_in_index<PL>(t, b, q);
+          const int64_t i0 = s0 + i, i1 = s1 + i;
+          float re = 0.f, im = 0.f;
+          if (i0 >= 0 && i0 < a.L) re = __ldg(xrow + i0);
+          if (i1 >= 0 && i1 < a.L) im = __ldg(xrow + i1);
+          v[b * R0 + q] = make_float2(re, im);
+        }
+    }
+    sync();  // stage read out; the previous pair's last exchange reads are done
+    if (t == 0 && tile + ngroups < a.total_tiles) issue(tile + ngroups);
+    block_fft_single<PL>(v, t, xbuf, tw, sync);
+    // pointwise multiply by H / F; palindromic plan: output register (b, q) is input register (b, q)
+    cpx u[P];
+#pragma unroll
+    for (int b = 0; b < B0; ++b)
+#pragma unroll
+      for (int q = 0; q < R0; ++q) {
+        const int k = fft_out_index<PL>(t, b, q);
+        const cpx yk = cmul(v[fft_out_reg<PL>(b, q)], Hs[k]);
+        u[b * R0 + q] = make_float2(yk.y, yk.x);  // swap for the inverse transform
+      }
+    sync();  // forward transform's last exchange fully consumed before the inverse reuses the buffer
+    block_fft_single<PL>(u, t, xbuf, tw, sync);
+    float* __restrict__ yrow = a.y + (int64_t)c * a.y_ld;
+#pragma unroll
+    for (int b = 0; b < B0; ++b)
+#pragma unroll
+      for (int q = 0; q < R0; ++q) {
+        const int i = fft_out_index<PL>(t, b, q);
+        if (i >= K1) {
+          const cpx r = u[fft_out_reg<PL>(b, q)];
+          const int64_t o0 = n0 + (i - K1) - a.start, o1 = o0 + a.V;
+          if (o0 >= 0 && o0 < a.out_len) __stcs(yrow + o0, r.y);  // Re(y): block 0
+          if (o1 >= 0 && o1 < a.out_len) __stcs(yrow + o1, r.x);  // Im(y): block 1
+        }
+      }
+  }
+}
+
 template <class PL>
 static int fir_tw_table(nxs_ctx* ctx, float2** out) {
   const uint64_t key = (uint64_t(PL::N) << 32) | (uint64_t(PL::T) << 8) | uint64_t(PL::NP) | (uint64_t(2) << 62) |
@@ -193,6 +336,67 @@ static int run_fir(nxs_ctx* ctx, FirArgs a, int64_t channels, const float* taps,
   return NXS_OK;
 }
 
+template <class PL>
+static int fir_twc_table(nxs_ctx* ctx, float2** out) {
+  const uint64_t key = (uint64_t(PL::N) << 32) | (uint64_t(PL::T) << 8) | uint64_t(PL::NP) | (uint64_t(3) << 62) |
+                       (uint64_t(PL::R(0)) << 20);
+  auto it = ctx->tables.find(key);
+  if (it != ctx->tables.end()) {
+    *out = it->second.tw;
+    return NXS_OK;
+  }
+  std::vector<float2> tw(PL::TWC_TOTAL > 0 ? PL::TWC_TOTAL : 1);
+  build_compact_twiddles<PL>(tw.data());
+  PlanTables t;
+  NXS_CUDA(ctx, cudaMalloc(&t.tw, tw.size() * sizeof(float2)));
+  NXS_CUDA(ctx, cudaMemcpy(t.tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+  ctx->tables[key] = t;
+  *out = t.tw;
+  return NXS_OK;
+}
+
+template <class PL, int THREADS, int MINB>
+static int run_fir_pg(nxs_ctx* ctx, FirArgs a, int64_t channels, const float* taps, cudaStream_t st) {
+  using CF = FirPgCfg<PL, THREADS>;
+  constexpr int F = PL::N;
+  float2* tw = nullptr;
+  int rc = fir_twc_table<PL>(ctx, &tw);
+  if (rc) return rc;
+  a.tw = tw;
+  rc = ensure_scratch(ctx, size_t(F) * sizeof(float2));
+  if (rc) return rc;
+  fir_spectrum_kernel<<<(F + 255) / 256, 256, 0, st>>>(taps, a.K, F, (float2*)ctx->d_scratch);
+  ctx->launches++;
+  NXS_CUDA(ctx, cudaGetLastError());
+  a.H = (const float2*)ctx->d_scratch;
+  a.V = F - a.K + 1;
+  a.b_lo = a.start / a.V;
+  const int64_t b_hi = (a.start + a.out_len - 1) / a.V;
+  const int64_t pairs = (b_hi - a.b_lo + 2) / 2;
+  const int64_t tiles = pairs * channels;
+  if (tiles >= (int64_t(1) << 31)) return NXS_EUNSUPPORTED;
+  a.pairs_per_channel = (int)pairs;
+  a.total_tiles = (int)tiles;
+  auto kern = fir_ols_pg_kernel<PL, THREADS, MINB>;
+  const size_t smem = CF::smem(a.V);
+  if (smem > 232448) return NXS_EUNSUPPORTED;
+  NXS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 1;
+  NXS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
+  if (occ < 1) occ = 1;
+  int64_t grid = int64_t(ctx->sm_count) * occ;
+  const int64_t need = (tiles + CF::G - 1) / CF::G;
+  if (grid > need) grid = need;
+  // TMA needs 16-byte aligned spans: row starts aligned (the kernel floors each span's start itself)
+  const int aligned_rows = (reinterpret_cast<uintptr_t>(a.x) & 15) == 0 && a.x_ld % 4 == 0;
+  prof_begin(ctx, st);
+  kern<<<(unsigned)grid, THREADS, smem, st>>>(a, aligned_rows);
+  prof_end(ctx, st);
+  ctx->launches++;
+  NXS_CUDA(ctx, cudaGetLastError());
+  return NXS_OK;
+}
+
 // short filters / very long filters: direct summation, one thread per output (fp32 FMA chain in
 // ascending tap order)
 __global__ void __launch_bounds__(256) fir_direct_kernel(const float* __restrict__ x, int64_t channels, int64_t L,
@@ -237,8 +441,22 @@ int launch_fir(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, i
   a.tw = nullptr;
   const int64_t K = num_taps;
   if (K >= 16 && K <= 129) return run_fir<Plan<256, 16, 16, 16>, 256, 2>(ctx, a, channels, taps, st);
-  if (K > 129 && K <= 513) return run_fir<Plan<1024, 64, 8, 16, 8>, 256, 2>(ctx, a, channels, taps, st);
-  if (K > 513 && K <= 3585) return run_fir<Plan<4096, 256, 16, 16, 16>, 256, 2>(ctx, a, channels, taps, st);
+  const bool pg = !getenv("NXS_FIR_NO_PG");
+  const char* var = getenv("NXS_FIR_VARIANT");  // tuning variants (tests/test_fir_conv_gpu.py)
+  const int variant = var ? atoi(var) : 0;
+  if (K > 129 && K <= 513) {
+    if (pg && variant == 1) return run_fir_pg<Plan<1024, 64, 8, 16, 8>, 256, 2>(ctx, a, channels, taps, st);
+    if (pg) return run_fir_pg<Plan<1024, 64, 8, 16, 8>, 384, 2>(ctx, a, channels, taps, st);
+    return run_fir<Plan<1024, 64, 8, 16, 8>, 256, 2>(ctx, a, channels, taps, st);
+  }
+  if (K > 513 && K <= 3585) {
+    using PL = Plan<4096, 256, 16, 16, 16>;
+    // three groups per SM when the stage (V + F samples) is small enough, else two
+    const bool three = FirPgCfg<PL, 768>::smem(int(4096 - K + 1)) <= 232448;
+    if (pg && variant != 1 && three) return run_fir_pg<PL, 768, 1>(ctx, a, channels, taps, st);
+    if (pg) return run_fir_pg<PL, 512, 1>(ctx, a, channels, taps, st);
+    return run_fir<Plan<4096, 256, 16, 16, 16>, 256, 2>(ctx, a, channels, taps, st);
+  }
   // K < 16 or K > 3585: direct
   if (K > (int64_t(1) << 30)) return NXS_EUNSUPPORTED;
   const int64_t total = channels * out_len;

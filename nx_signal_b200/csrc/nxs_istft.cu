@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(THREADS, MINB) istft_rola_kernel(const IstftAr
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  TwTable<PL> tw;
+  TwDerive<PL> tw;
   tw.init(twsm, t);
   const GroupSync<T> sync{1 + g};
 

@@ -211,7 +211,7 @@ template <class CF, int MINB, bool ONESIDED>
 __global__ void __launch_bounds__(CF::THREADS, MINB) stft_r2c_staged_kernel(const StftArgs a, const int tpc,
                                                                             const int total_tiles) {
   using PL = typename CF::PL;
-  using TW = typename std::conditional<CF::TWREG, TwRegs<PL>, TwTable<PL>>::type;
+  using TW = typename std::conditional<CF::TWREG, TwRegs<PL>, TwDerive<PL>>::type;
   constexpr int THREADS = CF::THREADS;
   constexpr int N = PL::N, T = PL::T, P = PL::P, G = CF::G, NFFT = 2 * N;
   constexpr int R0 = PL::R(0), B0 = P / R0;

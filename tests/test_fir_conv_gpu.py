@@ -163,3 +163,32 @@ def test_fir_linearity_and_device_entry_at_scale():
     # spot check against double on one channel's window
     want = ref_conv(a[0:1, :50_000].cpu().numpy(), taps.cpu().numpy(), "same")[:, :40_000]
     assert rel(ya[0:1, :40_000].cpu().numpy(), want) <= TOL
+
+
+# ---- per-group (TMA-staged) overlap-save kernel: alignment cases, variants, old-kernel agreement ----
+@pytest.mark.parametrize("K", [130, 513, 514, 2049, 3585])
+@pytest.mark.parametrize("L", [65_536, 65_537, 50_002])
+@pytest.mark.parametrize("variant", ["0", "1"])
+def test_fir_pg_alignment_and_variants(K, L, variant, monkeypatch):
+    """L % 4 == 0 rows are staged by TMA (spans start at arbitrary sample offsets: the kernel floors
+    them to 16 bytes), other row strides take the per-thread load path of the same kernel."""
+    monkeypatch.setenv("NXS_FIR_VARIANT", variant)
+    x = synth((3, L), K + L)
+    rng = np.random.default_rng(K + 1)
+    taps = (rng.standard_normal(K) / np.sqrt(K)).astype(np.float32)
+    for mode in ("same", "full", "valid"):
+        y = conv.convolve(x, taps[None, :], mode=mode, method="fft")
+        assert rel(y, ref_conv(x, taps, mode)) <= TOL
+
+
+def test_fir_pg_matches_previous_kernel(monkeypatch):
+    import torch
+
+    taps = torch.from_numpy(nx.filters.firwin(2049, [6000], sampling_rate=48000)).cuda()
+    x = torch.randn(5, 1_000_000, device="cuda", generator=torch.Generator(device="cuda").manual_seed(9))
+    y1 = conv.convolve(x, taps[None, :], mode="same", method="fft")
+    torch.cuda.synchronize()
+    monkeypatch.setenv("NXS_FIR_NO_PG", "1")
+    y2 = conv.convolve(x, taps[None, :], mode="same", method="fft")
+    torch.cuda.synchronize()
+    assert float((y1 - y2).abs().max() / y2.abs().max()) <= 2e-6
