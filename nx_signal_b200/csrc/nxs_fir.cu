@@ -256,18 +256,36 @@ __global__ void __launch_bounds__(THREADS, MINB) fir_ols_pg_kernel(const FirArgs
     sync();  // forward transform's last exchange fully consumed before the inverse reuses the buffer
     block_fft_single<PL>(u, t, xbuf, tw, sync);
     float* __restrict__ yrow = a.y + (int64_t)c * a.y_ld;
+    const int64_t obase = n0 - K1 - a.start;  // output index of FFT sample i is obase + i (block 0)
+    if (obase + K1 >= 0 && obase + F + a.V <= a.out_len) {
+      // interior pair: every kept sample of both blocks lands inside the row
+      float* __restrict__ y0 = yrow + obase;
+      float* __restrict__ y1 = y0 + a.V;
 #pragma unroll
-    for (int b = 0; b < B0; ++b)
+      for (int b = 0; b < B0; ++b)
 #pragma unroll
-      for (int q = 0; q < R0; ++q) {
-        const int i = fft_out_index<PL>(t, b, q);
-        if (i >= K1) {
-          const cpx r = u[fft_out_reg<PL>(b, q)];
-          const int64_t o0 = n0 + (i - K1) - a.start, o1 = o0 + a.V;
-          if (o0 >= 0 && o0 < a.out_len) __stcs(yrow + o0, r.y);  // Re(y): block 0
-          if (o1 >= 0 && o1 < a.out_len) __stcs(yrow + o1, r.x);  // Im(y): block 1
+        for (int q = 0; q < R0; ++q) {
+          const int i = fft_out_index<PL>(t, b, q);
+          if (i >= K1) {
+            const cpx r = u[fft_out_reg<PL>(b, q)];
+            __stcs(y0 + i, r.y);  // Re(y): block 0
+            __stcs(y1 + i, r.x);  // Im(y): block 1
+          }
         }
-      }
+    } else {
+#pragma unroll
+      for (int b = 0; b < B0; ++b)
+#pragma unroll
+        for (int q = 0; q < R0; ++q) {
+          const int i = fft_out_index<PL>(t, b, q);
+          if (i >= K1) {
+            const cpx r = u[fft_out_reg<PL>(b, q)];
+            const int64_t o0 = obase + i, o1 = o0 + a.V;
+            if (o0 >= 0 && o0 < a.out_len) __stcs(yrow + o0, r.y);
+            if (o1 >= 0 && o1 < a.out_len) __stcs(yrow + o1, r.x);
+          }
+        }
+    }
   }
 }
 

@@ -609,9 +609,190 @@ static int run_istft_two_kernels(nxs_ctx* ctx, const IstftArgs& a, int64_t chann
   return run_ola_norm(ctx, (const float2*)ctx->d_scratch, channels, a.M, PL::N, a.hop, a.out_len, a.w, a.y, st);
 }
 
+// ------------------------------------------------------------------------------------------
+// Edge fix-up in double.  Near both ends of a channel the reference divides by an overlap-added
+// window energy D[p] that tends to zero (lib/nx_signal.ex:630-637, e.g. the first / last ~0.1 N
+// samples under a Hann window): y = (frame sample ~ x w) / w^2.  Nx.BinaryBackend computes the
+// inverse FFT in f64 and rounds each sample *relatively*, so it stays accurate there; an fp32
+// FFT has an error proportional to the frame's largest sample, which the division amplifies by
+// 1 / w.  This kernel recomputes exactly those samples -- positions in the partially covered
+// head / tail of a channel with D[p] < 1 % of the full-coverage maximum -- as the reference
+// does: an f64 inverse DFT of the covering frames, rounded to c64 after the ifft, the rescale,
+// the window multiply and the overlap-add, then divided by D[p].  One warp per sample.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) istft_edge_f64_kernel(const float2* __restrict__ z, int64_t M, int64_t z_len,
+                                                             int nfft, int hop, const float* __restrict__ w,
+                                                             int scaling, float sr, int64_t out_len,
+                                                             const double2* __restrict__ tab,
+                                                             float2* __restrict__ y) {
+  __shared__ double red[256];
+  __shared__ float s_dmax, s_scale;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c = blockIdx.x, edge = blockIdx.y;
+  // Dmax: largest full-coverage normaliser; S: the :spectrum / :psd factor (lib/nx_signal.ex:611-625)
+  float dm = 0.f;
+  for (int r = tid; r < hop && r < nfft; r += blockDim.x) {
+    float d = 0.f;
+    for (int n = r; n < nfft; n += hop) {
+      const float a = fabsf(w[n]);
+      d += (float)((double)a * (double)a);
+    }
+    dm = fmaxf(dm, d);
+  }
+  double acc = 0.0;
+  if (scaling != NXS_SCALE_NONE)
+    for (int i = tid; i < nfft; i += blockDim.x) {
+      const float v = w[i];
+      acc += (scaling == NXS_SCALE_SPECTRUM) ? (double)v : (double)(float)((double)v * (double)v);
+    }
+  red[tid] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (tid < s) red[tid] += red[tid + s];
+    __syncthreads();
+  }
+  const double total = red[0];
+  __syncthreads();
+  red[tid] = (double)dm;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (tid < s) red[tid] = fmax(red[tid], red[tid + s]);
+    __syncthreads();
+  }
+  if (tid == 0) {
+    s_dmax = (float)red[0];
+    float S = 1.f;
+    if (scaling == NXS_SCALE_SPECTRUM) S = (float)total;
+    else if (scaling == NXS_SCALE_PSD) S = (float)sqrt((double)(float)((double)sr * (double)(float)total));
+    s_scale = S;
+  }
+  __syncthreads();
+  const float thresh = 0.01f * s_dmax;
+  const double S = (double)s_scale;
+  const int OV = nfft - hop;
+  // head: [0, OV), tail: [M hop, out_len) (= the last OV samples); never the same sample twice
+  int64_t p_lo, p_hi;
+  const int64_t head_end = OV < out_len ? OV : out_len;
+  if (edge == 0) {
+    p_lo = 0;
+    p_hi = head_end;
+  } else {
+    p_lo = M * hop > head_end ? M * hop : head_end;
+    p_hi = out_len;
+  }
+  const float2* __restrict__ zc = z + (int64_t)c * M * z_len;
+  const int nin = (int)(z_len < nfft ? z_len : nfft);
+  for (int64_t p = p_lo + warp; p < p_hi; p += blockDim.x / 32) {
+    const int64_t m_lo = p - nfft + 1 <= 0 ? 0 : (p - nfft + hop) / hop;
+    int64_t m_hi = p / hop;
+    if (m_hi > M - 1) m_hi = M - 1;
+    float D = 0.f;
+    for (int64_t m = m_lo; m <= m_hi; ++m) {
+      const float a = fabsf(w[p - m * hop]);
+      D += (float)((double)a * (double)a);
+    }
+    if (!(D < thresh) || !(D > 1.0e-10f)) continue;  // well conditioned, or the reference's guard case
+    double ore = 0.0, oim = 0.0;  // overlap-add of c64 terms, accumulated in f64
+    for (int64_t m = m_lo; m <= m_hi; ++m) {
+      const int n = (int)(p - m * hop);
+      const float2* __restrict__ zf = zc + m * z_len;
+      // s = sum_k Z[k] exp(+2 pi i k n / nfft), k split over the lanes
+      double sre = 0.0, sim = 0.0;
+      int idx = (int)(((int64_t)lane * n) % nfft);
+      const int step = (int)(((int64_t)32 * n) % nfft);
+      for (int k = lane; k < nin; k += 32) {
+        const float2 v = zf[k];
+        const double2 e = tab[idx];
+        sre += (double)v.x * e.x - (double)v.y * e.y;
+        sim += (double)v.x * e.y + (double)v.y * e.x;
+        idx += step;
+        if (idx >= nfft) idx -= nfft;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        sre += __shfl_xor_sync(0xffffffffu, sre, o);
+        sim += __shfl_xor_sync(0xffffffffu, sim, o);
+      }
+      float fre = (float)(sre / nfft), fim = (float)(sim / nfft);  // Nx.ifft -> c64
+      if (scaling != NXS_SCALE_NONE) {
+        fre = (float)((double)fre * S);
+        fim = (float)((double)fim * S);
+      }
+      const double wn = (double)w[n];
+      ore += (double)(float)((double)fre * wn);  // frames * window -> c64
+      oim += (double)(float)((double)fim * wn);
+    }
+    if (lane == 0) {
+      const float rre = (float)ore, rim = (float)oim;  // overlap_and_add -> c64
+      y[(int64_t)c * out_len + p] = make_float2((float)((double)rre / (double)D), (float)((double)rim / (double)D));
+    }
+  }
+}
+
+static int get_dft_table_f64(nxs_ctx* ctx, int64_t n, double2** out) {
+  const uint64_t key = (uint64_t(5) << 32) | uint64_t(n);
+  auto it = ctx->dft_tables.find(key);
+  if (it != ctx->dft_tables.end()) {
+    *out = reinterpret_cast<double2*>(it->second);
+    return NXS_OK;
+  }
+  std::vector<double2> tab(n);
+  for (int64_t m = 0; m < n; ++m) {
+    // exact at the multiples of pi/2, as cospi / sinpi would be
+    const int64_t m8 = (8 * m) % (8 * n);
+    double cs, sn;
+    if (m8 == 0) { cs = 1; sn = 0; }
+    else if (m8 == 2 * n) { cs = 0; sn = 1; }
+    else if (m8 == 4 * n) { cs = -1; sn = 0; }
+    else if (m8 == 6 * n) { cs = 0; sn = -1; }
+    else {
+      const double ang = 2.0 * M_PI * double(m) / double(n);
+      cs = cos(ang);
+      sn = sin(ang);
+    }
+    tab[m] = make_double2(cs, sn);
+  }
+  double2* d = nullptr;
+  NXS_CUDA(ctx, cudaMalloc(&d, n * sizeof(double2)));
+  NXS_CUDA(ctx, cudaMemcpy(d, tab.data(), n * sizeof(double2), cudaMemcpyHostToDevice));
+  ctx->dft_tables[key] = reinterpret_cast<float2*>(d);
+  *out = d;
+  return NXS_OK;
+}
+
+static int launch_istft_main(nxs_ctx* ctx, const float2* z, int64_t channels, int64_t num_frames, int64_t z_len,
+                             const float* window, int64_t frame_length, int64_t hop, int64_t fft_length, int scaling,
+                             double sampling_rate, float2* y, cudaStream_t st);
+
 int launch_istft(nxs_ctx* ctx, const float2* z, int64_t channels, int64_t num_frames, int64_t z_len,
                  const float* window, int64_t frame_length, int64_t hop, int64_t fft_length, int scaling,
                  double sampling_rate, float2* y, cudaStream_t st) {
+  if (channels <= 0) return NXS_OK;
+  int rc = launch_istft_main(ctx, z, channels, num_frames, z_len, window, frame_length, hop, fft_length, scaling,
+                             sampling_rate, y, st);
+  if (rc) return rc;
+  // no overlap: nothing is partially covered; beyond 2^16 points the f64 table is not worth its memory
+  if (hop >= fft_length || fft_length > 65536 || getenv("NXS_ISTFT_NO_EDGE_F64")) return NXS_OK;
+  double2* tab = nullptr;
+  rc = get_dft_table_f64(ctx, fft_length, &tab);
+  if (rc) return rc;
+  const int64_t out_len = num_frames * hop + (fft_length - hop);
+  int64_t done = 0;
+  while (done < channels) {  // gridDim.x limit is 2^31 - 1; channels beyond that come in slices
+    const int64_t n = channels - done < (int64_t(1) << 30) ? channels - done : (int64_t(1) << 30);
+    istft_edge_f64_kernel<<<dim3((unsigned)n, 2), 256, 0, st>>>(z + done * num_frames * z_len, num_frames, z_len,
+                                                                (int)fft_length, (int)hop, window, scaling,
+                                                                (float)sampling_rate, out_len, tab, y + done * out_len);
+    ctx->launches++;
+    NXS_CUDA(ctx, cudaGetLastError());
+    done += n;
+  }
+  return NXS_OK;
+}
+
+static int launch_istft_main(nxs_ctx* ctx, const float2* z, int64_t channels, int64_t num_frames, int64_t z_len,
+                             const float* window, int64_t frame_length, int64_t hop, int64_t fft_length, int scaling,
+                             double sampling_rate, float2* y, cudaStream_t st) {
   if (channels <= 0) return NXS_OK;
   const int64_t nfft = fft_length;
   if (nfft > (int64_t(1) << 24)) return NXS_EUNSUPPORTED;

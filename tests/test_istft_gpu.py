@@ -53,7 +53,7 @@ def test_doctest_roundtrip(scaling):  # lib/nx_signal.ex:545-579 (generic path: 
     np.testing.assert_allclose(r.real, [0, 10, 1, 0, 10, 10, 2, 20], atol=2e-5)
     zo, _, _ = o.stft(t, o.hann(4), **kw)
     ro = o.istft(zo, o.hann(4), **kw)
-    assert rel(r, ro, o.hann(4), 2) <= TOL
+    assert rel(r, ro) <= TOL
 
 
 def test_cfg5_shape_reduced_vs_oracle():
@@ -65,7 +65,7 @@ def test_cfg5_shape_reduced_vs_oracle():
     yo = o.istft_fast(zo, w, **kw)
     y = nx.istft(zo, w, **kw)
     assert y.shape == yo.shape and y.dtype == np.complex64
-    assert rel(y, yo, w, 256) <= TOL
+    assert rel(y, yo) <= TOL  # plain 1e-5 everywhere: the ill-conditioned edge samples are recomputed in f64
     # and the round trip through our own stft reproduces x away from the edges
     z, _, _ = nx.stft(x, w, **kw)
     y2 = nx.istft(z, w, **kw)
@@ -108,7 +108,7 @@ def test_long_channel_many_segments():
     w = o.hann(nfft)
     y = nx.istft(z, w, overlap_length=nfft - hop, fft_length=nfft)
     yo = o.istft_fast(z, w, overlap_length=nfft - hop, fft_length=nfft)
-    assert rel(y, yo, w, hop) <= TOL
+    assert rel(y, yo) <= TOL
 
 
 @pytest.mark.parametrize("scaling", ["spectrum", "psd"])
@@ -117,7 +117,7 @@ def test_scaling(scaling):
     w = o.hann(512)
     kw = dict(overlap_length=384, fft_length=512, sampling_rate=16000, scaling=scaling)
     zo, _, _ = o.stft_fast(x, w, **kw)
-    assert rel(nx.istft(zo, w, **kw), o.istft_fast(zo, w, **kw), w, 128) <= TOL
+    assert rel(nx.istft(zo, w, **kw), o.istft_fast(zo, w, **kw)) <= TOL
 
 
 def test_z_len_padding_and_truncation():  # Nx.ifft(length:) pads / truncates the last axis
@@ -127,7 +127,7 @@ def test_z_len_padding_and_truncation():  # Nx.ifft(length:) pads / truncates th
         z = (rng.standard_normal((2, 50, zlen)) + 1j * rng.standard_normal((2, 50, zlen))).astype(np.complex64)
         y = nx.istft(z, w, overlap_length=192, fft_length=256)
         yo = o.istft_fast(z, w, overlap_length=192, fft_length=256)
-        assert rel(y, yo, w, 64) <= TOL
+        assert rel(y, yo) <= TOL
 
 
 def test_zero_window_guard():  # select(norm > 1e-10, norm, 1.0), lib/nx_signal.ex:635
@@ -167,9 +167,7 @@ def test_device_roundtrip_at_scale():
     zs = z[0, :40].cpu().numpy()
     yo = o.istft_fast(zs, nx.windows.hann(N), overlap_length=N - H, fft_length=N)
     got = y[0, : 39 * H].cpu().numpy()  # samples not touched by frames >= 40
-    d = ola_energy(nx.windows.hann(N), H, 40)[: 39 * H]
-    cond = np.maximum(1.0, np.sqrt(0.01 * d.max() / np.where(d > 1e-10, d, 1.0)))
-    assert (np.abs(got - yo[: 39 * H]) / cond).max() / np.abs(yo).max() <= TOL
+    assert np.abs(got - yo[: 39 * H]).max() / np.abs(yo).max() <= TOL
 
 
 # ---- register overlap-add fast path (hop = N/2, N/4, N/8; z_len == N) --------------------------
@@ -229,3 +227,22 @@ def test_rola_zero_window_guard_and_scaling():
         yo = o.istft_fast(z, w, **kw)
         assert np.isfinite(y.view(np.float32)).all()
         assert rel(y, yo, w, 128) <= TOL
+
+
+def test_edge_samples_meet_plain_tolerance_only_with_f64_fixup(monkeypatch):
+    """The first / last ~0.1 N samples under a Hann window divide by a vanishing window energy
+    (lib/nx_signal.ex:630-637).  With the f64 edge kernel they meet the plain 1e-5 bound; with it
+    switched off they only meet the conditioning-weighted bound -- which is why the kernel exists."""
+    x = synth((2, 60_000), 77)
+    w = o.hann(1024)
+    kw = dict(overlap_length=768, fft_length=1024, sampling_rate=48000)
+    zo, _, _ = o.stft_fast(x, w, **kw)
+    yo = o.istft_fast(zo, w, **kw)
+    y = nx.istft(zo, w, **kw)
+    edge = np.r_[0:120, yo.shape[-1] - 120:yo.shape[-1]]
+    assert rel(y[:, edge], yo[:, edge]) * np.abs(yo[:, edge]).max() / np.abs(yo).max() <= TOL
+    assert rel(y, yo) <= TOL
+    monkeypatch.setenv("NXS_ISTFT_NO_EDGE_F64", "1")
+    y0 = nx.istft(zo, w, **kw)
+    assert rel(y0, yo, w, 256) <= TOL          # conditioning-weighted bound holds
+    assert np.abs(y0[:, 1:60] - yo[:, 1:60]).max() > np.abs(y[:, 1:60] - yo[:, 1:60]).max()
