@@ -105,6 +105,12 @@ int nxs_firwin_f32(int64_t num_taps, const double* cutoffs, int ncut, int window
 /* NxSignal.fft_frequencies(sampling_rate, fft_length: n)  lib/nx_signal.ex:154-166 */
 int nxs_fft_frequencies_f32(double sampling_rate, int64_t fft_length, float* out);
 
+/* NxSignal.mel_filters(fft_length, mel_bins, sampling_rate, max_mel:, mel_frequency_spacing:)
+ * lib/nx_signal.ex:397-445 -- out [mel_bins][fft_length] f32, bit-compatible with the
+ * reference's per-op f32 rounding (defaults: max_mel 3016, mel_frequency_spacing 200/3). */
+int nxs_mel_filters_f32(int64_t fft_length, int64_t mel_bins, double sampling_rate, double max_mel,
+                        double mel_frequency_spacing, float* out);
+
 /* frame times of stft/3: linspace(N/(2 sr), N/(2 sr) * M, n: M)  lib/nx_signal.ex:108-111 */
 int nxs_stft_times_f32(int64_t frame_length, double sampling_rate, int64_t num_frames, float* out);
 
@@ -139,6 +145,19 @@ int nxs_stft_onesided_f32_dev(nxs_ctx* ctx, const float* x, int64_t channels, in
                               int64_t x_ld, const float* window, int64_t frame_length, int64_t hop,
                               int64_t fft_length, int pad_mode, int64_t pad_lo, int64_t pad_hi,
                               int scaling, double sampling_rate, float* z, int64_t z_ld, void* stream);
+
+/* ---- log-mel: NxSignal.stft_to_mel(z, sampling_rate, fft_length:, mel_bins:, ...)
+ * lib/nx_signal.ex:486-513.
+ * z   [channels][num_frames][z_ld] c64; only bins 0 .. fft_length/2 - 1 are read, so both the
+ *     two-sided (z_ld = fft_length) and the one-sided (z_ld >= fft_length/2 + 1) STFT fit
+ * out [channels][num_frames][mel_bins] f32 = (max(log10(clip(|z|^2 . filters, 1e-10)), max - 8) + 4) / 4,
+ *     the maximum taken per channel (Nx.reduce_max on a vectorised tensor). */
+int nxs_stft_to_mel_f32_dev(nxs_ctx* ctx, const float* z, int64_t channels, int64_t num_frames,
+                            int64_t z_ld, int64_t fft_length, int64_t mel_bins, double sampling_rate,
+                            double max_mel, double mel_frequency_spacing, float* out, void* stream);
+int nxs_stft_to_mel_f32_host(nxs_ctx* ctx, const float* z, int64_t channels, int64_t num_frames,
+                             int64_t z_ld, int64_t fft_length, int64_t mel_bins, double sampling_rate,
+                             double max_mel, double mel_frequency_spacing, float* out);
 
 /* ---- ISTFT: NxSignal.istft(data, window, opts)  lib/nx_signal.ex:582-638 ---
  * z      [channels][num_frames][z_len] c64; Nx.ifft(length: fft_length) pads /

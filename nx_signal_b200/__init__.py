@@ -25,7 +25,7 @@ Filters = filters
 Convolution = convolution
 
 __all__ = [
-    "stft", "istft", "as_windowed", "overlap_and_add", "fft_frequencies", "stft_times",
+    "stft", "istft", "as_windowed", "overlap_and_add", "fft_frequencies", "stft_times", "mel_filters", "stft_to_mel",
     "Windows", "Filters", "Convolution", "windows", "filters", "convolution", "NxSignalArgumentError",
 ]
 
@@ -147,6 +147,44 @@ def stft(data, window, overlap_length=None, fft_length="power_of_two", window_pa
     times = A.from_host(x, stft_times(N, sampling_rate, M))
     freqs = A.from_host(x, fft_frequencies(sampling_rate, nfft)[:nout])
     return z, times, freqs
+
+
+def mel_filters(fft_length, mel_bins, sampling_rate, max_mel=3016, mel_frequency_spacing=200 / 3, type="f32"):
+    """NxSignal.mel_filters/4 (lib/nx_signal.ex:397-445): f32 [mel_bins, fft_length]."""
+    out = np.empty((int(mel_bins), int(fft_length)), dtype=np.float32)
+    _lib.check(_lib.lib().nxs_mel_filters_f32(int(fft_length), int(mel_bins), float(sampling_rate), float(max_mel),
+                                              float(mel_frequency_spacing), out.ctypes.data), what="mel_filters")
+    return out
+
+
+def stft_to_mel(z, sampling_rate, fft_length=None, mel_bins=128, max_mel=3016, mel_frequency_spacing=200 / 3,
+                type="f32"):
+    """NxSignal.stft_to_mel/3 (lib/nx_signal.ex:486-513): z c64 [..., M, K] -> f32 [..., M, mel_bins].
+
+    Only bins 0 .. fft_length // 2 - 1 of z are used (:496), so K may be fft_length (the
+    reference's two-sided spectrum) or fft_length // 2 + 1 (``stft(..., onesided=True)``).  Leading
+    axes stand in for Nx vectorised axes: the dynamic-range maximum (:512) is taken per entry."""
+    if fft_length is None:
+        raise NxSignalArgumentError("missing :fft_length option")
+    zz = A.to_c64(z)
+    if zz.ndim < 2:
+        raise NxSignalArgumentError("z must have at least the [frames, frequencies] axes")
+    M, K = int(zz.shape[-2]), int(zz.shape[-1])
+    nfft = int(fft_length)
+    if K < nfft // 2:
+        raise NxSignalArgumentError(f"z has {K} frequency bins, fewer than fft_length / 2 = {nfft // 2}")
+    batch_shape = tuple(zz.shape[:-2])
+    Cn = int(np.prod(batch_shape, dtype=np.int64)) if batch_shape else 1
+    out = A.empty_like_kind(zz, batch_shape + (M, int(mel_bins)), "f32")
+    if Cn > 0 and M > 0:
+        ctx = _lib.context(A.device_index(zz))
+        args = (Cn, M, K, nfft, int(mel_bins), float(sampling_rate), float(max_mel), float(mel_frequency_spacing))
+        if A.is_cuda(zz):
+            rc = _lib.lib().nxs_stft_to_mel_f32_dev(ctx, A.ptr(zz), *args, A.ptr(out), A.stream_of(zz))
+        else:
+            rc = _lib.lib().nxs_stft_to_mel_f32_host(ctx, A.ptr(zz), *args, A.ptr(out))
+        _lib.check(rc, ctx, "stft_to_mel")
+    return out
 
 
 def istft(data, window, fft_length=None, overlap_length=None, scaling=None, sampling_rate=1000):

@@ -196,6 +196,10 @@ int nxs_ctx_destroy(nxs_ctx* ctx) {
     cudaFree(kv.second.post);
   }
   for (auto& kv : ctx->dft_tables) cudaFree(kv.second);
+  for (auto& b : ctx->mel_banks) {
+    cudaFree(b.d_wts);
+    cudaFree(b.d_idx);
+  }
   cudaFree(ctx->d_coef);
   cudaFree(ctx->d_scratch);
   cudaFree(ctx->d_stage_in);
@@ -460,6 +464,41 @@ int nxs_istft_c64_host(nxs_ctx* ctx, const float* z, int64_t channels, int64_t n
                                               (const float*)dw, frame_length, hop, fft_length, scaling,
                                               sampling_rate, (float2*)dy, ctx->stream);
                         });
+}
+
+// ---- stft_to_mel --------------------------------------------------------------------------------
+static int mel_check(int64_t channels, int64_t num_frames, int64_t z_ld, int64_t fft_length, int64_t mel_bins,
+                     double sampling_rate, double f_sp) {
+  if (channels < 0 || num_frames < 1 || fft_length < 2 || mel_bins < 1) return NXS_ESHAPE;
+  if (z_ld < fft_length / 2) return NXS_ESHAPE;  // slice_along_axis(0, div(fft_length, 2)) must fit (lib/nx_signal.ex:496)
+  if (!(sampling_rate == sampling_rate) || !(f_sp > 0)) return NXS_EINVAL;
+  return NXS_OK;
+}
+
+int nxs_stft_to_mel_f32_dev(nxs_ctx* ctx, const float* z, int64_t channels, int64_t num_frames, int64_t z_ld,
+                            int64_t fft_length, int64_t mel_bins, double sampling_rate, double max_mel,
+                            double mel_frequency_spacing, float* out, void* stream) {
+  if (!ctx || !z || !out) return NXS_EINVAL;
+  int rc = mel_check(channels, num_frames, z_ld, fft_length, mel_bins, sampling_rate, mel_frequency_spacing);
+  if (rc) return rc;
+  DeviceGuard guard(ctx->device);
+  return launch_stft_to_mel(ctx, reinterpret_cast<const float2*>(z), channels, num_frames, z_ld, fft_length, mel_bins,
+                            sampling_rate, max_mel, mel_frequency_spacing, out, pick(ctx, stream));
+}
+
+int nxs_stft_to_mel_f32_host(nxs_ctx* ctx, const float* z, int64_t channels, int64_t num_frames, int64_t z_ld,
+                             int64_t fft_length, int64_t mel_bins, double sampling_rate, double max_mel,
+                             double mel_frequency_spacing, float* out) {
+  if (!ctx || !z || !out) return NXS_EINVAL;
+  int rc = mel_check(channels, num_frames, z_ld, fft_length, mel_bins, sampling_rate, mel_frequency_spacing);
+  if (rc) return rc;
+  DeviceGuard guard(ctx->device);
+  const size_t in_bytes = size_t(channels) * num_frames * z_ld * sizeof(float2);
+  const size_t out_bytes = size_t(channels) * num_frames * mel_bins * sizeof(float);
+  return host_roundtrip(ctx, z, in_bytes, nullptr, 0, out, out_bytes, [&](void* dz, void*, void* dout) {
+    return launch_stft_to_mel(ctx, (const float2*)dz, channels, num_frames, z_ld, fft_length, mel_bins, sampling_rate,
+                              max_mel, mel_frequency_spacing, (float*)dout, ctx->stream);
+  });
 }
 
 // ---- as_windowed ------------------------------------------------------------------------------

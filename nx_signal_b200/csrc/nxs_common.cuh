@@ -19,6 +19,14 @@ struct PlanTables {
   float2* post = nullptr;  // r2c post-pass: -i * exp(-i pi k / N), k in [0, N/2]   (N = nfft/2)
 };
 
+// sparse mel filterbank (nxs_mel.cu) of one parameter set, resident on the device
+struct MelBank {
+  int64_t nfft = 0, mel_bins = 0;
+  double sr = 0, max_mel = 0, f_sp = 0;
+  float* d_wts = nullptr;  // packed nonzero weights
+  int* d_idx = nullptr;    // [3][mel_bins]: start, count, offset
+};
+
 }  // namespace nxs
 
 struct nxs_ctx {
@@ -54,6 +62,7 @@ struct nxs_ctx {
   // twiddle tables keyed by (kind << 32 | N)
   std::unordered_map<uint64_t, nxs::PlanTables> tables;
   std::unordered_map<uint64_t, float2*> dft_tables;  // generic DFT: exp(-2 pi i m / n), m < n
+  std::vector<nxs::MelBank> mel_banks;
 };
 
 namespace nxs {
@@ -97,6 +106,9 @@ int launch_overlap_and_add(nxs_ctx* ctx, const float* t, int complex_, int64_t b
                            int64_t frame_length, int64_t overlap, float* out, cudaStream_t st);
 int launch_fir(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, int64_t x_ld,
                const float* taps, int64_t num_taps, int mode, float* y, int64_t y_ld, cudaStream_t st);
+int launch_stft_to_mel(nxs_ctx* ctx, const float2* z, int64_t channels, int64_t num_frames, int64_t z_ld,
+                       int64_t fft_length, int64_t mel_bins, double sampling_rate, double max_mel, double f_sp,
+                       float* out, cudaStream_t st);
 int launch_convolve_nd(nxs_ctx* ctx, const float* a, const int64_t* as, const float* b, const int64_t* bs,
                        int is_complex, int mode, float* out, cudaStream_t st);
 

@@ -197,6 +197,45 @@ int nxs_fft_frequencies_f32(double sampling_rate, int64_t fft_length, float* out
   return NXS_OK;
 }
 
+// NxSignal.mel_filters/4 (lib/nx_signal.ex:397-445): Slaney-style triangular filters,
+// out [mel_bins][fft_length], every op rounded to f32 as the reference's defn graph does.
+int nxs_mel_filters_f32(int64_t fft_length, int64_t mel_bins, double sampling_rate, double max_mel,
+                        double mel_frequency_spacing, float* out) {
+  if (fft_length < 1 || mel_bins < 1 || !out || !(mel_frequency_spacing > 0)) return NXS_EINVAL;
+  const double f_sp = mel_frequency_spacing;
+  std::vector<float> fftfreqs(fft_length), mels(mel_bins + 2), mel_f(mel_bins + 2);
+  int rc = nxs_fft_frequencies_f32(sampling_rate, fft_length, fftfreqs.data());
+  if (rc) return rc;
+  linspace(0.0, lit(max_mel / f_sp), mel_bins + 2, true, mels.data());  // :412
+  const double min_log_hz = 1000.0, min_log_mel = lit(min_log_hz / f_sp);
+  const double logstep = dvd((double)r32(log(lit(6.4))), 27.0);  // :419
+  for (int64_t i = 0; i < mel_bins + 2; ++i) {
+    const double m = (double)mels[i];
+    if ((float)m >= (float)min_log_mel) {  // :421-426
+      const double e = (double)r32(exp(mul(logstep, sub(m, min_log_mel))));
+      mel_f[i] = r32(mul(min_log_hz, e));
+    } else {
+      mel_f[i] = r32(mul(lit(f_sp), m));
+    }
+  }
+  for (int64_t j = 0; j < mel_bins; ++j) {
+    const double fd0 = sub((double)mel_f[j + 1], (double)mel_f[j]);
+    const double fd1 = sub((double)mel_f[j + 2], (double)mel_f[j + 1]);
+    const double enorm = dvd(2.0, sub((double)mel_f[j + 2], (double)mel_f[j]));  // :436
+    for (int64_t k = 0; k < fft_length; ++k) {
+      const double r0 = sub((double)mel_f[j], (double)fftfreqs[k]);
+      const double r2 = sub((double)mel_f[j + 2], (double)fftfreqs[k]);
+      const float lower = r32(dvd(-r0, fd0));  // :431
+      const float upper = r32(dvd(r2, fd1));   // :432
+      float wgt = lower < upper ? lower : upper;
+      if (lower != lower || upper != upper) wgt = NAN;  // Nx.min propagates NaN (0/0 when two edges coincide)
+      if (!(wgt > 0.0f) && wgt == wgt) wgt = 0.0f;
+      out[j * fft_length + k] = r32(mul((double)wgt, enorm));
+    }
+  }
+  return NXS_OK;
+}
+
 int nxs_stft_times_f32(int64_t frame_length, double sampling_rate, int64_t num_frames, float* out) {
   if (num_frames < 0 || (!out && num_frames > 0)) return NXS_EINVAL;
   if (num_frames == 0) return NXS_OK;

@@ -1,0 +1,187 @@
+// nxs_mel.cu -- log-mel epilogue of the STFT for sm_100a.
+//
+// Replaces NxSignal.stft_to_mel/3 (lib/nx_signal.ex:486-513): |z|^2 over the first
+// fft_length/2 bins (:490, :496-499) -> dot with the Slaney mel filterbank of mel_filters/4
+// (:397-445, built bit-exactly on the host by nxs_mel_filters_f32) (:501-507) ->
+// log10(clip(., 1e-10)) (:511) -> max(., reduce_max - 8) (:512) -> (. + 4) / 4 (:513).
+// The filterbank is triangular, i.e. sparse: each mel bin touches a short run of FFT bins, so
+// the "dot" is ~2 multiply-adds per FFT bin and the kernel is bound by reading z once
+// (4 * fft_length bytes per frame: only the lower half-spectrum is touched; a one-sided
+// spectrum from nxs_stft_onesided_f32_dev is accepted through z_ld).
+//
+// One warp per frame: the frame's power spectrum goes to shared memory, lane l then owns mel
+// bins l, l+32, ...  The per-channel maximum (Nx.reduce_max over a vectorised tensor reduces
+// per entry) is gathered with an ordered-integer atomicMax; a second, tiny kernel applies the
+// dynamic-range clamp and the affine map.
+#include <math.h>
+#include <string.h>
+
+#include "nxs_common.cuh"
+
+namespace nxs {
+
+struct MelArgs {
+  const float2* z;  // [C][M][z_ld]
+  int64_t M, z_ld, total_frames;
+  int half;      // fft_length / 2 bins used
+  int mel_bins;
+  const float* wts;  // packed nonzero filter weights
+  const int* start;  // [mel_bins] first FFT bin of each filter's run
+  const int* count;  // [mel_bins] run length
+  const int* offs;   // [mel_bins] offset of the run in wts
+  float* out;        // [C][M][mel_bins]
+  int* chmax;        // [C] ordered-int maximum of log_spec per channel
+};
+
+__device__ __forceinline__ int float_key(float v) {
+  const int b = __float_as_int(v);
+  return b >= 0 ? b : b ^ 0x7fffffff;
+}
+__device__ __forceinline__ float key_float(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
+
+__global__ void __launch_bounds__(256) mel_logspec_kernel(const MelArgs a) {
+  extern __shared__ float pw_all[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  float* pw = pw_all + (size_t)warp * a.half;
+  int64_t cur_c = -1;
+  float cur_max = -INFINITY;
+  for (int64_t f = (int64_t)blockIdx.x * wpb + warp; f < a.total_frames; f += (int64_t)gridDim.x * wpb) {
+    const int64_t c = f / a.M;
+    if (c != cur_c) {
+      if (cur_c >= 0 && lane == 0) atomicMax(a.chmax + cur_c, float_key(cur_max));
+      cur_c = c;
+      cur_max = -INFINITY;
+    }
+    const float2* __restrict__ zf = a.z + f * a.z_ld;
+    for (int k = lane; k < a.half; k += 32) {
+      const float2 v = __ldcs(zf + k);
+      pw[k] = v.x * v.x + v.y * v.y;  // Nx.abs(z) ** 2
+    }
+    __syncwarp();
+    float m = -INFINITY;
+    for (int j = lane; j < a.mel_bins; j += 32) {
+      const int s = a.start[j], n = a.count[j];
+      const float* __restrict__ w = a.wts + a.offs[j];
+      float acc = 0.f;
+      for (int i = 0; i < n; ++i) acc = fmaf(pw[s + i], __ldg(w + i), acc);
+      // Nx.log(Nx.clip(mel, 1e-10, inf)) / Nx.log(10)
+      const float v = logf(fmaxf(acc, 1.0e-10f)) / 2.3025851f;
+      a.out[f * a.mel_bins + j] = v;
+      m = fmaxf(m, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    cur_max = fmaxf(cur_max, m);
+    __syncwarp();
+  }
+  if (cur_c >= 0 && lane == 0) atomicMax(a.chmax + cur_c, float_key(cur_max));
+}
+
+// log_spec = max(log_spec, reduce_max(log_spec) - 8); (log_spec + 4) / 4   (lib/nx_signal.ex:512-513)
+__global__ void __launch_bounds__(256) mel_finalize_kernel(float* __restrict__ out, int64_t per_channel, int64_t total,
+                                                           const int* __restrict__ chmax) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const float floor_v = key_float(chmax[i / per_channel]) - 8.0f;
+    out[i] = (fmaxf(out[i], floor_v) + 4.0f) / 4.0f;
+  }
+}
+
+// sparse filterbank of one (fft_length, mel_bins, sampling_rate, max_mel, f_sp) on the device
+static int get_mel_bank(nxs_ctx* ctx, int64_t nfft, int64_t mel_bins, double sr, double max_mel, double f_sp,
+                        MelBank** out) {
+  for (auto& b : ctx->mel_banks)
+    if (b.nfft == nfft && b.mel_bins == mel_bins && b.sr == sr && b.max_mel == max_mel && b.f_sp == f_sp) {
+      *out = &b;
+      return NXS_OK;
+    }
+  std::vector<float> dense(size_t(mel_bins) * size_t(nfft));
+  int rc = nxs_mel_filters_f32(nfft, mel_bins, sr, max_mel, f_sp, dense.data());
+  if (rc) return rc;
+  const int64_t half = nfft / 2;
+  std::vector<int> start(mel_bins), count(mel_bins), offs(mel_bins);
+  std::vector<float> wts;
+  for (int64_t j = 0; j < mel_bins; ++j) {
+    const float* row = dense.data() + j * nfft;
+    int64_t lo = half, hi = -1;
+    for (int64_t k = 0; k < half; ++k)
+      if (row[k] != 0.0f) {  // NaN weights (degenerate filters) compare unequal and are kept
+        if (k < lo) lo = k;
+        hi = k;
+      }
+    offs[j] = (int)wts.size();
+    if (hi < 0) {
+      start[j] = 0;
+      count[j] = 0;
+    } else {
+      start[j] = (int)lo;
+      count[j] = (int)(hi - lo + 1);
+      wts.insert(wts.end(), row + lo, row + hi + 1);
+    }
+  }
+  if (wts.empty()) wts.push_back(0.f);
+  MelBank b;
+  b.nfft = nfft;
+  b.mel_bins = mel_bins;
+  b.sr = sr;
+  b.max_mel = max_mel;
+  b.f_sp = f_sp;
+  const size_t ib = size_t(mel_bins) * sizeof(int);
+  NXS_CUDA(ctx, cudaMalloc(&b.d_wts, wts.size() * sizeof(float)));
+  NXS_CUDA(ctx, cudaMalloc(&b.d_idx, 3 * ib));
+  NXS_CUDA(ctx, cudaMemcpy(b.d_wts, wts.data(), wts.size() * sizeof(float), cudaMemcpyHostToDevice));
+  NXS_CUDA(ctx, cudaMemcpy(b.d_idx, start.data(), ib, cudaMemcpyHostToDevice));
+  NXS_CUDA(ctx, cudaMemcpy(b.d_idx + mel_bins, count.data(), ib, cudaMemcpyHostToDevice));
+  NXS_CUDA(ctx, cudaMemcpy(b.d_idx + 2 * mel_bins, offs.data(), ib, cudaMemcpyHostToDevice));
+  ctx->mel_banks.push_back(b);
+  *out = &ctx->mel_banks.back();
+  return NXS_OK;
+}
+
+int launch_stft_to_mel(nxs_ctx* ctx, const float2* z, int64_t channels, int64_t num_frames, int64_t z_ld,
+                       int64_t fft_length, int64_t mel_bins, double sampling_rate, double max_mel, double f_sp,
+                       float* out, cudaStream_t st) {
+  if (channels <= 0 || num_frames <= 0) return NXS_OK;
+  const int64_t half = fft_length / 2;
+  if (half > 49152 || mel_bins > (int64_t(1) << 20)) return NXS_EUNSUPPORTED;
+  MelBank* bank = nullptr;
+  int rc = get_mel_bank(ctx, fft_length, mel_bins, sampling_rate, max_mel, f_sp, &bank);
+  if (rc) return rc;
+  rc = ensure_scratch(ctx, size_t(channels) * sizeof(int));
+  if (rc) return rc;
+  int* chmax = (int*)ctx->d_scratch;
+  // 0x80808080 is the ordered key of about -3.4e38: below every log10 value the kernel can produce
+  NXS_CUDA(ctx, cudaMemsetAsync(chmax, 0x80, size_t(channels) * sizeof(int), st));
+  MelArgs a;
+  a.z = z;
+  a.M = num_frames;
+  a.z_ld = z_ld;
+  a.total_frames = channels * num_frames;
+  a.half = (int)half;
+  a.mel_bins = (int)mel_bins;
+  a.wts = bank->d_wts;
+  a.start = bank->d_idx;
+  a.count = bank->d_idx + mel_bins;
+  a.offs = bank->d_idx + 2 * mel_bins;
+  a.out = out;
+  a.chmax = chmax;
+  int wpb = 8;
+  while (wpb > 1 && size_t(wpb) * half * sizeof(float) > 96 * 1024) wpb >>= 1;
+  const size_t smem = size_t(wpb) * (half > 0 ? half : 1) * sizeof(float);
+  NXS_CUDA(ctx, cudaFuncSetAttribute(mel_logspec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+  int64_t grid = (a.total_frames + wpb - 1) / wpb;
+  if (grid > int64_t(ctx->sm_count) * 8) grid = int64_t(ctx->sm_count) * 8;
+  prof_begin(ctx, st);
+  mel_logspec_kernel<<<(unsigned)grid, wpb * 32, smem, st>>>(a);
+  prof_end(ctx, st);
+  ctx->launches++;
+  NXS_CUDA(ctx, cudaGetLastError());
+  const int64_t per_channel = num_frames * mel_bins, total = per_channel * channels;
+  int64_t g2 = (total + 255) / 256;
+  if (g2 > int64_t(ctx->sm_count) * 16) g2 = int64_t(ctx->sm_count) * 16;
+  mel_finalize_kernel<<<(unsigned)g2, 256, 0, st>>>(out, per_channel, total, chmax);
+  ctx->launches++;
+  NXS_CUDA(ctx, cudaGetLastError());
+  return NXS_OK;
+}
+
+}  // namespace nxs

@@ -812,6 +812,9 @@ def mel_filters(fft_length, mel_bins, sampling_rate, max_mel=3016, mel_frequency
     lower = _div(_f(-_d(ramps[:mel_bins])), fdiff[:mel_bins])
     upper = _div(ramps[2 : mel_bins + 2], fdiff[1 : mel_bins + 1])
     weights = np.maximum(F32(0), np.minimum(lower, upper)).astype(F32)
+    # Nx.max(0, x) is :erlang.max(0.0, x), which returns its first argument on a tie: +0.0 for x = -0.0
+    # (numpy returns the second); the doctest prints 0.0 at [0][0] (lib/nx_signal.ex:388)
+    weights = np.where(weights == 0, F32(0), weights).astype(F32)
     enorm = _div(2.0, _sub(mel_f[2 : mel_bins + 2], mel_f[:mel_bins]))
     return _mul(weights, enorm[:, None])
 

@@ -139,3 +139,22 @@ def test_option_validation_matches_reference_messages():
         nx.convolution.convolve(np.array([1]), np.array(2))
     with pytest.raises(nx.NxSignalArgumentError):
         nx.convolution.convolve(np.arange(6).reshape(2, 3), np.arange(6).reshape(3, 2), mode="valid")
+
+
+# ---- mel_filters (lib/nx_signal.ex:397-445) ---------------------------------------------------------
+@pytest.mark.parametrize("nfft,mels,sr,kw", [
+    (10, 5, 8.0e3, {}), (16, 4, 8.0e3, {}), (1024, 128, 48000, {}), (512, 80, 16000, {}), (400, 40, 22050, {}),
+    (1024, 64, 48000, dict(max_mel=2000, mel_frequency_spacing=50.0)), (2048, 128, 44100, {}),
+])
+def test_mel_filters_bit_exact_vs_oracle(nfft, mels, sr, kw):
+    got = nx.mel_filters(nfft, mels, sr, **kw)
+    want = o.mel_filters(nfft, mels, sr, **kw)
+    assert got.shape == (mels, nfft) and got.dtype == np.float32
+    np.testing.assert_array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_mel_filters_doctest_row():  # lib/nx_signal.ex:384-394
+    m = nx.mel_filters(10, 5, 8.0e3)
+    np.testing.assert_array_equal(m[0], np.array([0.0, 8.129208e-4, 0, 0, 0, 0, 0, 0, 0, 0], np.float32))
+    np.testing.assert_array_equal(m[4, 4:], np.array([7.329034e-5, 2.3422057e-4, 3.8295105e-4, 2.871204e-4,
+                                                      1.9128979e-4, 9.545916e-5], np.float32))

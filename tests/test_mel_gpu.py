@@ -1,0 +1,82 @@
+"""GPU parity of the log-mel epilogue (NxSignal.stft_to_mel/3, lib/nx_signal.ex:486-513) against
+the oracle.  Outputs are O(1) after the (x + 4) / 4 map; tolerance 1e-5 absolute == relative."""
+import numpy as np
+import pytest
+
+import nx_signal_b200 as nx
+from oracle import nxsignal_oracle as o
+from tests.util import TOL, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_doctest_stft_to_mel():  # lib/nx_signal.ex:465-483
+    kw = dict(overlap_length=2, fft_length=16, sampling_rate=8.0e3, window_padding="reflect")
+    z, _, _ = nx.stft(np.arange(10, dtype=np.int32), nx.windows.hann(4), **kw)
+    mel = nx.stft_to_mel(z, 8.0e3, fft_length=16, mel_bins=4)
+    want = np.array([[0.29005307, 0.17422175, 0.18422472, 0.09807998],
+                     [0.6093881, 0.5647397, 0.43538243, 0.086352706],
+                     [0.75841033, 0.70850146, 0.5636921, 0.17911881],
+                     [0.8461772, 0.7952491, 0.64707625, 0.25204098],
+                     [0.9085489, 0.85726047, 0.70786566, 0.30867678],
+                     [0.9085489, 0.85726047, 0.70786566, 0.30867678]], np.float32)
+    assert mel.shape == (6, 4) and mel.dtype == np.float32
+    np.testing.assert_allclose(mel, want, atol=TOL, rtol=0)
+
+
+@pytest.mark.parametrize("nfft,mels,sr", [(1024, 128, 48000), (512, 80, 16000), (400, 40, 22050), (2048, 128, 44100),
+                                           (256, 33, 8000), (8192, 256, 48000)])
+def test_stft_to_mel_vs_oracle(nfft, mels, sr):
+    N = min(nfft, 1024) if nfft != 400 else 400
+    x = synth((2, 30 * nfft), nfft + mels, fs=float(sr))
+    w = o.hann(N)
+    z, _, _ = o.stft_fast(x, w, overlap_length=N // 2, fft_length=nfft, sampling_rate=sr)
+    got = nx.stft_to_mel(z, sr, fft_length=nfft, mel_bins=mels)
+    want = np.stack([o.stft_to_mel(z[c], sr, nfft, mels) for c in range(z.shape[0])])  # per-entry reduce_max
+    assert got.shape == want.shape
+    np.testing.assert_allclose(got, want, atol=TOL, rtol=0)
+
+
+def test_dynamic_range_clamp_is_per_channel_and_active():
+    """A loud and a quiet channel: each is clamped against its own maximum - 8 (log10 units), and the
+    quiet bins of the loud channel do hit the floor."""
+    rng = np.random.default_rng(3)
+    nfft, mels, sr = 512, 64, 16000
+    z = (rng.standard_normal((2, 50, nfft)) + 1j * rng.standard_normal((2, 50, nfft))).astype(np.complex64)
+    z[0, :, : nfft // 8] *= 1e6   # > 8 decades of power between the low and high mel bins of channel 0
+    z[1] *= 1e-3
+    got = nx.stft_to_mel(z, sr, fft_length=nfft, mel_bins=mels)
+    want = np.stack([o.stft_to_mel(z[c], sr, nfft, mels) for c in range(2)])
+    np.testing.assert_allclose(got, want, atol=TOL, rtol=0)
+    floor0 = got[0].max() - 2.0  # (max - 8 + 4) / 4 == max' - 2 after the affine map
+    assert np.isclose(got[0].min(), floor0, atol=1e-6) and (got[0] == got[0].min()).sum() > 10
+
+
+def test_onesided_spectrum_and_device_tensors_at_scale():
+    """cfg2-style chain on the device: one-sided STFT -> log-mel, equal to the two-sided chain."""
+    import torch
+
+    C, L, nfft, hop = 4, 48000 * 20, 1024, 256
+    x = torch.from_numpy(synth((C, L), 9)).cuda()
+    w = torch.from_numpy(o.hann(nfft)).cuda()
+    kw = dict(overlap_length=nfft - hop, fft_length=nfft, sampling_rate=48000)
+    z2, _, _ = nx.stft(x, w, **kw)
+    z1, _, _ = nx.stft(x, w, onesided=True, **kw)
+    m2 = nx.stft_to_mel(z2, 48000, fft_length=nfft, mel_bins=128)
+    m1 = nx.stft_to_mel(z1, 48000, fft_length=nfft, mel_bins=128)
+    assert m1.is_cuda and m1.shape == (C, z2.shape[1], 128)
+    assert torch.equal(m1, m2)
+    want = o.stft_to_mel(z2[1, :300].cpu().numpy(), 48000, nfft, 128)
+    # the oracle's maximum is over 300 frames only: compare where neither side is clamped
+    got = m1[1, :300].cpu().numpy()
+    free = (want > want.min() + 1e-3) & (got > got.min() + 1e-3)
+    assert free.mean() > 0.9
+    np.testing.assert_allclose(got[free], want[free], atol=TOL, rtol=0)
+
+
+def test_errors():
+    z = np.zeros((5, 16), np.complex64)
+    with pytest.raises(nx.NxSignalArgumentError, match="fft_length"):
+        nx.stft_to_mel(z, 8000.0)
+    with pytest.raises(nx.NxSignalArgumentError, match="fewer than"):
+        nx.stft_to_mel(z, 8000.0, fft_length=64, mel_bins=4)

@@ -1,0 +1,29 @@
+"""Times stft_to_mel on cfg2's spectrum shape. usage: run_mel.py [channels] [seconds] [nfft] [hop] [mels] [onesided]"""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import nx_signal_b200 as nx
+from nx_signal_b200 import _lib, _arrays as A
+C = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+secs = float(sys.argv[2]) if len(sys.argv) > 2 else 600
+nfft = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
+hop = int(sys.argv[4]) if len(sys.argv) > 4 else 256
+mels = int(sys.argv[5]) if len(sys.argv) > 5 else 128
+onesided = int(sys.argv[6]) if len(sys.argv) > 6 else 0
+L = int(48000 * secs); M = (L - nfft) // hop + 1
+K = nfft // 2 + 1 if onesided else nfft
+dev = torch.device("cuda", 0)
+z = torch.randn(C, M, K, 2, device=dev)
+out = torch.empty(C, M, mels, device=dev)
+ctx = _lib.context(0); lib = _lib.lib()
+def step():
+    _lib.check(lib.nxs_stft_to_mel_f32_dev(ctx, A.ptr(z), C, M, K, nfft, mels, 48000.0, 3016.0, 200 / 3, A.ptr(out), A.stream_of(z)), ctx)
+for _ in range(2): step()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(10): step()
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / 10
+algo = 8 * C * M * (nfft // 2) + 4 * C * M * mels
+print(f"MEL C={C} M={M} nfft={nfft} mels={mels} K={K}: {ms:.4f} ms per call  {algo/(ms*1e-3)/1e9:.1f} GB/s algorithmic  {C*M/(ms*1e-3)/1e6:.1f} Mframes/s")
