@@ -121,6 +121,28 @@ static ERL_NIF_TERM fir(ErlNifEnv* env, int argc, const ERL_NIF_TERM argv[]) {
   return enif_make_tuple3(env, enif_make_atom(env, "ok"), yt, enif_make_int64(env, out_len));
 }
 
+/* stft_to_mel(ctx, z_bin, channels, frames, z_len, fft_length, mel_bins, sr, max_mel, f_sp)
+ * -- NxSignal.stft_to_mel/3, lib/nx_signal.ex:486-513 */
+static ERL_NIF_TERM stft_to_mel(ErlNifEnv* env, int argc, const ERL_NIF_TERM argv[]) {
+  ctx_res* r;
+  ErlNifBinary z;
+  ErlNifSInt64 ch, frames, zlen, nfft, mels;
+  double sr, max_mel, f_sp;
+  if (argc != 10 || !enif_get_resource(env, argv[0], CTX_TYPE, (void**)&r) ||
+      !enif_inspect_binary(env, argv[1], &z) || !enif_get_int64(env, argv[2], &ch) ||
+      !enif_get_int64(env, argv[3], &frames) || !enif_get_int64(env, argv[4], &zlen) ||
+      !enif_get_int64(env, argv[5], &nfft) || !enif_get_int64(env, argv[6], &mels) ||
+      !enif_get_double(env, argv[7], &sr) || !enif_get_double(env, argv[8], &max_mel) ||
+      !enif_get_double(env, argv[9], &f_sp))
+    return enif_make_badarg(env);
+  if (z.size < (size_t)(ch * frames * zlen) * 2 * sizeof(float)) return enif_make_badarg(env);
+  ERL_NIF_TERM mt;
+  float* mel = (float*)enif_make_new_binary(env, (size_t)(ch * frames * mels) * sizeof(float), &mt);
+  int rc = nxs_stft_to_mel_f32_host(r->ctx, (const float*)z.data, ch, frames, zlen, nfft, mels, sr, max_mel, f_sp, mel);
+  if (rc) return mk_error(env, rc);
+  return enif_make_tuple2(env, enif_make_atom(env, "ok"), mt);
+}
+
 /* window(kind, n, periodic, beta, eps) -- host-side, bit-compatible with Nx.BinaryBackend */
 static ERL_NIF_TERM window(ErlNifEnv* env, int argc, const ERL_NIF_TERM argv[]) {
   int kind, periodic;
@@ -148,6 +170,7 @@ static ErlNifFunc funcs[] = {
     {"stft", 12, stft, ERL_NIF_DIRTY_JOB_IO_BOUND},
     {"istft", 10, istft, ERL_NIF_DIRTY_JOB_IO_BOUND},
     {"fir", 6, fir, ERL_NIF_DIRTY_JOB_IO_BOUND},
+    {"stft_to_mel", 10, stft_to_mel, ERL_NIF_DIRTY_JOB_IO_BOUND},
     {"window", 5, window, 0},
 };
 

@@ -8,6 +8,7 @@ defmodule NxSignalB200.NIF do
   def stft(_c, _x, _ch, _len, _w, _hop, _nfft, _pad, _lo, _hi, _scal, _sr), do: :erlang.nif_error(:not_loaded)
   def istft(_c, _z, _ch, _frames, _zlen, _w, _hop, _nfft, _scal, _sr), do: :erlang.nif_error(:not_loaded)
   def fir(_c, _x, _ch, _len, _h, _mode), do: :erlang.nif_error(:not_loaded)
+  def stft_to_mel(_c, _z, _ch, _frames, _zlen, _nfft, _mels, _sr, _max_mel, _f_sp), do: :erlang.nif_error(:not_loaded)
   def window(_kind, _n, _periodic, _beta, _eps), do: :erlang.nif_error(:not_loaded)
 end
 
@@ -154,6 +155,28 @@ defmodule NxSignalB200 do
       {:ok, y, out_len} ->
         shape = x |> Nx.shape() |> Tuple.to_list() |> List.replace_at(-1, out_len) |> List.to_tuple()
         y |> Nx.from_binary(:f32) |> Nx.reshape(shape)
+
+      err ->
+        raise_nif(err)
+    end
+  end
+
+  @doc "`NxSignal.stft_to_mel/3` (lib/nx_signal.ex:486-513): `z {frames, frequencies}` (vectorised axes = batch)."
+  def stft_to_mel(z, sampling_rate, opts \\ []) do
+    opts = Keyword.validate!(opts, [:fft_length, :max_mel, :mel_frequency_spacing, mel_bins: 128, type: {:f, 32}])
+    nfft = opts[:fft_length] || raise(ArgumentError, "missing :fft_length option")
+    vec_axes = z.vectorized_axes
+    zz = Nx.devectorize(z)
+    frames = Nx.axis_size(zz, -2)
+    zlen = Nx.axis_size(zz, -1)
+    ch = div(Nx.size(zz), frames * zlen)
+
+    case NxSignalB200.NIF.stft_to_mel(ctx(), Nx.to_binary(Nx.as_type(zz, :c64)), ch, frames, zlen, nfft,
+           opts[:mel_bins], sampling_rate * 1.0, (opts[:max_mel] || 3016) * 1.0,
+           (opts[:mel_frequency_spacing] || 200 / 3) * 1.0) do
+      {:ok, mel} ->
+        shape = zz |> Nx.shape() |> Tuple.to_list() |> Enum.drop(-2) |> Kernel.++([frames, opts[:mel_bins]]) |> List.to_tuple()
+        mel |> Nx.from_binary(:f32) |> Nx.reshape(shape) |> Nx.vectorize(vec_axes) |> Nx.rename([:frames, :mel])
 
       err ->
         raise_nif(err)
