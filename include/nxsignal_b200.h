@@ -159,6 +159,18 @@ int nxs_stft_to_mel_f32_host(nxs_ctx* ctx, const float* z, int64_t channels, int
                              int64_t z_ld, int64_t fft_length, int64_t mel_bins, double sampling_rate,
                              double max_mel, double mel_frequency_spacing, float* out);
 
+/* Fused form of NxSignal.stft/3 |> NxSignal.stft_to_mel/3: the same
+ * values as nxs_stft_f32_dev followed by nxs_stft_to_mel_f32_dev, but the spectrum never leaves
+ * the SM (8 fft_length bytes per frame not written and not re-read).  Served by the TMA-staged
+ * kernels (power-of-two fft_length 512 .. 8192 == frame_length, hop % 4 == 0, 16-byte aligned
+ * rows); NXS_EUNSUPPORTED otherwise -- the caller then chains the two entries.
+ * out [channels][num_frames][mel_bins] f32 */
+int nxs_stft_mel_f32_dev(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, int64_t x_ld,
+                         const float* window, int64_t frame_length, int64_t hop, int64_t fft_length,
+                         int pad_mode, int64_t pad_lo, int64_t pad_hi, int scaling, double sampling_rate,
+                         int64_t mel_bins, double max_mel, double mel_frequency_spacing, float* out,
+                         void* stream);
+
 /* ---- ISTFT: NxSignal.istft(data, window, opts)  lib/nx_signal.ex:582-638 ---
  * z      [channels][num_frames][z_len] c64; Nx.ifft(length: fft_length) pads /
  *        truncates the last axis to fft_length, which must equal frame_length

@@ -25,7 +25,7 @@ Filters = filters
 Convolution = convolution
 
 __all__ = [
-    "stft", "istft", "as_windowed", "overlap_and_add", "fft_frequencies", "stft_times", "mel_filters", "stft_to_mel",
+    "stft", "istft", "as_windowed", "overlap_and_add", "fft_frequencies", "stft_times", "mel_filters", "stft_to_mel", "stft_mel",
     "Windows", "Filters", "Convolution", "windows", "filters", "convolution", "NxSignalArgumentError",
 ]
 
@@ -184,6 +184,43 @@ def stft_to_mel(z, sampling_rate, fft_length=None, mel_bins=128, max_mel=3016, m
         else:
             rc = _lib.lib().nxs_stft_to_mel_f32_host(ctx, A.ptr(zz), *args, A.ptr(out))
         _lib.check(rc, ctx, "stft_to_mel")
+    return out
+
+
+def stft_mel(data, window, overlap_length=None, fft_length="power_of_two", window_padding="valid",
+             sampling_rate=100, scaling=None, mel_bins=128, max_mel=3016, mel_frequency_spacing=200 / 3):
+    """``stft_to_mel(stft(data, window, ...)[0], sampling_rate, ...)`` in one pass (extension,
+    SURVEY 8f rank 1): CUDA tensors, f32 [..., M, mel_bins].  The fused kernel keeps each frame's
+    spectrum on chip; configurations it does not serve chain the two device entries instead."""
+    if not A.is_cuda(data):
+        raise NotImplementedError("stft_mel takes CUDA tensors")
+    scale = _scaling_code(scaling)
+    x = A.to_real_f32(data, "data")
+    w = A.like_device(x, A.to_real_f32(window, "window"))
+    N = int(w.shape[0])
+    if overlap_length is None:
+        overlap_length = N // 2
+    hop = N - int(overlap_length)
+    if hop < 1:
+        raise NxSignalArgumentError(f"expected an integer >= 1 or a list of integers, got: {hop!r}")
+    nfft = _next_pow2(N) if fft_length == "power_of_two" else int(fft_length)
+    mode, lo, hi = _padding_code(window_padding)
+    L = int(x.shape[-1])
+    batch_shape = tuple(x.shape[:-1])
+    Cn = int(np.prod(batch_shape, dtype=np.int64)) if batch_shape else 1
+    M = _num_frames(L, N, hop, mode, lo, hi)
+    out = A.empty_like_kind(x, batch_shape + (M, int(mel_bins)), "f32")
+    if M > 0 and Cn > 0:
+        ctx = _lib.context(A.device_index(x))
+        rc = _lib.lib().nxs_stft_mel_f32_dev(ctx, A.ptr(x), Cn, L, L, A.ptr(w), N, hop, nfft, mode, lo, hi, scale,
+                                             float(sampling_rate), int(mel_bins), float(max_mel),
+                                             float(mel_frequency_spacing), A.ptr(out), A.stream_of(x))
+        if rc == _lib.NXS_EUNSUPPORTED:
+            z, _, _ = stft(x, w, overlap_length=overlap_length, fft_length=nfft, window_padding=window_padding,
+                           sampling_rate=sampling_rate, scaling=scaling, onesided=nfft % 2 == 0)
+            return stft_to_mel(z, sampling_rate, fft_length=nfft, mel_bins=mel_bins, max_mel=max_mel,
+                               mel_frequency_spacing=mel_frequency_spacing)
+        _lib.check(rc, ctx, "stft_mel")
     return out
 
 

@@ -501,6 +501,25 @@ int nxs_stft_to_mel_f32_host(nxs_ctx* ctx, const float* z, int64_t channels, int
   });
 }
 
+int nxs_stft_mel_f32_dev(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, int64_t x_ld,
+                         const float* window, int64_t frame_length, int64_t hop, int64_t fft_length, int pad_mode,
+                         int64_t pad_lo, int64_t pad_hi, int scaling, double sampling_rate, int64_t mel_bins,
+                         double max_mel, double mel_frequency_spacing, float* out, void* stream) {
+  if (!ctx || !x || !window || !out) return NXS_EINVAL;
+  PadGeom g;
+  int64_t M = 0;
+  int rc = stft_check(channels, length, x_ld, frame_length, hop, fft_length, pad_mode, pad_lo, pad_hi, scaling,
+                      sampling_rate, &g, &M);
+  if (rc) return rc;
+  if (M > 0) {
+    rc = mel_check(channels, M, fft_length, fft_length, mel_bins, sampling_rate, mel_frequency_spacing);
+    if (rc) return rc;
+  }
+  DeviceGuard guard(ctx->device);
+  return launch_stft_mel(ctx, x, channels, length, x_ld, window, frame_length, hop, fft_length, g, M, scaling,
+                         sampling_rate, mel_bins, max_mel, mel_frequency_spacing, out, pick(ctx, stream));
+}
+
 // ---- as_windowed ------------------------------------------------------------------------------
 static int aw_check(int elem_size, int64_t channels, int64_t length, int64_t x_ld, int64_t window_length,
                     int64_t stride, int pad_mode, int64_t pad_lo, int64_t pad_hi, PadGeom* g, int64_t* M) {

@@ -24,7 +24,17 @@ struct MelBank {
   int64_t nfft = 0, mel_bins = 0;
   double sr = 0, max_mel = 0, f_sp = 0;
   float* d_wts = nullptr;  // packed nonzero weights
+  int nw = 0;              // their count
   int* d_idx = nullptr;    // [3][mel_bins]: start, count, offset
+};
+
+// fused log-mel epilogue of the STFT kernel (launch_stft): the spectrum is never stored
+struct MelEpilogue {
+  const float* wts;
+  const int* idx;
+  int mel_bins, nw;
+  float* out;  // [channels * num_frames][mel_bins]
+  int* chmax;  // [channels]
 };
 
 }  // namespace nxs
@@ -92,7 +102,7 @@ int64_t frames_for(int64_t length, int64_t window_length, int64_t stride, const 
 int launch_stft(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, int64_t x_ld,
                 const float* window, int64_t frame_length, int64_t hop, int64_t fft_length,
                 const PadGeom& g, int64_t num_frames, int scaling, double sampling_rate, float2* z,
-                int64_t z_ld, int onesided, cudaStream_t st);
+                int64_t z_ld, int onesided, cudaStream_t st, const MelEpilogue* mel = nullptr);
 // true when launch_stft serves fft_length with a kernel whose upper half-spectrum is the exact
 // conjugate mirror of the lower half (the r2c kernels; not the generic DFT)
 bool stft_has_exact_mirror(int64_t fft_length);
@@ -109,6 +119,10 @@ int launch_fir(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, i
 int launch_stft_to_mel(nxs_ctx* ctx, const float2* z, int64_t channels, int64_t num_frames, int64_t z_ld,
                        int64_t fft_length, int64_t mel_bins, double sampling_rate, double max_mel, double f_sp,
                        float* out, cudaStream_t st);
+int launch_stft_mel(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, int64_t x_ld,
+                    const float* window, int64_t frame_length, int64_t hop, int64_t fft_length, const PadGeom& g,
+                    int64_t num_frames, int scaling, double sampling_rate, int64_t mel_bins, double max_mel,
+                    double f_sp, float* out, cudaStream_t st);
 int launch_convolve_nd(nxs_ctx* ctx, const float* a, const int64_t* as, const float* b, const int64_t* bs,
                        int is_complex, int mode, float* out, cudaStream_t st);
 

@@ -62,10 +62,19 @@ __global__ void __launch_bounds__(256) mel_logspec_kernel(const MelArgs a) {
     for (int j = lane; j < a.mel_bins; j += 32) {
       const int s = a.start[j], n = a.count[j];
       const float* __restrict__ w = a.wts + a.offs[j];
-      float acc = 0.f;
-      for (int i = 0; i < n; ++i) acc = fmaf(pw[s + i], __ldg(w + i), acc);
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;  // independent partial sums (same order as the fused epilogue)
+      const float* __restrict__ pp = pw + s;
+      int i = 0;
+      for (; i + 4 <= n; i += 4) {
+        a0 = fmaf(pp[i], __ldg(w + i), a0);
+        a1 = fmaf(pp[i + 1], __ldg(w + i + 1), a1);
+        a2 = fmaf(pp[i + 2], __ldg(w + i + 2), a2);
+        a3 = fmaf(pp[i + 3], __ldg(w + i + 3), a3);
+      }
+      for (; i < n; ++i) a0 = fmaf(pp[i], __ldg(w + i), a0);
+      const float acc = (a0 + a1) + (a2 + a3);
       // Nx.log(Nx.clip(mel, 1e-10, inf)) / Nx.log(10)
-      const float v = logf(fmaxf(acc, 1.0e-10f)) / 2.3025851f;
+      const float v = __log2f(fmaxf(acc, 1.0e-10f)) * 0.30102999566f;
       a.out[f * a.mel_bins + j] = v;
       m = fmaxf(m, v);
     }
@@ -125,6 +134,7 @@ static int get_mel_bank(nxs_ctx* ctx, int64_t nfft, int64_t mel_bins, double sr,
   b.sr = sr;
   b.max_mel = max_mel;
   b.f_sp = f_sp;
+  b.nw = (int)wts.size();
   const size_t ib = size_t(mel_bins) * sizeof(int);
   NXS_CUDA(ctx, cudaMalloc(&b.d_wts, wts.size() * sizeof(float)));
   NXS_CUDA(ctx, cudaMalloc(&b.d_idx, 3 * ib));
@@ -175,6 +185,34 @@ int launch_stft_to_mel(nxs_ctx* ctx, const float2* z, int64_t channels, int64_t 
   prof_end(ctx, st);
   ctx->launches++;
   NXS_CUDA(ctx, cudaGetLastError());
+  const int64_t per_channel = num_frames * mel_bins, total = per_channel * channels;
+  int64_t g2 = (total + 255) / 256;
+  if (g2 > int64_t(ctx->sm_count) * 16) g2 = int64_t(ctx->sm_count) * 16;
+  mel_finalize_kernel<<<(unsigned)g2, 256, 0, st>>>(out, per_channel, total, chmax);
+  ctx->launches++;
+  NXS_CUDA(ctx, cudaGetLastError());
+  return NXS_OK;
+}
+
+// stft -> log-mel in one pass: the STFT kernel's epilogue reduces each frame's spectrum to mel
+// powers on chip (the spectrum is never stored), then the same finalize pass as above.
+int launch_stft_mel(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, int64_t x_ld,
+                    const float* window, int64_t frame_length, int64_t hop, int64_t fft_length, const PadGeom& g,
+                    int64_t num_frames, int scaling, double sampling_rate, int64_t mel_bins, double max_mel,
+                    double f_sp, float* out, cudaStream_t st) {
+  if (channels <= 0 || num_frames <= 0) return NXS_OK;
+  if (mel_bins > (int64_t(1) << 16)) return NXS_EUNSUPPORTED;
+  MelBank* bank = nullptr;
+  int rc = get_mel_bank(ctx, fft_length, mel_bins, sampling_rate, max_mel, f_sp, &bank);
+  if (rc) return rc;
+  rc = ensure_scratch(ctx, size_t(channels) * sizeof(int));
+  if (rc) return rc;
+  int* chmax = (int*)ctx->d_scratch;
+  NXS_CUDA(ctx, cudaMemsetAsync(chmax, 0x80, size_t(channels) * sizeof(int), st));
+  MelEpilogue mel{bank->d_wts, bank->d_idx, (int)mel_bins, bank->nw, out, chmax};
+  rc = launch_stft(ctx, x, channels, length, x_ld, window, frame_length, hop, fft_length, g, num_frames, scaling,
+                   sampling_rate, nullptr, fft_length, 0, st, &mel);
+  if (rc) return rc;
   const int64_t per_channel = num_frames * mel_bins, total = per_channel * channels;
   int64_t g2 = (total + 255) / 256;
   if (g2 > int64_t(ctx->sm_count) * 16) g2 = int64_t(ctx->sm_count) * 16;

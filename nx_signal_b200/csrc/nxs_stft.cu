@@ -64,7 +64,21 @@ struct StftArgs {
   int reflect;
   const float2* tw;
   const float2* post;
+  // fused log-mel epilogue (MODE 2): sparse filterbank (nxs_mel.cu layout) and outputs
+  const float* mel_wts = nullptr;
+  const int* mel_idx = nullptr;  // [3][mel_bins]: start, count, offset
+  int mel_bins = 0, mel_nw = 0;  // filters, packed weights
+  float* mel_out = nullptr;      // [total_frames][mel_bins] log10 mel power (before the clamp)
+  int* mel_chmax = nullptr;      // [channels] ordered-int maximum
 };
+
+// MODE of the r2c kernels' epilogue
+enum { kTwoSided = 0, kOneSided = 1, kMel = 2 };
+
+__device__ __forceinline__ int mel_float_key(float v) {
+  const int b = __float_as_int(v);
+  return b >= 0 ? b : b ^ 0x7fffffff;
+}
 
 __device__ __forceinline__ float load_padded(const float* __restrict__ xrow, int64_t src, int64_t L,
                                              int reflect) {
@@ -207,7 +221,7 @@ struct StagedCfg {
   static constexpr size_t SMEM = BAR_OFF + 16 * (PERGROUP ? G : 1);
 };
 
-template <class CF, int MINB, bool ONESIDED>
+template <class CF, int MINB, int MODE>
 __global__ void __launch_bounds__(CF::THREADS, MINB) stft_r2c_staged_kernel(const StftArgs a, const int tpc,
                                                                             const int total_tiles) {
   using PL = typename CF::PL;
@@ -225,6 +239,16 @@ __global__ void __launch_bounds__(CF::THREADS, MINB) stft_r2c_staged_kernel(cons
   float* stage0 = reinterpret_cast<float*>(smem_raw + CF::STAGE_OFF);
   const uint32_t bar0 = smem_u32(smem_raw + CF::BAR_OFF);
 
+  constexpr bool ONESIDED = MODE == kOneSided;
+  // mel epilogue tables live behind the configuration's own shared memory
+  float* const mel_w = reinterpret_cast<float*>(smem_raw + ((CF::SMEM + 15) / 16) * 16);
+  int* const mel_i = reinterpret_cast<int*>(mel_w + a.mel_nw);
+  if constexpr (MODE == kMel) {
+    for (int i = tid; i < a.mel_nw; i += THREADS) mel_w[i] = a.mel_wts[i];
+    for (int i = tid; i < 3 * a.mel_bins; i += THREADS) mel_i[i] = a.mel_idx[i];
+  }
+  int mel_c = -1;            // channel the running maximum belongs to
+  float mel_max = -INFINITY;  // running maximum of this thread's log-mel values
   for (int i = tid; i < NFFT; i += THREADS) wsm[i] = a.wprep[i];
   if constexpr (!CF::TWREG) {
     cpx* twsm = reinterpret_cast<cpx*>(smem_raw + CF::TW_OFF);
@@ -348,7 +372,75 @@ __global__ void __launch_bounds__(CF::THREADS, MINB) stft_r2c_staged_kernel(cons
 #pragma unroll
       for (int q = 0; q < RL; ++q) pb[fft_out_index<PL>(t, b, q)] = v[fft_out_reg<PL>(b, q)];
     sync();
-    if (active) {
+    if constexpr (MODE == kMel) {
+      // power of bins 0 .. N-1 (the lower half-spectrum, lib/nx_signal.ex:496) -> shared memory,
+      // then each thread owns mel bins in serpentine order (narrow low filters pair with wide high ones)
+      float p0[P / 2], p1[P / 2], ph = 0.f;
+      if (active) {
+#pragma unroll
+        for (int i = 0; i < P / 2; ++i) {
+          const int kk = t + i * T;
+          const cpx A = pb[kk];
+          const cpx Bc = cconj(pb[(N - kk) & (N - 1)]);
+          const cpx E = cadd(A, Bc), O = csub(A, Bc);
+          const cpx Tm = cmul(wpost[i], O);
+          const cpx X0 = cadd(E, Tm), X1 = csub(E, Tm);
+          p0[i] = X0.x * X0.x + X0.y * X0.y;  // bin kk
+          p1[i] = X1.x * X1.x + X1.y * X1.y;  // bin N - kk (|conj| = |.|)
+          if (kk == 0) {
+            const cpx Zh = pb[N / 2];
+            ph = 4.f * (Zh.x * Zh.x + Zh.y * Zh.y);  // bin N / 2
+          }
+        }
+      }
+      sync();  // every read of the exchange buffer is done: it becomes the power spectrum
+      float* pw = reinterpret_cast<float*>(pb);
+      if (active) {
+#pragma unroll
+        for (int i = 0; i < P / 2; ++i) {
+          const int kk = t + i * T;
+          pw[kk] = p0[i];
+          if (kk > 0) pw[N - kk] = p1[i];
+          else pw[N / 2] = ph;
+        }
+      }
+      sync();
+      if (active) {
+        if (c != mel_c) {  // uniform over the group
+          if (mel_c >= 0) {
+            float m = mel_max;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if ((tid & 31) == 0) atomicMax(a.mel_chmax + mel_c, mel_float_key(m));
+          }
+          mel_c = c;
+          mel_max = -INFINITY;
+        }
+        float* __restrict__ orow = a.mel_out + f * a.mel_bins;
+        for (int r = 0, j0 = 0; j0 < a.mel_bins; ++r, j0 += T) {
+          const int j = j0 + ((r & 1) ? T - 1 - t : t);
+          if (j < a.mel_bins) {
+            const int s0 = mel_i[j], n = mel_i[a.mel_bins + j];
+            const float* __restrict__ w = mel_w + mel_i[2 * a.mel_bins + j];
+            // four independent partial sums: the loads of one round are in flight together
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            const float* __restrict__ pp = pw + s0;
+            int i = 0;
+            for (; i + 4 <= n; i += 4) {
+              a0 = fmaf(pp[i], w[i], a0);
+              a1 = fmaf(pp[i + 1], w[i + 1], a1);
+              a2 = fmaf(pp[i + 2], w[i + 2], a2);
+              a3 = fmaf(pp[i + 3], w[i + 3], a3);
+            }
+            for (; i < n; ++i) a0 = fmaf(pp[i], w[i], a0);
+            const float acc = (a0 + a1) + (a2 + a3);
+            const float v = __log2f(fmaxf(acc, 1.0e-10f)) * 0.30102999566f;  // log10(clip(mel, 1e-10)), :511
+            orow[j] = v;
+            mel_max = fmaxf(mel_max, v);
+          }
+        }
+      }
+    } else if (active) {
       float2* __restrict__ zf = a.z + f * (ONESIDED ? a.z_ld : (int64_t)NFFT);
 #pragma unroll
       for (int i = 0; i < P / 2; ++i) {
@@ -374,6 +466,14 @@ __global__ void __launch_bounds__(CF::THREADS, MINB) stft_r2c_staged_kernel(cons
       cpx* tmp = bufA;
       bufA = bufB;
       bufB = tmp;
+    }
+  }
+  if constexpr (MODE == kMel) {
+    if (mel_c >= 0) {  // uniform over a warp: its threads belong to one group
+      float m = mel_max;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if ((tid & 31) == 0) atomicMax(a.mel_chmax + mel_c, mel_float_key(m));
     }
   }
 }
@@ -470,6 +570,7 @@ int get_dft_table(nxs_ctx* ctx, int64_t n, int sign, float2** out) {
 
 template <class PL, class TW, int THREADS>
 static int run_r2c(nxs_ctx* ctx, StftArgs a, cudaStream_t st) {
+  if (a.mel_out) return NXS_EUNSUPPORTED;  // the caller chains stft -> stft_to_mel instead
   PlanTables tabs;
   int rc = get_tables<PL>(ctx, &tabs);
   if (rc) return rc;
@@ -505,15 +606,20 @@ static int run_r2c_staged(nxs_ctx* ctx, StftArgs a, int64_t channels, cudaStream
   a.post = tabs.post;
   const int64_t tpc = (a.M + CF::G - 1) / CF::G;
   const int64_t tiles = tpc * channels;
-  auto kern = a.onesided ? stft_r2c_staged_kernel<CF, MINB, true> : stft_r2c_staged_kernel<CF, MINB, false>;
-  NXS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF::SMEM));
+  auto kern = a.mel_out ? stft_r2c_staged_kernel<CF, MINB, kMel>
+              : a.onesided ? stft_r2c_staged_kernel<CF, MINB, kOneSided>
+                           : stft_r2c_staged_kernel<CF, MINB, kTwoSided>;
+  size_t smem = CF::SMEM;
+  if (a.mel_out) smem = (CF::SMEM + 15) / 16 * 16 + size_t(a.mel_nw) * sizeof(float) + 3 * size_t(a.mel_bins) * sizeof(int);
+  if (smem > 232448) return NXS_EUNSUPPORTED;
+  NXS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 1;
-  NXS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, CF::SMEM));
+  NXS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
   if (occ < 1) occ = 1;
   int64_t grid = int64_t(ctx->sm_count) * occ;
   if (grid > tiles) grid = tiles;
   prof_begin(ctx, st);
-  kern<<<(unsigned)grid, THREADS, CF::SMEM, st>>>(a, (int)tpc, (int)tiles);
+  kern<<<(unsigned)grid, THREADS, smem, st>>>(a, (int)tpc, (int)tiles);
   prof_end(ctx, st);
   ctx->launches++;
   NXS_CUDA(ctx, cudaGetLastError());
@@ -550,7 +656,7 @@ bool stft_has_exact_mirror(int64_t nfft) {
 int launch_stft(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, int64_t x_ld,
                 const float* window, int64_t frame_length, int64_t hop, int64_t fft_length,
                 const PadGeom& g, int64_t num_frames, int scaling, double sampling_rate, float2* z,
-                int64_t z_ld, int onesided, cudaStream_t st) {
+                int64_t z_ld, int onesided, cudaStream_t st, const MelEpilogue* mel) {
   if (num_frames <= 0 || channels <= 0) return NXS_OK;
   if (fft_length > (int64_t(1) << 24) || frame_length > (int64_t(1) << 24)) return NXS_EUNSUPPORTED;
   const int64_t nfft = fft_length;
@@ -573,6 +679,14 @@ int launch_stft(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, 
   a.reflect = g.reflect;
   a.tw = nullptr;
   a.post = nullptr;
+  if (mel) {  // fused log-mel epilogue: served by the staged kernels only
+    a.mel_wts = mel->wts;
+    a.mel_idx = mel->idx;
+    a.mel_bins = mel->mel_bins;
+    a.mel_nw = mel->nw;
+    a.mel_out = mel->out;
+    a.mel_chmax = mel->chmax;
+  }
 
   const bool fast = stft_has_exact_mirror(nfft);
   rc = launch_prep_window(ctx, window, frame_length, nfft, scaling, sampling_rate, fast ? 0.5f : 1.0f, 0,
@@ -630,6 +744,7 @@ int launch_stft(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, 
       default: break;
     }
   }
+  if (a.mel_out) return NXS_EUNSUPPORTED;
   float2* tab = nullptr;
   rc = get_dft_table(ctx, nfft, -1, &tab);
   if (rc) return rc;

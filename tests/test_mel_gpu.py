@@ -80,3 +80,46 @@ def test_errors():
         nx.stft_to_mel(z, 8000.0)
     with pytest.raises(nx.NxSignalArgumentError, match="fewer than"):
         nx.stft_to_mel(z, 8000.0, fft_length=64, mel_bins=4)
+
+
+# ---- fused STFT -> log-mel (the spectrum never leaves the SM) ------------------------------------
+@pytest.mark.parametrize("nfft,hop,mels,padding,scaling", [
+    (1024, 256, 128, "valid", None), (1024, 256, 80, "reflect", "spectrum"), (512, 128, 64, "valid", None),
+    (2048, 512, 128, "same", "psd"), (4096, 1024, 128, "valid", None), (8192, 2048, 256, "valid", None),
+    (1024, 1024, 40, "valid", None), (1024, 64, 300, "valid", None),
+    (1024, 250, 128, "valid", None),   # hop % 4 != 0: served by chaining the two entries
+    (400, 160, 40, "valid", None),     # generic length: chained
+])
+def test_fused_stft_mel_equals_chain_and_oracle(nfft, hop, mels, padding, scaling):
+    import torch
+
+    sr = 48000
+    x = synth((3, 40 * nfft + 4 * 33), 5 + nfft + hop)
+    w = o.hann(nfft)
+    kw = dict(overlap_length=nfft - hop, fft_length=nfft, sampling_rate=sr, window_padding=padding, scaling=scaling)
+    xd, wd = torch.from_numpy(x).cuda(), torch.from_numpy(w).cuda()
+    fused = nx.stft_mel(xd, wd, mel_bins=mels, **kw)
+    z, _, _ = nx.stft(xd, wd, **kw)
+    chain = nx.stft_to_mel(z, sr, fft_length=nfft, mel_bins=mels)
+    assert fused.shape == chain.shape == (3, z.shape[1], mels)
+    # same arithmetic in both paths up to the summation order inside a filter
+    assert float((fused - chain).abs().max()) <= 2e-6
+    zo, _, _ = o.stft_fast(x, w, **kw)
+    want = np.stack([o.stft_to_mel(zo[c], sr, nfft, mels) for c in range(3)])
+    np.testing.assert_allclose(fused.cpu().numpy(), want, atol=TOL, rtol=0)
+
+
+def test_fused_stft_mel_at_scale_channels_have_own_maximum():
+    import torch
+
+    C, L, nfft, hop = 6, 48000 * 30, 1024, 256
+    x = torch.from_numpy(synth((C, L), 21)).cuda()
+    x[1] *= 1e-3   # a quiet channel: its clamp floor must come from its own maximum
+    x[4, : L // 2] = 0  # half silent: those frames sit on the floor
+    w = torch.from_numpy(o.hann(nfft)).cuda()
+    kw = dict(overlap_length=nfft - hop, fft_length=nfft, sampling_rate=48000)
+    fused = nx.stft_mel(x, w, mel_bins=128, **kw)
+    z, _, _ = nx.stft(x, w, onesided=True, **kw)
+    chain = nx.stft_to_mel(z, 48000, fft_length=nfft, mel_bins=128)
+    assert float((fused - chain).abs().max()) <= 2e-6
+    assert float(fused[4, : 1000].max()) == float(fused[4].min())

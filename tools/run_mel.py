@@ -27,3 +27,17 @@ e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 10
 algo = 8 * C * M * (nfft // 2) + 4 * C * M * mels
 print(f"MEL C={C} M={M} nfft={nfft} mels={mels} K={K}: {ms:.4f} ms per call  {algo/(ms*1e-3)/1e9:.1f} GB/s algorithmic  {C*M/(ms*1e-3)/1e6:.1f} Mframes/s")
+
+# fused stft -> mel on the same workload
+x = torch.randn(C, L, device=dev)
+w = torch.from_numpy(nx.windows.hann(nfft)).to(dev)
+def fstep():
+    _lib.check(lib.nxs_stft_mel_f32_dev(ctx, A.ptr(x), C, L, L, A.ptr(w), nfft, hop, nfft, 0, 0, 0, 0, 48000.0, mels, 3016.0, 200 / 3, A.ptr(out), A.stream_of(x)), ctx)
+for _ in range(2): fstep()
+torch.cuda.synchronize()
+e0.record()
+for _ in range(10): fstep()
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / 10
+algo = 4 * C * L + 4 * C * M * mels
+print(f"FUSED STFT+MEL C={C} M={M} nfft={nfft} hop={hop} mels={mels}: {ms:.4f} ms per call  {C*M/(ms*1e-3)/1e6:.1f} Mframes/s  ({algo/(ms*1e-3)/1e9:.1f} GB/s algorithmic: x in, mel out)")
