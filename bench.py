@@ -362,7 +362,7 @@ def main():
         "config": {"workload": WORKLOAD, "channels_per_gpu": CHANNELS, "fft_length": NFFT, "hop": HOP,
                    "l2": "inputs larger than L2 (0.92 GB in, 7.37 GB out per step)", "parity_frame_rel_err": parity},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "kernel": "stft_r2c_staged_kernel<StagedCfg<Plan<512,64,8,8,8>,256,2,tw-regs,per-group TMA>,2,two-sided>",
+                     "traffic": traffic, "peak_source": peak_src, "kernel": "stft_r2c_staged_kernel<StagedCfg<Plan<512,64,8,8,8>,256,2,tw-regs,per-group TMA,win-regs>,2,two-sided>",
                      "kernel_ms": kern_avg_ms, "kernel_launches_timed": kern_n, "algorithmic_bytes": ALGO_BYTES},
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }

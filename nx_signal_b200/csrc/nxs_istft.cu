@@ -201,20 +201,21 @@ __global__ void __launch_bounds__(THREADS, MINB) istft_kernel(const IstftArgs a)
 // frame has been read out of it, so the load of frame m+1 overlaps the FFT of frame m.
 // Segments after the first recompute the HOPDIV-1 frames that overlap their start.
 // ------------------------------------------------------------------------------------------
-template <class PL, int THREADS>
+// XD: two exchange buffers per group (no barrier between a middle pass's reads and writes)
+template <class PL, int THREADS, bool XD = false>
 struct RolaCfg {
   static constexpr int G = THREADS / PL::T, N = PL::N;
-  static constexpr size_t GROUP_BYTES = (size_t(N) + size_t(PL::BUF)) * sizeof(cpx);  // stage + exchange
+  static constexpr size_t GROUP_BYTES = (size_t(N) + size_t(XD ? 2 : 1) * size_t(PL::BUF)) * sizeof(cpx);  // stage + exchange
   static constexpr size_t WIN_OFF = size_t(G) * GROUP_BYTES;
-  static constexpr size_t W2_OFF = WIN_OFF + size_t(N) * sizeof(float);
-  static constexpr size_t TW_OFF = W2_OFF + size_t(N) * sizeof(float);
+  static constexpr size_t TW_OFF = WIN_OFF + size_t(N) * sizeof(float);
   static constexpr size_t BAR_OFF = TW_OFF + size_t(PL::TW_TOTAL) * sizeof(cpx);
   static constexpr size_t SMEM = BAR_OFF + 8 * size_t(G) + 8;
 };
 
-template <class PL, int THREADS, int MINB, int HOPDIV>
+template <class PL, int THREADS, int MINB, int HOPDIV, bool XD = false>
 __global__ void __launch_bounds__(THREADS, MINB) istft_rola_kernel(const IstftArgs a) {
-  using CF = RolaCfg<PL, THREADS>;
+  using CF = RolaCfg<PL, THREADS, XD>;
+  static_assert(!XD || PL::NP == 3, "the two-buffer form relies on the 3-pass buffer rotation");
   constexpr int N = PL::N, T = PL::T, P = PL::P, G = CF::G;
   constexpr int R0 = PL::R(0), B0 = P / R0;
   constexpr int RL = PL::R(PL::NP - 1), BL = P / RL;
@@ -226,15 +227,15 @@ __global__ void __launch_bounds__(THREADS, MINB) istft_rola_kernel(const IstftAr
   cpx* const stage = reinterpret_cast<cpx*>(smem_raw + size_t(g) * CF::GROUP_BYTES);
   cpx* const xbuf = stage + N;
   float* wsm = reinterpret_cast<float*>(smem_raw + CF::WIN_OFF);
-  float* w2sm = reinterpret_cast<float*>(smem_raw + CF::W2_OFF);
   cpx* twsm = reinterpret_cast<cpx*>(smem_raw + CF::TW_OFF);
   const uint32_t mybar = smem_u32(smem_raw + CF::BAR_OFF) + 8 * g;
 
-  for (int i = tid; i < N; i += THREADS) {
-    wsm[i] = a.wprep[i];
-    const float w = a.w[i];
-    w2sm[i] = (float)((double)fabsf(w) * (double)fabsf(w));  // Nx.abs(window) ** 2, f32
-  }
+  for (int i = tid; i < N; i += THREADS) wsm[i] = a.wprep[i];
+  // Nx.abs(window) ** 2 in f32; only the per-thread constants and the channel edges need it
+  auto w2 = [&](int n) {
+    const float w = fabsf(__ldg(a.w + n));
+    return (float)((double)w * (double)w);
+  };
   for (int i = tid; i < PL::TW_TOTAL; i += THREADS) twsm[i] = a.tw[i];
   if (tid == 0) {
     for (int i = 0; i < G; ++i) mbar_init(smem_u32(smem_raw + CF::BAR_OFF) + 8 * i, 1);
@@ -252,7 +253,7 @@ __global__ void __launch_bounds__(THREADS, MINB) istft_rola_kernel(const IstftAr
   for (int j = 0; j < S; ++j) {
     float nr = 0.f;
 #pragma unroll
-    for (int k = HOPDIV - 1; k >= 0; --k) nr += w2sm[t + j * T + k * HOP];
+    for (int k = HOPDIV - 1; k >= 0; --k) nr += w2(t + j * T + k * HOP);
     normc[j] = nr;
   }
   // exact normaliser at output position p of a channel (edges: fewer covering frames)
@@ -261,7 +262,7 @@ __global__ void __launch_bounds__(THREADS, MINB) istft_rola_kernel(const IstftAr
     int64_t m_hi = p / HOP;
     if (m_hi > a.M - 1) m_hi = a.M - 1;
     float nr = 0.f;
-    for (int64_t m = m_lo; m <= m_hi; ++m) nr += w2sm[(int)(p - m * HOP)];
+    for (int64_t m = m_lo; m <= m_hi; ++m) nr += w2((int)(p - m * HOP));
     return nr;
   };
 
@@ -316,7 +317,8 @@ __global__ void __launch_bounds__(THREADS, MINB) istft_rola_kernel(const IstftAr
         if (m + 1 < me) issue(c, m + 1);
         else if (nseg < a.total_segs) issue(nc, nmb);
       }
-      block_fft_single<PL>(v, t, xbuf, tw, sync);
+      if constexpr (XD) block_fft<PL>(v, t, xbuf, xbuf + PL::BUF, tw, sync);
+      else block_fft_single<PL>(v, t, xbuf, tw, sync);
       // window, accumulate: thread t holds n = t + j*T at v[fft_out_reg(b, q)], j = b + q*BL
 #pragma unroll
       for (int b = 0; b < BL; ++b)
@@ -525,14 +527,14 @@ static int run_istft(nxs_ctx* ctx, IstftArgs a, int64_t channels, cudaStream_t s
 }
 
 // register overlap-add kernel: requires z_len == N, hop * HOPDIV == N, hop % T == 0 and 16-byte aligned rows
-template <class PL, int THREADS, int MINB, int HOPDIV>
+template <class PL, int THREADS, int MINB, int HOPDIV, bool XD = false>
 static int run_istft_rola(nxs_ctx* ctx, IstftArgs a, int64_t channels, cudaStream_t st) {
-  using CF = RolaCfg<PL, THREADS>;
+  using CF = RolaCfg<PL, THREADS, XD>;
   float2* tw = nullptr;
   int rc = get_tw_table<PL>(ctx, &tw);
   if (rc) return rc;
   a.tw = tw;
-  auto kern = istft_rola_kernel<PL, THREADS, MINB, HOPDIV>;
+  auto kern = istft_rola_kernel<PL, THREADS, MINB, HOPDIV, XD>;
   NXS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF::SMEM));
   int occ = 1;
   NXS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, CF::SMEM));
@@ -568,7 +570,14 @@ static int try_istft_rola(nxs_ctx* ctx, const IstftArgs& a, int64_t channels, cu
   if (a.M >= (int64_t(1) << 40)) return NXS_OK;
   *done = true;
   if (a.hop * 2 == PL::N) return run_istft_rola<PL, THREADS, MINB, 2>(ctx, a, channels, st);
-  if (a.hop * 4 == PL::N) return run_istft_rola<PL, THREADS, MINB, 4>(ctx, a, channels, st);
+  if (a.hop * 4 == PL::N) {
+    if constexpr (PL::N == 1024) {  // tuning variant (tests/test_istft_gpu.py)
+      const char* var = getenv("NXS_ISTFT_VARIANT");
+      if (var && atoi(var) == 1) return run_istft_rola<PL, THREADS, MINB, 4>(ctx, a, channels, st);
+      return run_istft_rola<PL, THREADS, MINB, 4, true>(ctx, a, channels, st);  // two exchange buffers still fit 2 CTAs/SM
+    }
+    return run_istft_rola<PL, THREADS, MINB, 4>(ctx, a, channels, st);
+  }
   if constexpr (PL::P >= 8) {
     if (a.hop * 8 == PL::N) return run_istft_rola<PL, THREADS, MINB, 8>(ctx, a, channels, st);
   }

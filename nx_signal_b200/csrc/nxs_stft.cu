@@ -203,11 +203,13 @@ __global__ void __launch_bounds__(THREADS) stft_r2c_kernel(const StftArgs a) {
 // TMA is issued as soon as the group has read the stage into registers, so it still overlaps the
 // whole FFT; halves the shared memory of the large plans (2 CTAs/SM instead of 1) for one
 // extra group barrier per middle pass.
-template <class PL_, int THREADS_, int HOPDIV_, bool TWREG_, bool PERGROUP_ = false, bool LEAN_ = false>
+// WINREG: the thread's P window values (constant across frames) live in registers.
+template <class PL_, int THREADS_, int HOPDIV_, bool TWREG_, bool PERGROUP_ = false, bool LEAN_ = false,
+          bool WINREG_ = false>
 struct StagedCfg {
   using PL = PL_;
   static constexpr int THREADS = THREADS_, HOPDIV = HOPDIV_;
-  static constexpr bool TWREG = TWREG_, PERGROUP = PERGROUP_, LEAN = LEAN_;
+  static constexpr bool TWREG = TWREG_, PERGROUP = PERGROUP_, LEAN = LEAN_, WINREG = WINREG_;
   static_assert(!LEAN || PERGROUP, "LEAN needs per-group staging");
   static constexpr int G = THREADS / PL::T, NFFT = 2 * PL::N;
   static constexpr int NSTAGE = LEAN ? 1 : 2, NXBUF = LEAN ? 1 : 2;
@@ -268,6 +270,14 @@ __global__ void __launch_bounds__(CF::THREADS, MINB) stft_r2c_staged_kernel(cons
   for (int i = 0; i < P / 2; ++i) wpost[i] = __ldg(a.post + t + i * T);
   const GroupSync<T> sync{1 + g};
   const int hop = (int)a.hop;
+  float2 wreg[CF::WINREG ? P : 1];
+  if constexpr (CF::WINREG) {
+#pragma unroll
+    for (int b = 0; b < B0; ++b)
+#pragma unroll
+      for (int q = 0; q < R0; ++q)
+        wreg[b * R0 + q] = reinterpret_cast<const float2*>(wsm)[fft_in_index<PL>(t, b, q)];
+  }
 
   // is this tile (PERGROUP: this group's frame) fully interior (no padding) -> staged through TMA
   auto tile_geom = [&](int tile, int& c, int& m0, int& gact, int64_t& src0) {
@@ -331,7 +341,10 @@ __global__ void __launch_bounds__(CF::THREADS, MINB) stft_r2c_staged_kernel(cons
 #pragma unroll
           for (int q = 0; q < R0; ++q) {
             const int i = fft_in_index<PL>(t, b, q);
-            const float2 xx = xp[i], ww = wp[i];
+            const float2 xx = xp[i];
+            float2 ww;
+            if constexpr (CF::WINREG) ww = wreg[b * R0 + q];
+            else ww = wp[i];
             v[b * R0 + q] = make_float2(xx.x * ww.x, xx.y * ww.y);
           }
       } else {
@@ -709,14 +722,16 @@ int launch_stft(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, 
       }
       case 1024: {
         using PL = Plan<512, 64, 8, 8, 8>;
-        // tuning variants (tests/test_stft_variants_gpu.py); default = per-group staging, 256 x 2
+        // tuning variants (tests/test_stft_variants_gpu.py); default = per-group staging, 256 x 2,
+        // twiddles and window in registers
         const char* var = getenv("NXS_STFT_VARIANT");
         const int variant = var ? atoi(var) : 0;
         if (variant == 1) { using CF = StagedCfg<PL, 256, 2, true, false>; NXS_TRY_STAGED(CF, 2); }
         if (variant == 2) { using CF = StagedCfg<PL, 512, 2, true, true>; NXS_TRY_STAGED(CF, 1); }
         if (variant == 3) { using CF = StagedCfg<PL, 128, 2, true, true>; NXS_TRY_STAGED(CF, 4); }
         if (variant == 4) { using CF = StagedCfg<PL, 256, 2, true, true, true>; NXS_TRY_STAGED(CF, 2); }
-        { using CF = StagedCfg<PL, 256, 2, true, true>; NXS_TRY_STAGED(CF, 2); }
+        if (variant == 5) { using CF = StagedCfg<PL, 256, 2, true, true>; NXS_TRY_STAGED(CF, 2); }
+        { using CF = StagedCfg<PL, 256, 2, true, true, false, true>; NXS_TRY_STAGED(CF, 2); }
         return run_r2c<PL, TwRegs<PL>, 512>(ctx, a, st);
       }
       case 2048: {

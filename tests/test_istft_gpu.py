@@ -246,3 +246,13 @@ def test_edge_samples_meet_plain_tolerance_only_with_f64_fixup(monkeypatch):
     y0 = nx.istft(zo, w, **kw)
     assert rel(y0, yo, w, 256) <= TOL          # conditioning-weighted bound holds
     assert np.abs(y0[:, 1:60] - yo[:, 1:60]).max() > np.abs(y[:, 1:60] - yo[:, 1:60]).max()
+
+
+def test_rola_two_exchange_buffer_variant(monkeypatch):
+    rng = np.random.default_rng(21)
+    z = (rng.standard_normal((3, 700, 1024)) + 1j * rng.standard_normal((3, 700, 1024))).astype(np.complex64)
+    w = o.hann(1024)
+    kw = dict(overlap_length=768, fft_length=1024)
+    yo = o.istft_fast(z, w, **kw)
+    monkeypatch.setenv("NXS_ISTFT_VARIANT", "1")
+    assert rel(nx.istft(z, w, **kw), yo) <= TOL
