@@ -171,6 +171,73 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def other_kernels(torch, nx, _lib, A, dev, local_rank, peak):
+    """Kernel times of the path's other rows on their BASELINE shapes: ISTFT cfg5,
+    FIR cfg4, one GPU's shard of cfg3, and the log-mel epilogue on cfg2's spectrum.  Mean of 5
+    launches after 2 warm-ups, CUDA events around the dominant kernel (`nxs_ctx_profile`)."""
+    lib = _lib.lib()
+    ctx = _lib.context(local_rank)
+    out = {}
+
+    def timed(fn, iters=5):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize(dev)
+        _lib.profile(True, local_rank)
+        _lib.profile_read(local_rank)
+        for _ in range(iters):
+            fn()
+        ms, n = _lib.profile_read(local_rank)
+        _lib.profile(False, local_rank)
+        return ms / max(n, 1)
+
+    def entry(ms, algo_bytes, units, unit_name):
+        gbs = algo_bytes / (ms * 1e-3) / 1e9
+        return {"kernel_ms": ms, "algorithmic_bytes": int(algo_bytes), "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peak,
+                unit_name: units / (ms * 1e-3)}
+
+    g = torch.Generator(device=dev).manual_seed(7)
+    # ISTFT, cfg5: 32 ch x 60 s, hann(1024), hop 256
+    C5, L5 = 32, FS * 60
+    M5 = (L5 - NFFT) // HOP + 1
+    w = torch.from_numpy(nx.windows.hann(NFFT)).to(dev)
+    z = torch.randn(C5, M5, NFFT, 2, device=dev, generator=g)
+    y = torch.empty(C5, M5 * HOP + NFFT - HOP, 2, device=dev)
+    s = A.stream_of(z)
+    ms = timed(lambda: _lib.check(lib.nxs_istft_c64_dev(ctx, A.ptr(z), C5, M5, NFFT, A.ptr(w), NFFT, HOP, NFFT, 0,
+                                                       float(FS), A.ptr(y), s), ctx))
+    out["istft_cfg5"] = entry(ms, 8 * C5 * M5 * NFFT + 8 * C5 * (M5 * HOP + NFFT - HOP), C5 * M5, "frames_per_s")
+    # log-mel epilogue on the same spectrum shape (reads the lower half-spectrum)
+    mel = torch.empty(C5, M5, 128, device=dev)
+    ms = timed(lambda: _lib.check(lib.nxs_stft_to_mel_f32_dev(ctx, A.ptr(z), C5, M5, NFFT, NFFT, 128, float(FS), 3016.0,
+                                                             200 / 3, A.ptr(mel), s), ctx))
+    out["stft_to_mel_cfg5_spectrum"] = entry(ms, 4 * C5 * M5 * NFFT + 4 * C5 * M5 * 128, C5 * M5, "frames_per_s")
+    del z, y, mel
+    # STFT, one GPU's shard of cfg3: 128 ch x 60 s, hann(4096), hop 1024
+    C3, N3, H3 = 128, 4096, 1024
+    M3 = (L5 - N3) // H3 + 1
+    x3 = torch.randn(C3, L5, device=dev, generator=g)
+    w3 = torch.from_numpy(nx.windows.hann(N3)).to(dev)
+    z3 = torch.empty(C3, M3, N3, 2, device=dev)
+    ms = timed(lambda: _lib.check(lib.nxs_stft_f32_dev(ctx, A.ptr(x3), C3, L5, L5, A.ptr(w3), N3, H3, N3, _lib.PAD_VALID, 0, 0,
+                                                      _lib.SCALE_NONE, float(FS), A.ptr(z3), s), ctx))
+    out["stft_cfg3_shard"] = entry(ms, 4 * C3 * L5 + 8 * C3 * M3 * N3, C3 * M3, "frames_per_s")
+    del x3, z3
+    torch.cuda.empty_cache()
+    # FIR, cfg4: 64 ch x 600 s, firwin(2049) lowpass, mode :same
+    C4 = 64
+    taps = torch.from_numpy(nx.filters.firwin(2049, [6000], sampling_rate=FS)).to(dev)
+    x4 = torch.randn(C4, L, device=dev, generator=g)
+    y4 = torch.empty_like(x4)
+    ms = timed(lambda: _lib.check(lib.nxs_fir_f32_dev(ctx, A.ptr(x4), C4, L, L, A.ptr(taps), 2049, 1, A.ptr(y4), L, s), ctx),
+               iters=3)
+    out["fir_cfg4"] = entry(ms, 8 * C4 * L, C4 * L, "samples_per_s")
+    out["fir_cfg4"]["note"] = "instruction-issue-bound at K = 2049 (two 4096-pt complex FFTs per 4096 outputs), not HBM-bound"
+    del x4, y4
+    torch.cuda.empty_cache()
+    return out
+
+
 def make_input(torch, dev, seed):
     g = torch.Generator(device=dev).manual_seed(seed)
     x = torch.randn(CHANNELS, L, device=dev, generator=g, dtype=torch.float32) * 0.25
@@ -187,6 +254,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the ISTFT / FIR / mel / cfg3 kernel timings")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -343,6 +411,13 @@ def main():
             traffic = json.load(open(tp)).get("stft_r2c_1024_bytes_per_launch")
         except Exception:
             traffic = None
+    # the path's other kernels on their BASELINE shapes (device-resident, CUDA events; not part of `value`)
+    other = None
+    if world == 1 and not args.no_extras:
+        try:
+            other = other_kernels(torch, nx, _lib, A, dev, local_rank, peak)
+        except Exception as ex:  # report, never fake
+            other = {"error": repr(ex)[:200]}
     cpu = None
     if world == 1 and not args.no_cpu:
         port = CpuPort()
@@ -365,6 +440,7 @@ def main():
                      "traffic": traffic, "peak_source": peak_src, "kernel": "stft_r2c_staged_kernel<StagedCfg<Plan<512,64,8,8,8>,256,2,tw-regs,per-group TMA,win-regs>,2,two-sided>",
                      "kernel_ms": kern_avg_ms, "kernel_launches_timed": kern_n, "algorithmic_bytes": ALGO_BYTES},
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "other_kernels": other,
     }
     print(json.dumps(line), flush=True)
     if dist is not None:
