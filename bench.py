@@ -61,7 +61,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -382,6 +382,19 @@ def main():
                "path": "nxs_stft_f32_host on pinned host buffers (wall clock, max over ranks): H2D | kernel | "
                        "D2H of bins 0..nfft/2 | host threads write the conjugate-mirror bins; result = the "
                        "reference's two-sided c64 tensor, bit-identical to the device entry"}
+        # transparency: the same call with the host mirror switched off (both spectrum halves over PCIe)
+        os.environ["NXS_HOST_NO_MIRROR"] = "1"
+        try:
+            step_host()
+            barrier()
+            te = time.perf_counter()
+            step_host()
+            barrier()
+            e2e["ms_per_step_full_d2h_no_host_mirror"] = 1e3 * (time.perf_counter() - te)
+        finally:
+            del os.environ["NXS_HOST_NO_MIRROR"]
+        step_host()  # leave the mirrored result in zh for the checks below
+        e2e["host_timeline_ms"] = [round(1e3 * t, 2) for t in _lib.host_timeline(local_rank)]
         if rank == 0:
             got = zh[0, :16].numpy()
             e2e["parity"] = float((np.abs(got - zo).max(-1) / np.abs(zo).max(-1)).max())
