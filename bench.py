@@ -232,7 +232,13 @@ def other_kernels(torch, nx, _lib, A, dev, local_rank, peak):
     ms = timed(lambda: _lib.check(lib.nxs_fir_f32_dev(ctx, A.ptr(x4), C4, L, L, A.ptr(taps), 2049, 1, A.ptr(y4), L, s), ctx),
                iters=3)
     out["fir_cfg4"] = entry(ms, 8 * C4 * L, C4 * L, "samples_per_s")
-    out["fir_cfg4"]["note"] = "instruction-issue-bound at K = 2049 (two 4096-pt complex FFTs per 4096 outputs), not HBM-bound"
+    # fp32 roofline (SURVEY 8d asks for both): 1821 flops per thread per block pair in the kernel's SASS
+    # (768 FADD + 327 FMUL + 2 x 363 FFMA) x 256 threads / 4096 outputs = 113.8 flop per output sample
+    tfl = 113.8 * C4 * L / (ms * 1e-3) / 1e12
+    fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12  # SMs x lanes x FMA x max SM clock
+    out["fir_cfg4"].update({"fp32_tflops": tfl, "fp32_peak_tflops": fp32_peak, "frac_of_fp32_peak": tfl / fp32_peak,
+                            "note": "instruction-issue-bound at K = 2049 (two 4096-pt complex FFTs per 4096 outputs; ncu: "
+                                    "76 % of issue slots busy, DRAM 11 %), not HBM-bound"})
     del x4, y4
     torch.cuda.empty_cache()
     return out
