@@ -4,15 +4,21 @@
 // (:611-625) -> * window (:628) -> overlap_and_add (:627-628, :684-735) -> divide by the
 // overlap-added |window|^2 with the `> 1e-10 else 1` guard (:630-637), returning c64.
 //
-// A CTA owns a segment of consecutive frames of one channel and walks it in batches of G
-// frames.  Each group of T threads inverse-transforms one frame (full complex FFT through the
-// re/im swap identity), multiplies by the prepared window w * S / nfft and leaves the frame in
-// shared memory; then the whole CTA gathers the batch's overlap-add: every output sample sums
-// its covering frames in ascending frame order plus a carry kept in shared memory from the
-// previous batch, so there are no atomics and the result is deterministic.  The normaliser is
-// accumulated the same way from |w|^2, which reproduces the reference's edge behaviour (fewer
-// covering frames at both ends) exactly.  Segments after the first recompute the few frames
-// that overlap their start (warm-up batches) instead of exchanging partial sums.
+// Kernels, fastest first (launch_istft picks):
+//   istft_rola_kernel      hop = N/2, N/4, N/8: a group of T threads walks consecutive frames
+//                          and keeps the running overlap-add in registers (no CTA barrier, no
+//                          atomics, TMA-staged input) -- the hot path
+//   istft_kernel           any hop: a CTA owns a segment of frames, every group inverse-
+//                          transforms one frame into shared memory and the CTA gathers the
+//                          overlap-add (ascending frame order + a carry: deterministic)
+//   ifft_frames_kernel /   nfft >= 4096 with an unsupported hop, and generic lengths: frames
+//   istft_dft_frames_kernel  to a scratch tensor, then istft_ola_norm_kernel gathers
+//   istft_edge_f64_kernel  always last: recomputes the ill-conditioned head / tail samples in
+//                          double, as the reference's f64 backend effectively does
+// Segments after the first recompute the few frames that overlap their start (warm-up)
+// instead of exchanging partial sums.  The normaliser is accumulated the same way from
+// |w|^2, which reproduces the reference's edge behaviour (fewer covering frames at both
+// ends) exactly.
 #include <math.h>
 #include <stdlib.h>
 
@@ -868,8 +874,6 @@ static int launch_istft_main(nxs_ctx* ctx, const float2* z, int64_t channels, in
   ctx->launches++;
   NXS_CUDA(ctx, cudaGetLastError());
   return run_ola_norm(ctx, (const float2*)ctx->d_scratch, channels, num_frames, nfft, hop, a.out_len, window, y, st);
-  // (unreachable)
-  return NXS_OK;
 }
 
 }  // namespace nxs

@@ -186,14 +186,19 @@ __global__ void __launch_bounds__(THREADS) stft_r2c_kernel(const StftArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Staged variant (the hot path): a CTA walks tiles of G consecutive frames of one channel.
-// The contiguous span a tile needs, (G-1)*hop + nfft samples, is brought into shared memory
-// by ONE cp.async.bulk (TMA, 1-D) signalled through an mbarrier, double-buffered so the
-// next tile's span lands while this tile's FFTs run: every input sample crosses HBM/L2 once
-// per tile although nfft/hop frames use it, and no thread ever waits on a global load.
-// Groups synchronise on their own named barrier, so the G frames of a tile drift apart and
-// overlap their FP and shared-memory phases.  Tiles that touch the padding region (or are
-// not 16-byte aligned) take the per-thread load path instead.
+// Staged variant (the hot path).  Input arrives by cp.async.bulk (TMA, 1-D) signalled through
+// mbarriers, so no thread ever waits on a global load, and groups synchronise on their own
+// named barrier, so the frames in flight on an SM drift apart and overlap their FP, shared-
+// memory and global phases.  Two staging layouts:
+//   per tile  (PERGROUP = false, the first version): a CTA walks tiles of G consecutive frames
+//             of one channel and ONE bulk copy brings the tile's contiguous span,
+//             (G-1)*hop + nfft samples, double-buffered; a CTA-wide barrier per tile.
+//   per group (PERGROUP = true, what ships): every group stages its own frame and free-runs;
+//             the nfft/hop-fold re-read of the input is served by L2, and no CTA-wide barrier
+//             exists in the steady state.
+// Tiles that touch the padding region (or are not 16-byte aligned) take the per-thread load
+// path instead.  MODE selects the epilogue: the reference's two-sided spectrum, the one-sided
+// half (bins 0 .. nfft/2), or the fused log-mel reduction (the spectrum is never stored).
 // ------------------------------------------------------------------------------------------
 // HOPDIV: the stage holds spans for hop <= nfft / HOPDIV; TWREG: twiddles in registers, else a
 // shared-memory copy of the per-pass table.
