@@ -219,7 +219,9 @@ struct StagedCfg {
   static constexpr int G = THREADS / PL::T, NFFT = 2 * PL::N;
   static constexpr int NSTAGE = LEAN ? 1 : 2, NXBUF = LEAN ? 1 : 2;
   // floats per stage: one tile span, or G private frames
-  static constexpr int STAGE = PERGROUP ? G * NFFT : NFFT + (G - 1) * (NFFT / HOPDIV);
+  // (per-group frames carry 4 floats of slack: the copy starts at the 16-byte boundary below the frame)
+  static constexpr int FRAME_STAGE = NFFT + 4;
+  static constexpr int STAGE = PERGROUP ? G * FRAME_STAGE : NFFT + (G - 1) * (NFFT / HOPDIV);
   static constexpr size_t BUF_BYTES = size_t(G) * NXBUF * PL::BUF * sizeof(cpx);
   static constexpr size_t WIN_OFF = BUF_BYTES;
   static constexpr size_t STAGE_OFF = WIN_OFF + size_t(NFFT) * sizeof(float);
@@ -292,23 +294,27 @@ __global__ void __launch_bounds__(CF::THREADS, MINB) stft_r2c_staged_kernel(cons
     gact = left < G ? (int)left : G;
     src0 = (int64_t)m0 * hop - a.pad_lo;
     if constexpr (CF::PERGROUP) {
+      // any hop: the copy covers [s & ~3, ...) in whole 16-byte units and must stay inside the row
       const int64_t s = src0 + (int64_t)g * hop;
-      return g < gact && s >= 0 && s + NFFT <= a.L;
+      return g < gact && s >= 0 && (s & ~(int64_t)3) + (((s & 3) + NFFT + 3) & ~3) <= a.L;
     } else {
       return src0 >= 0 && src0 + (int64_t)(gact - 1) * hop + NFFT <= a.L;
     }
   };
   // mbarrier / stage buffer of (stage) for this thread's group
   const uint32_t mybar = CF::PERGROUP ? bar0 + 16 * g : bar0;
-  float* const mystage = CF::PERGROUP ? stage0 + (size_t)g * NFFT : stage0;
+  float* const mystage = CF::PERGROUP ? stage0 + (size_t)g * CF::FRAME_STAGE : stage0;
   auto issue = [&](int tile, int stage) {
     int c, m0, gact;
     int64_t src0;
     if (tile_geom(tile, c, m0, gact, src0)) {
-      const uint32_t bytes =
-          (uint32_t)((CF::PERGROUP ? NFFT : (gact - 1) * hop + NFFT) * sizeof(float));
       const uint32_t bar = mybar + 8 * stage;
-      const int64_t s = CF::PERGROUP ? src0 + (int64_t)g * hop : src0;
+      int64_t s = CF::PERGROUP ? src0 + (int64_t)g * hop : src0;
+      uint32_t bytes = (uint32_t)((CF::PERGROUP ? NFFT : (gact - 1) * hop + NFFT) * sizeof(float));
+      if constexpr (CF::PERGROUP) {
+        bytes = (uint32_t)((((s & 3) + NFFT + 3) & ~3) * sizeof(float));
+        s &= ~(int64_t)3;
+      }
       mbar_expect_tx(bar, bytes);
       tma_load_1d(smem_u32(mystage + (size_t)stage * CF::STAGE), a.x + (int64_t)c * a.x_ld + s, bytes, bar);
     }
@@ -338,20 +344,35 @@ __global__ void __launch_bounds__(CF::THREADS, MINB) stft_r2c_staged_kernel(cons
       mbar_wait(mybar + 8 * stage, (phase_bits >> stage) & 1);
       phase_bits ^= (1u << stage);
       if (active) {
-        const float2* __restrict__ xp = reinterpret_cast<const float2*>(
-            mystage + (size_t)stage * CF::STAGE + (CF::PERGROUP ? (size_t)0 : (size_t)g * hop));
+        // offset of the frame inside the staged copy (per group: 0..3 samples past the 16-byte boundary)
+        const int off = CF::PERGROUP ? (int)((src0 + (int64_t)g * hop) & 3) : g * hop;
+        const float* __restrict__ xs = mystage + (size_t)stage * CF::STAGE + off;
         const float2* __restrict__ wp = reinterpret_cast<const float2*>(wsm);
+        if (!CF::PERGROUP || !(off & 1)) {
+          const float2* __restrict__ xp = reinterpret_cast<const float2*>(xs);
 #pragma unroll
-        for (int b = 0; b < B0; ++b)
+          for (int b = 0; b < B0; ++b)
 #pragma unroll
-          for (int q = 0; q < R0; ++q) {
-            const int i = fft_in_index<PL>(t, b, q);
-            const float2 xx = xp[i];
-            float2 ww;
-            if constexpr (CF::WINREG) ww = wreg[b * R0 + q];
-            else ww = wp[i];
-            v[b * R0 + q] = make_float2(xx.x * ww.x, xx.y * ww.y);
-          }
+            for (int q = 0; q < R0; ++q) {
+              const int i = fft_in_index<PL>(t, b, q);
+              const float2 xx = xp[i];
+              float2 ww;
+              if constexpr (CF::WINREG) ww = wreg[b * R0 + q];
+              else ww = wp[i];
+              v[b * R0 + q] = make_float2(xx.x * ww.x, xx.y * ww.y);
+            }
+        } else {  // odd sample offset: the pairs are not 8-byte aligned in shared memory
+#pragma unroll
+          for (int b = 0; b < B0; ++b)
+#pragma unroll
+            for (int q = 0; q < R0; ++q) {
+              const int i = fft_in_index<PL>(t, b, q);
+              float2 ww;
+              if constexpr (CF::WINREG) ww = wreg[b * R0 + q];
+              else ww = wp[i];
+              v[b * R0 + q] = make_float2(xs[2 * i] * ww.x, xs[2 * i + 1] * ww.y);
+            }
+        }
       } else {
 #pragma unroll
         for (int i = 0; i < P; ++i) v[i] = make_float2(0.f, 0.f);
@@ -653,7 +674,10 @@ static int variant_env() {
 template <class CF>
 static bool staged_ok(const StftArgs& a, int64_t channels) {
   const int64_t tiles = ((a.M + CF::G - 1) / CF::G) * channels;
-  return a.nload == CF::NFFT && a.hop % 4 == 0 && (CF::PERGROUP || a.hop <= CF::NFFT / CF::HOPDIV) && a.pad_lo % 4 == 0 && a.x_ld % 4 == 0 &&
+  // per-group staging takes any hop / padding (each copy starts at the 16-byte boundary below its frame);
+  // the per-tile layout needs aligned spans.  Rows must start 16-byte aligned either way.
+  const bool aligned = CF::PERGROUP || (a.hop % 4 == 0 && a.pad_lo % 4 == 0 && a.hop <= CF::NFFT / CF::HOPDIV);
+  return a.nload == CF::NFFT && aligned && a.x_ld % 4 == 0 &&
          (reinterpret_cast<uintptr_t>(a.x) & 15) == 0 && tiles < (int64_t(1) << 30) &&
          CF::SMEM <= 231424;
 }

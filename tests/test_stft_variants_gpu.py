@@ -34,3 +34,20 @@ def test_staged_hops(nfft, hop_num, hop_den):
     z, _, _ = nx.stft(x, w, **kw)
     zo, _, _ = o.stft_fast(x, w, **kw)
     assert frame_rel_err(z, zo) <= TOL
+
+
+@pytest.mark.parametrize("nfft", [512, 1024, 2048, 4096])
+@pytest.mark.parametrize("hop", [250, 441, 333, 6, 1])
+@pytest.mark.parametrize("padding", ["valid", "same"])
+def test_staged_any_hop_and_padding_offset(nfft, hop, padding):
+    """Frames that start at any sample offset are still TMA-staged: the copy starts at the 16-byte
+    boundary below the frame (odd offsets read the stage with 4-byte loads).  `:same` padding makes
+    pad_lo odd (nfft/2 - 1), shifting every frame start."""
+    L = 30 * nfft + 123 if hop > 6 else 3 * nfft + 57
+    x = synth((2, L + (-L) % 4), 51 + nfft + hop)   # row stride a multiple of 4 samples -> staged path
+    w = o.hann(nfft)
+    kw = dict(overlap_length=nfft - hop, fft_length=nfft, sampling_rate=48000, window_padding=padding)
+    z, _, _ = nx.stft(x, w, **kw)
+    zo, _, _ = o.stft_fast(x, w, **kw)
+    assert z.shape == zo.shape
+    assert frame_rel_err(z, zo) <= TOL
