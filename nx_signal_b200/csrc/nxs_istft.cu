@@ -532,6 +532,178 @@ static int run_istft(nxs_ctx* ctx, IstftArgs a, int64_t channels, cudaStream_t s
   return NXS_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// Ring overlap-add variant: any hop <= N (z_len == N).  Same per-group walk as the register
+// kernel, but the running overlap-add lives in a per-group ring of N complex values in shared
+// memory: after the inverse FFT every thread adds its P windowed samples at (base + n) mod N,
+// the hop samples at the ring's base are then final (stored, normalised, zeroed) and the base
+// advances by hop -- no data moves, no CTA-wide barrier, deterministic.  Costs ~2 P extra
+// shared-memory accesses per thread and frame over the register form, and serves the hops
+// the register form cannot (hop not a multiple of the group width).
+// ------------------------------------------------------------------------------------------
+template <class PL, int THREADS>
+struct RingCfg {
+  static constexpr int G = THREADS / PL::T, N = PL::N;
+  static constexpr size_t GROUP_BYTES = (2 * size_t(N) + size_t(PL::BUF)) * sizeof(cpx);  // stage + ring + exchange
+  static constexpr size_t WIN_OFF = size_t(G) * GROUP_BYTES;
+  static constexpr size_t NORM_OFF = WIN_OFF + size_t(N) * sizeof(float);  // interior normaliser, hop <= N floats
+  static constexpr size_t TW_OFF = NORM_OFF + size_t(N) * sizeof(float);
+  static constexpr size_t BAR_OFF = TW_OFF + size_t(PL::TWC_TOTAL) * sizeof(cpx);
+  static constexpr size_t SMEM = BAR_OFF + 8 * size_t(G) + 8;
+};
+
+template <class PL, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) istft_ring_kernel(const IstftArgs a) {
+  using CF = RingCfg<PL, THREADS>;
+  constexpr int N = PL::N, T = PL::T, P = PL::P, G = CF::G;
+  constexpr int R0 = PL::R(0), B0 = P / R0;
+  constexpr int RL = PL::R(PL::NP - 1), BL = P / RL;
+  static_assert((N / RL) % T == 0, "last pass must leave n = t (mod T) in every thread");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tid = threadIdx.x, g = tid / T, t = tid % T;
+  cpx* const stage = reinterpret_cast<cpx*>(smem_raw + size_t(g) * CF::GROUP_BYTES);
+  cpx* const ring = stage + N;
+  cpx* const xbuf = ring + N;
+  float* wsm = reinterpret_cast<float*>(smem_raw + CF::WIN_OFF);
+  float* normsm = reinterpret_cast<float*>(smem_raw + CF::NORM_OFF);
+  cpx* twsm = reinterpret_cast<cpx*>(smem_raw + CF::TW_OFF);
+  const uint32_t mybar = smem_u32(smem_raw + CF::BAR_OFF) + 8 * g;
+  const int hop = a.hop;
+  const int kcov = (N + hop - 1) / hop;  // frames covering an interior sample (at most)
+
+  auto w2 = [&](int n) {
+    const float w = fabsf(__ldg(a.w + n));
+    return (float)((double)w * (double)w);  // Nx.abs(window) ** 2, f32
+  };
+  for (int i = tid; i < N; i += THREADS) wsm[i] = a.wprep[i];
+  // interior normaliser of the sample at offset p < hop of a frame that has all its predecessors:
+  // frames m, m-1, ... contribute w2[p], w2[p + hop], ...; ascending frame order = descending offset
+  for (int p = tid; p < hop; p += THREADS) {
+    float nr = 0.f;
+    for (int k = (N - 1 - p) / hop; k >= 0; --k) nr += w2(p + k * hop);
+    normsm[p] = nr;
+  }
+  for (int i = tid; i < PL::TWC_TOTAL; i += THREADS) twsm[i] = a.tw[i];
+  if (tid == 0) {
+    for (int i = 0; i < G; ++i) mbar_init(smem_u32(smem_raw + CF::BAR_OFF) + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  TwDeriveC<PL> tw;
+  tw.init(twsm, t);
+  const GroupSync<T> sync{1 + g};
+
+  auto norm_at = [&](int64_t p) {  // exact normaliser at output position p (edges: fewer covering frames)
+    int64_t m_lo = p - N + 1 <= 0 ? 0 : (p - N + hop) / hop;
+    int64_t m_hi = p / hop;
+    if (m_hi > a.M - 1) m_hi = a.M - 1;
+    float nr = 0.f;
+    for (int64_t m = m_lo; m <= m_hi; ++m) nr += w2((int)(p - m * hop));
+    return nr;
+  };
+  auto seg_bounds = [&](int seg, int& c, int64_t& mb, int64_t& ms, int64_t& me) {
+    c = seg / a.segs_per_channel;
+    const int si = seg - c * a.segs_per_channel;
+    ms = (int64_t)si * a.seg_frames;
+    me = ms + a.seg_frames;
+    if (me > a.M) me = a.M;
+    mb = ms - (kcov - 1);
+    if (mb < 0) mb = 0;
+  };
+  auto issue = [&](int c, int64_t m) {
+    mbar_expect_tx(mybar, (uint32_t)(N * sizeof(cpx)));
+    tma_load_1d(smem_u32(stage), a.z + ((int64_t)c * a.M + m) * N, (uint32_t)(N * sizeof(cpx)), mybar);
+  };
+
+  const int gid = blockIdx.x * G + g, ngroups = gridDim.x * G;
+  uint32_t parity = 0;
+  int seg = gid;
+  int c = 0;
+  int64_t mb = 0, ms = 0, me = 0;
+  if (seg < a.total_segs) {
+    seg_bounds(seg, c, mb, ms, me);
+    if (t == 0) issue(c, mb);
+  }
+  while (seg < a.total_segs) {
+    float2* __restrict__ yc = a.y + (int64_t)c * a.out_len;
+    for (int i = t; i < N; i += T) ring[i] = make_float2(0.f, 0.f);
+    int base = 0;  // ring index of the current frame's sample 0
+    const int nseg = seg + ngroups;
+    int nc = 0;
+    int64_t nmb = 0, nms = 0, nme = 0;
+    if (nseg < a.total_segs) seg_bounds(nseg, nc, nmb, nms, nme);
+
+    for (int64_t m = mb; m < me; ++m) {
+      cpx v[P];
+      mbar_wait(mybar, parity);
+      parity ^= 1;
+#pragma unroll
+      for (int b = 0; b < B0; ++b)
+#pragma unroll
+        for (int q = 0; q < R0; ++q) {
+          const cpx val = stage[fft_in_index<PL>(t, b, q)];
+          v[b * R0 + q] = make_float2(val.y, val.x);  // swap: ifft(x) = swap(fft(swap(x))) / n
+        }
+      sync();  // stage read out; ring zeroing / the previous frame's emission are complete
+      if (t == 0) {
+        if (m + 1 < me) issue(c, m + 1);
+        else if (nseg < a.total_segs) issue(nc, nmb);
+      }
+      block_fft_single<PL>(v, t, xbuf, tw, sync);
+      // ring[(base + n) mod N] += frame[n] * w'[n], n = t + j*T: each thread owns its own slots
+#pragma unroll
+      for (int b = 0; b < BL; ++b)
+#pragma unroll
+        for (int q = 0; q < RL; ++q) {
+          const int n = t + (b + q * BL) * T;
+          const cpx r = v[fft_out_reg<PL>(b, q)];
+          const float w = wsm[n];
+          int idx = base + n;
+          if (idx >= N) idx -= N;
+          cpx acc = ring[idx];
+          acc.x += r.y * w;
+          acc.y += r.x * w;
+          ring[idx] = acc;
+        }
+      sync();  // the frame is added: its first hop samples are final
+      const bool emit = m >= ms;
+      const bool interior = m >= kcov - 1;
+      const int64_t pos = m * (int64_t)hop;
+      for (int p = t; p < hop; p += T) {
+        int idx = base + p;
+        if (idx >= N) idx -= N;
+        if (emit) {
+          const cpx acc = ring[idx];
+          const float nr = interior ? normsm[p] : norm_at(pos + p);
+          const float d = nr > 1.0e-10f ? nr : 1.0f;  // select(norm > 1e-10, norm, 1.0)
+          __stcs(yc + pos + p, make_float2(acc.x / d, acc.y / d));
+        }
+        ring[idx] = make_float2(0.f, 0.f);  // becomes the tail of the next frames
+      }
+      base += hop;
+      if (base >= N) base -= N;
+    }
+    if (me == a.M) {  // tail of the channel: the N - hop samples no further frame completes
+      sync();
+      const int64_t pos = a.M * (int64_t)hop;
+      for (int p = t; p < N - hop; p += T) {
+        int idx = base + p;
+        if (idx >= N) idx -= N;
+        const cpx acc = ring[idx];
+        const float nr = norm_at(pos + p);
+        const float d = nr > 1.0e-10f ? nr : 1.0f;
+        __stcs(yc + pos + p, make_float2(acc.x / d, acc.y / d));
+      }
+    }
+    sync();  // emission done before the next segment zeroes the ring
+    seg = nseg;
+    c = nc;
+    mb = nmb;
+    ms = nms;
+    me = nme;
+  }
+}
+
 // register overlap-add kernel: requires z_len == N, hop * HOPDIV == N, hop % T == 0 and 16-byte aligned rows
 template <class PL, int THREADS, int MINB, int HOPDIV, bool XD = false>
 static int run_istft_rola(nxs_ctx* ctx, IstftArgs a, int64_t channels, cudaStream_t st) {
@@ -550,6 +722,62 @@ static int run_istft_rola(nxs_ctx* ctx, IstftArgs a, int64_t channels, cudaStrea
   const int64_t total_frames = channels * a.M;
   int64_t seg = (total_frames + groups * 4 - 1) / (groups * 4);
   const int64_t seg_min = 16 * (HOPDIV - 1) > 32 ? 16 * (HOPDIV - 1) : 32;
+  if (seg < seg_min) seg = seg_min;
+  if (seg > a.M) seg = a.M;
+  a.seg_frames = (int)seg;
+  a.segs_per_channel = (int)((a.M + seg - 1) / seg);
+  const int64_t total = int64_t(a.segs_per_channel) * channels;
+  if (total >= (int64_t(1) << 31)) return NXS_EUNSUPPORTED;
+  a.total_segs = (int)total;
+  a.warm_batches = 0;
+  int64_t grid = (total + CF::G - 1) / CF::G;
+  if (grid > int64_t(ctx->sm_count) * occ) grid = int64_t(ctx->sm_count) * occ;
+  prof_begin(ctx, st);
+  kern<<<(unsigned)grid, THREADS, CF::SMEM, st>>>(a);
+  prof_end(ctx, st);
+  ctx->launches++;
+  NXS_CUDA(ctx, cudaGetLastError());
+  return NXS_OK;
+}
+
+template <class PL>
+static int get_twc_table(nxs_ctx* ctx, float2** out) {
+  const uint64_t key = (uint64_t(PL::N) << 32) | (uint64_t(PL::T) << 8) | uint64_t(PL::NP) | (uint64_t(1) << 62) |
+                       (uint64_t(1) << 61);
+  auto it = ctx->tables.find(key);
+  if (it != ctx->tables.end()) {
+    *out = it->second.tw;
+    return NXS_OK;
+  }
+  std::vector<float2> tw(PL::TWC_TOTAL > 0 ? PL::TWC_TOTAL : 1);
+  build_compact_twiddles<PL>(tw.data());
+  PlanTables t;
+  NXS_CUDA(ctx, cudaMalloc(&t.tw, tw.size() * sizeof(float2)));
+  NXS_CUDA(ctx, cudaMemcpy(t.tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+  ctx->tables[key] = t;
+  *out = t.tw;
+  return NXS_OK;
+}
+
+// ring overlap-add kernel: requires z_len == N, 16-byte aligned rows, hop <= N
+template <class PL, int THREADS, int MINB>
+static int run_istft_ring(nxs_ctx* ctx, IstftArgs a, int64_t channels, cudaStream_t st) {
+  using CF = RingCfg<PL, THREADS>;
+  float2* tw = nullptr;
+  int rc = get_twc_table<PL>(ctx, &tw);
+  if (rc) return rc;
+  a.tw = tw;
+  auto kern = istft_ring_kernel<PL, THREADS, MINB>;
+  if (CF::SMEM > 232448) return NXS_EUNSUPPORTED;
+  NXS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF::SMEM));
+  int occ = 1;
+  NXS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, CF::SMEM));
+  if (occ < 1) occ = 1;
+  const int64_t kcov = (PL::N + a.hop - 1) / a.hop;
+  const int64_t groups = int64_t(ctx->sm_count) * occ * CF::G;
+  const int64_t total_frames = channels * a.M;
+  int64_t seg = (total_frames + groups * 4 - 1) / (groups * 4);
+  const int64_t seg_min = 16 * (kcov - 1) > 32 ? 16 * (kcov - 1) : 32;  // <= 6 % recomputed frames
   if (seg < seg_min) seg = seg_min;
   if (seg > a.M) seg = a.M;
   a.seg_frames = (int)seg;
@@ -842,6 +1070,18 @@ static int launch_istft_main(nxs_ctx* ctx, const float2* z, int64_t channels, in
       default: break;
     }
     if (rc || done) return rc;
+    // any other hop (<= N, at most 64 covering frames): ring overlap-add
+    const bool ring_ok = a.z_len == nfft && (reinterpret_cast<uintptr_t>(a.z) & 15) == 0 && a.hop * 64 >= nfft &&
+                         !getenv("NXS_ISTFT_NO_ROLA") && !getenv("NXS_ISTFT_NO_RING");
+    if (ring_ok) {
+      switch (nfft) {
+        case 256: return run_istft_ring<Plan<256, 32, 8, 8, 4>, 256, 2>(ctx, a, channels, st);
+        case 512: return run_istft_ring<Plan<512, 64, 8, 8, 8>, 256, 2>(ctx, a, channels, st);
+        case 1024: return run_istft_ring<Plan<1024, 64, 16, 8, 8>, 256, 2>(ctx, a, channels, st);
+        case 2048: return run_istft_ring<Plan<2048, 128, 16, 16, 8>, 256, 1>(ctx, a, channels, st);
+        default: break;  // 4096: stage + ring + exchange of two groups exceed shared memory -> scratch path below
+      }
+    }
   }
   if (pow2 && nfft >= 32 && nfft <= 8192) {
     switch (nfft) {

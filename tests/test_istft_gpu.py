@@ -256,3 +256,40 @@ def test_rola_two_exchange_buffer_variant(monkeypatch):
     yo = o.istft_fast(z, w, **kw)
     monkeypatch.setenv("NXS_ISTFT_VARIANT", "1")
     assert rel(nx.istft(z, w, **kw), yo) <= TOL
+
+
+# ---- ring overlap-add kernel (any hop <= N) -----------------------------------------------------
+@pytest.mark.parametrize("nfft", [256, 512, 1024, 2048])
+@pytest.mark.parametrize("hop_spec", ["250/1024", "441/1024", "3/16", "1000/1024", "1/1", "17/1024", "1/40"])
+@pytest.mark.parametrize("M", [1, 3, 400])
+def test_ring_hops(nfft, hop_spec, M):
+    num, den = (int(v) for v in hop_spec.split("/"))
+    hop = max(1, nfft * num // den)
+    rng = np.random.default_rng(nfft + hop + M)
+    z = (rng.standard_normal((2, M, nfft)) + 1j * rng.standard_normal((2, M, nfft))).astype(np.complex64)
+    w = (o.hann(nfft) + np.float32(0.07)).astype(np.float32)
+    kw = dict(overlap_length=nfft - hop, fft_length=nfft)
+    y = nx.istft(z, w, **kw)
+    yo = o.istft_fast(z, w, **kw)
+    assert y.shape == (2, M * hop + nfft - hop)
+    assert rel(y, yo) <= TOL
+
+
+def test_ring_many_segments_matches_gather_kernel(monkeypatch):
+    import torch
+
+    C, M, nfft, hop = 3, 30_000, 1024, 250
+    z = torch.view_as_complex(torch.randn(C, M, nfft, 2, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5)))
+    w = torch.from_numpy(o.hann(nfft)).cuda()
+    kw = dict(overlap_length=nfft - hop, fft_length=nfft)
+    y1 = nx.istft(z, w, **kw)
+    torch.cuda.synchronize()
+    monkeypatch.setenv("NXS_ISTFT_NO_RING", "1")
+    y2 = nx.istft(z, w, **kw)
+    torch.cuda.synchronize()
+    a, b = y1.cpu().numpy(), y2.cpu().numpy()
+    assert rel(a, b) <= 2e-6
+    m0, m1 = 12_000, 12_500
+    yo = o.istft_fast(z[1, m0:m1].cpu().numpy(), o.hann(nfft), **kw)
+    lo, hi = nfft, (m1 - m0) * hop - nfft
+    assert np.abs(a[1, m0 * hop + lo: m0 * hop + hi] - yo[lo:hi]).max() / np.abs(yo).max() <= TOL
