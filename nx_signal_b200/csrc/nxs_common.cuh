@@ -88,6 +88,8 @@ void prof_begin(nxs_ctx* ctx, cudaStream_t st);
 void prof_end(nxs_ctx* ctx, cudaStream_t st);
 int ensure_coef(nxs_ctx* ctx, size_t bytes);
 int ensure_scratch(nxs_ctx* ctx, size_t bytes);
+// exp(+2 pi i m / n), m < n, in double (exact at multiples of pi/2); cached per context
+int get_dft_table_f64(nxs_ctx* ctx, int64_t n, double2** out);
 
 // padding geometry shared by stft / as_windowed (lib/nx_signal.ex:303-331, 343-349)
 struct PadGeom {

@@ -35,23 +35,43 @@ struct FirArgs {
   int total_tiles;
   const float2* H;  // [F], already divided by F
   const float2* tw;
+  int accumulate = 0;  // 1: y += result (later partitions of a long filter)
 };
 
-// H[k] = (1/F) sum_j h[j] exp(-2 pi i j k / F), accumulated in double
+// H[k] = (1/F) sum_j h[j] exp(-2 pi i j k / F), accumulated in double.  One warp per bin k (the
+// taps are split over the lanes); tab[m] = exp(+2 pi i m / F) in double (nxs_common: get_dft_table_f64).
 __global__ void __launch_bounds__(256) fir_spectrum_kernel(const float* __restrict__ taps, int K, int F,
-                                                           float2* __restrict__ H) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+                                                           const double2* __restrict__ tab, float2* __restrict__ H) {
+  const int lane = threadIdx.x & 31;
+  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (k >= F) return;
   double re = 0.0, im = 0.0;
-  for (int j = 0; j < K; ++j) {
-    const int r = (int)(((int64_t)j * k) % F);
-    double s, c;
-    sincospi(-2.0 * (double)r / (double)F, &s, &c);
+  int idx = (int)(((int64_t)lane * k) % F);
+  const int step = (int)(((int64_t)32 * k) % F);
+  for (int j = lane; j < K; j += 32) {
+    const double2 e = tab[idx];
     const double h = (double)taps[j];
-    re += h * c;
-    im += h * s;
+    re += h * e.x;
+    im -= h * e.y;
+    idx += step;
+    if (idx >= F) idx -= F;
   }
-  H[k] = make_float2((float)(re / F), (float)(im / F));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    re += __shfl_xor_sync(0xffffffffu, re, o);
+    im += __shfl_xor_sync(0xffffffffu, im, o);
+  }
+  if (lane == 0) H[k] = make_float2((float)(re / F), (float)(im / F));
+}
+
+static int launch_fir_spectrum(nxs_ctx* ctx, const float* taps, int K, int F, float2* H, cudaStream_t st) {
+  double2* tab = nullptr;
+  int rc = get_dft_table_f64(ctx, F, &tab);
+  if (rc) return rc;
+  fir_spectrum_kernel<<<(F + 7) / 8, 256, 0, st>>>(taps, K, F, tab, H);
+  ctx->launches++;
+  NXS_CUDA(ctx, cudaGetLastError());
+  return NXS_OK;
 }
 
 template <class PL, int THREADS, int MINB>
@@ -267,7 +287,11 @@ __global__ void __launch_bounds__(THREADS, MINB) fir_ols_pg_kernel(const FirArgs
         for (int q = 0; q < R0; ++q) {
           const int i = fft_out_index<PL>(t, b, q);
           if (i >= K1) {
-            const cpx r = u[fft_out_reg<PL>(b, q)];
+            cpx r = u[fft_out_reg<PL>(b, q)];
+            if (a.accumulate) {
+              r.y += y0[i];
+              r.x += y1[i];
+            }
             __stcs(y0 + i, r.y);  // Re(y): block 0
             __stcs(y1 + i, r.x);  // Im(y): block 1
           }
@@ -281,8 +305,8 @@ __global__ void __launch_bounds__(THREADS, MINB) fir_ols_pg_kernel(const FirArgs
           if (i >= K1) {
             const cpx r = u[fft_out_reg<PL>(b, q)];
             const int64_t o0 = obase + i, o1 = o0 + a.V;
-            if (o0 >= 0 && o0 < a.out_len) __stcs(yrow + o0, r.y);
-            if (o1 >= 0 && o1 < a.out_len) __stcs(yrow + o1, r.x);
+            if (o0 >= 0 && o0 < a.out_len) __stcs(yrow + o0, a.accumulate ? r.y + yrow[o0] : r.y);
+            if (o1 >= 0 && o1 < a.out_len) __stcs(yrow + o1, a.accumulate ? r.x + yrow[o1] : r.x);
           }
         }
     }
@@ -324,9 +348,8 @@ static int run_fir(nxs_ctx* ctx, FirArgs a, int64_t channels, const float* taps,
   a.tw = tw;
   rc = ensure_scratch(ctx, size_t(F) * sizeof(float2));
   if (rc) return rc;
-  fir_spectrum_kernel<<<(F + 255) / 256, 256, 0, st>>>(taps, a.K, F, (float2*)ctx->d_scratch);
-  ctx->launches++;
-  NXS_CUDA(ctx, cudaGetLastError());
+  rc = launch_fir_spectrum(ctx, taps, a.K, F, (float2*)ctx->d_scratch, st);
+  if (rc) return rc;
   a.H = (const float2*)ctx->d_scratch;
   a.V = F - a.K + 1;
   a.b_lo = a.start / a.V;
@@ -383,12 +406,14 @@ static int run_fir_pg(nxs_ctx* ctx, FirArgs a, int64_t channels, const float* ta
   a.tw = tw;
   rc = ensure_scratch(ctx, size_t(F) * sizeof(float2));
   if (rc) return rc;
-  fir_spectrum_kernel<<<(F + 255) / 256, 256, 0, st>>>(taps, a.K, F, (float2*)ctx->d_scratch);
-  ctx->launches++;
-  NXS_CUDA(ctx, cudaGetLastError());
+  rc = launch_fir_spectrum(ctx, taps, a.K, F, (float2*)ctx->d_scratch, st);
+  if (rc) return rc;
   a.H = (const float2*)ctx->d_scratch;
   a.V = F - a.K + 1;
-  a.b_lo = a.start / a.V;
+  // blocks whose outputs fall inside [0, out_len): full-convolution indices [start, start + out_len),
+  // clipped at 0 (a later partition of a long filter has start < 0: its first outputs do not exist)
+  if (a.start + a.out_len <= 0) return NXS_OK;
+  a.b_lo = (a.start > 0 ? a.start : 0) / a.V;
   const int64_t b_hi = (a.start + a.out_len - 1) / a.V;
   const int64_t pairs = (b_hi - a.b_lo + 2) / 2;
   const int64_t tiles = pairs * channels;
@@ -467,15 +492,39 @@ int launch_fir(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, i
     if (pg) return run_fir_pg<Plan<1024, 64, 8, 16, 8>, 384, 2>(ctx, a, channels, taps, st);
     return run_fir<Plan<1024, 64, 8, 16, 8>, 256, 2>(ctx, a, channels, taps, st);
   }
-  if (K > 513 && K <= 3585) {
+  if (K > 513 && (K <= 3585 || pg)) {
     using PL = Plan<4096, 256, 16, 16, 16>;
-    // three groups per SM when the stage (V + F samples) is small enough, else two
-    const bool three = FirPgCfg<PL, 768>::smem(int(4096 - K + 1)) <= 232448;
-    if (pg && variant != 1 && three) return run_fir_pg<PL, 768, 1>(ctx, a, channels, taps, st);
-    if (pg) return run_fir_pg<PL, 512, 1>(ctx, a, channels, taps, st);
-    return run_fir<Plan<4096, 256, 16, 16, 16>, 256, 2>(ctx, a, channels, taps, st);
+    if (!pg) return run_fir<PL, 256, 2>(ctx, a, channels, taps, st);
+    // Long filters are cut into n equal runs of KP taps and the partial convolutions accumulated,
+    // y[n] += (x * h_p)[n - p KP]: a block of F = 4096 yields 4097 - KP outputs, so the work per
+    // output is ~ n / (4097 - K / n); n = 1 up to K ~ 2900, then 2, ...  (K = 3585 in one pass would
+    // keep only 512 of every 4096 samples.)
+    int64_t n_best = 1;
+    double c_best = 1e300;
+    for (int64_t n = 1; n <= (K + 511) / 512; ++n) {
+      const int64_t kp = (K + n - 1) / n;
+      if (kp > 3585) continue;
+      const double c = (double(n) + 0.15 * double(n - 1)) / double(4097 - kp);  // later passes read-modify-write y
+      if (c < c_best) {
+        c_best = c;
+        n_best = n;
+      }
+    }
+    const int64_t KP = (K + n_best - 1) / n_best;
+    for (int64_t p = 0; p * KP < K; ++p) {
+      FirArgs ap = a;
+      ap.K = (int)(K - p * KP < KP ? K - p * KP : KP);
+      ap.start = a.start - p * KP;
+      ap.accumulate = p > 0;
+      // three groups per SM when the stage (V + F samples) is small enough, else two
+      const bool three = variant != 1 && FirPgCfg<PL, 768>::smem(int(4096 - ap.K + 1)) <= 232448;
+      rc = three ? run_fir_pg<PL, 768, 1>(ctx, ap, channels, taps + p * KP, st)
+                 : run_fir_pg<PL, 512, 1>(ctx, ap, channels, taps + p * KP, st);
+      if (rc) return rc;
+    }
+    return NXS_OK;
   }
-  // K < 16 or K > 3585: direct
+  // K < 16 (or the per-group kernels switched off): direct
   if (K > (int64_t(1) << 30)) return NXS_EUNSUPPORTED;
   const int64_t total = channels * out_len;
   int64_t grid = (total + 255) / 256;

@@ -972,7 +972,7 @@ __global__ void __launch_bounds__(256) istft_edge_f64_kernel(const float2* __res
   }
 }
 
-static int get_dft_table_f64(nxs_ctx* ctx, int64_t n, double2** out) {
+int get_dft_table_f64(nxs_ctx* ctx, int64_t n, double2** out) {
   const uint64_t key = (uint64_t(5) << 32) | uint64_t(n);
   auto it = ctx->dft_tables.find(key);
   if (it != ctx->dft_tables.end()) {

@@ -192,3 +192,23 @@ def test_fir_pg_matches_previous_kernel(monkeypatch):
     y2 = conv.convolve(x, taps[None, :], mode="same", method="fft")
     torch.cuda.synchronize()
     assert float((y1 - y2).abs().max() / y2.abs().max()) <= 2e-6
+
+
+@pytest.mark.parametrize("K", [2731, 2732, 3585, 3586, 4097, 4100, 6000, 10_000])
+@pytest.mark.parametrize("mode", ["full", "same", "valid"])
+def test_long_filters_by_partition(K, mode):
+    """K > 3585: the taps are cut into runs of 2049 and the partial convolutions accumulated
+    (y[n] += (x * h_p)[n - 2049 p]); 4100 leaves a 2-tap last partition."""
+    x = synth((2, 30_000 + 4 * (K % 7)), 60 + K)
+    rng = np.random.default_rng(K)
+    taps = (rng.standard_normal(K) / np.sqrt(K)).astype(np.float32)
+    y = conv.convolve(x, taps[None, :], mode=mode, method="fft")
+    assert rel(y, ref_conv(x, taps, mode)) <= TOL
+
+
+def test_long_filter_longer_than_signal():
+    x = synth((2, 3000), 5)
+    taps = (np.random.default_rng(1).standard_normal(9001) / 95).astype(np.float32)
+    for mode in ("full", "same"):  # :valid needs one operand to cover the other in every dimension (convolution.ex:131-134)
+        y = conv.convolve(x, taps[None, :], mode=mode, method="fft")
+        assert rel(y, ref_conv(x, taps, mode)) <= TOL

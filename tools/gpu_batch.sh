@@ -1,4 +1,4 @@
-OUT=gpurun_out/r01r; mkdir -p $OUT
-timeout 1200 python -m pytest tests/test_istft_gpu.py tests/test_golden_gpu.py -x -q > $OUT/pytest.log 2>&1; tail -6 $OUT/pytest.log
-{ for h in 256 250 192 441 1024 64; do timeout 120 python tools/run_istft.py 32 60 1024 $h 10; done; timeout 120 python tools/run_istft.py 32 60 2048 500 5; timeout 120 python tools/run_istft.py 32 60 512 100 5; } > $OUT/odd_shapes.txt 2>&1
-cat $OUT/odd_shapes.txt
+OUT=gpurun_out/r01s; mkdir -p $OUT
+timeout 1200 python -m pytest tests/test_fir_conv_gpu.py -x -q > $OUT/pytest.log 2>&1; tail -4 $OUT/pytest.log
+{ for k in 2049 2731 2732 3585 4097 8193 16385; do timeout 200 python tools/run_fir.py 64 600 $k 2; done; } > $OUT/fir.txt 2>&1
+cat $OUT/fir.txt

@@ -21,5 +21,12 @@ torch.cuda.synchronize()
 _lib.profile(True); _lib.profile_read()
 for _ in range(iters): step()
 ms, n = _lib.profile_read()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(iters): step()
+e1.record(); torch.cuda.synchronize()
+call_ms = e0.elapsed_time(e1) / iters
+passes = n // iters
+ms, n = call_ms, 1  # whole call (all partitions of a long filter)
 algo = 8 * C * L
-print(f"FIR C={C} L={L} K={K}: kernel {ms/n:.4f} ms  {algo/(ms/n*1e-3)/1e9:.1f} GB/s algorithmic  {C*L/(ms/n*1e-3)/1e9:.2f} Gsamples/s")
+print(f"FIR C={C} L={L} K={K} ({passes} pass{'es' if passes != 1 else ''}): call {ms/n:.4f} ms  {algo/(ms/n*1e-3)/1e9:.1f} GB/s algorithmic  {C*L/(ms/n*1e-3)/1e9:.2f} Gsamples/s")
