@@ -1,0 +1,36 @@
+# compute-sanitizer over small cases of every hot kernel: memcheck (OOB / misaligned) and racecheck (shared-memory hazards)
+OUT=gpurun_out/sanitize; mkdir -p $OUT
+cat > /tmp/san_cases.py <<'PY'
+import sys, numpy as np, torch
+sys.path.insert(0, ".")
+import nx_signal_b200 as nx
+from oracle import nxsignal_oracle as o
+rng = np.random.default_rng(0)
+def chk(name, got, want, tol=1e-5):
+    got = np.asarray(got.cpu() if hasattr(got, "cpu") else got); e = np.abs(got - want).max() / max(np.abs(want).max(), 1e-30)
+    print(name, "rel err %.2e" % e, "OK" if e <= tol else "FAIL"); assert e <= tol
+for nfft, hop, pad in [(1024, 256, "valid"), (1024, 250, "reflect"), (1024, 441, "same"), (2048, 512, "valid"), (4096, 1024, "valid"), (512, 128, "valid"), (8192, 2048, "valid"), (256, 64, "valid")]:
+    x = rng.standard_normal((2, 12 * nfft)).astype(np.float32); w = o.hann(nfft)
+    kw = dict(overlap_length=nfft - hop, fft_length=nfft, sampling_rate=48000, window_padding=pad)
+    z, _, _ = nx.stft(torch.from_numpy(x).cuda(), torch.from_numpy(w).cuda(), **kw)
+    zo, _, _ = o.stft_fast(x, w, **kw); chk(f"stft {nfft}/{hop}/{pad}", torch.view_as_real(z), np.stack([zo.real, zo.imag], -1))
+    if nfft <= 4096:
+        m = nx.stft_mel(torch.from_numpy(x).cuda(), torch.from_numpy(w).cuda(), mel_bins=40, **kw)
+        mo = np.stack([o.stft_to_mel(zo[c], 48000, nfft, 40) for c in range(2)]); chk(f"stft_mel {nfft}", m, mo)
+for nfft, hop in [(1024, 256), (1024, 512), (1024, 128), (1024, 250), (1024, 1024), (512, 128), (2048, 512), (4096, 1024), (256, 100), (2048, 700), (4096, 1000), (128, 32)]:
+    z = (rng.standard_normal((2, 40, nfft)) + 1j * rng.standard_normal((2, 40, nfft))).astype(np.complex64); w = o.hann(nfft)
+    y = nx.istft(torch.from_numpy(z).cuda(), torch.from_numpy(w).cuda(), overlap_length=nfft - hop, fft_length=nfft)
+    yo = o.istft_fast(z, w, overlap_length=nfft - hop, fft_length=nfft); chk(f"istft {nfft}/{hop}", torch.view_as_real(y), np.stack([yo.real, yo.imag], -1))
+for K, L in [(2049, 30000), (255, 20000), (4097, 30000), (65, 5000), (600, 20001)]:
+    x = rng.standard_normal((2, L)).astype(np.float32); taps = (rng.standard_normal(K) / np.sqrt(K)).astype(np.float32)
+    y = nx.convolution.convolve(torch.from_numpy(x).cuda(), torch.from_numpy(taps).cuda()[None, :], mode="same", method="fft")
+    from scipy.signal import oaconvolve
+    full = oaconvolve(x.astype(np.float64), taps.astype(np.float64)[None, :], mode="full", axes=-1); s = (K - 1) // 2
+    chk(f"fir K={K}", y, full[:, s:s + L].astype(np.float32))
+z = (rng.standard_normal((2, 50, 1024)) + 1j * rng.standard_normal((2, 50, 1024))).astype(np.complex64)
+m = nx.stft_to_mel(torch.from_numpy(z).cuda(), 48000, fft_length=1024, mel_bins=128)
+chk("stft_to_mel", m, np.stack([o.stft_to_mel(z[c], 48000, 1024, 128) for c in range(2)]))
+torch.cuda.synchronize(); print("all cases done")
+PY
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 1 python /tmp/san_cases.py > $OUT/memcheck.log 2>&1; echo "memcheck rc=$?" | tee -a $OUT/memcheck.log; grep -c "OK" $OUT/memcheck.log; grep -E "ERROR SUMMARY|Invalid|FAIL" $OUT/memcheck.log | head -5
+timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 1 python /tmp/san_cases.py > $OUT/racecheck.log 2>&1; echo "racecheck rc=$?" | tee -a $OUT/racecheck.log; grep -E "RACECHECK SUMMARY|hazard|FAIL" $OUT/racecheck.log | sort | uniq -c | head -10
