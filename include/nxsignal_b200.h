@@ -183,6 +183,23 @@ int nxs_istft_c64_host(nxs_ctx* ctx, const float* z, int64_t channels, int64_t n
                        int64_t z_len, const float* window, int64_t frame_length, int64_t hop,
                        int64_t fft_length, int scaling, double sampling_rate, float* y);
 
+/* ---- c2r ISTFT (opt-in extension, not a reference head) ---
+ * The counterpart of nxs_stft_onesided_f32_dev: z [channels][num_frames][z_ld]
+ * c64 holds bins 0 .. fft_length/2 (z_ld >= fft_length/2 + 1), y
+ * [channels][num_frames*hop + frame_length - hop] is REAL f32 and equals
+ * Re(NxSignal.istft(ext(z), window, opts)) (lib/nx_signal.ex:582-638) with
+ * ext(z)[k] = conj(z[fft_length - k]) for k > fft_length/2.  fft_length must be
+ * even and equal frame_length.  fft_length in {512, 1024, 2048, 4096} with
+ * hop = N/2, N/4, N/8 runs the packed half-length kernel (asynchronous); other
+ * shapes extend the spectrum on the device, run the c64 path and synchronise
+ * the stream before returning. */
+int nxs_istft_c2r_f32_dev(nxs_ctx* ctx, const float* z, int64_t channels, int64_t num_frames,
+                          int64_t z_ld, const float* window, int64_t frame_length, int64_t hop,
+                          int64_t fft_length, int scaling, double sampling_rate, float* y, void* stream);
+int nxs_istft_c2r_f32_host(nxs_ctx* ctx, const float* z, int64_t channels, int64_t num_frames,
+                           int64_t z_ld, const float* window, int64_t frame_length, int64_t hop,
+                           int64_t fft_length, int scaling, double sampling_rate, float* y);
+
 /* ---- framing: NxSignal.as_windowed(tensor, opts)  lib/nx_signal.ex:249-364 -
  * x [channels][x_ld] (elem_size 4 or 8 bytes: f32/s32 or c64/s64/f64)
  * out [channels][num_frames][window_length] of the same element type */

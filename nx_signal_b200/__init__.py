@@ -224,11 +224,16 @@ def stft_mel(data, window, overlap_length=None, fft_length="power_of_two", windo
     return out
 
 
-def istft(data, window, fft_length=None, overlap_length=None, scaling=None, sampling_rate=1000):
+def istft(data, window, fft_length=None, overlap_length=None, scaling=None, sampling_rate=1000, onesided=False):
     """NxSignal.istft/3 (lib/nx_signal.ex:582-638).
 
     data c64 [..., M, K], window [N] -> c64 [..., M*hop + N - hop].  fft_length defaults to
-    the next power of two >= K; it must equal N (the reference's `frames * window`)."""
+    the next power of two >= K; it must equal N (the reference's `frames * window`).
+
+    ``onesided=True`` is an opt-in extension (not in the reference), the counterpart
+    of ``stft(..., onesided=True)``: data holds bins 0 .. fft_length // 2 (K = fft_length // 2 + 1,
+    fft_length defaults to len(window)) and the result is the REAL f32 signal
+    Re(istft(ext(data))), ext = conjugate-mirror extension."""
     scale = _scaling_code(scaling)
     if scaling == "psd" and sampling_rate is None:
         raise NxSignalArgumentError(":sampling_rate is mandatory if scaling is :psd")
@@ -239,10 +244,16 @@ def istft(data, window, fft_length=None, overlap_length=None, scaling=None, samp
     N = int(w.shape[0])
     K = int(z.shape[-1])
     M = int(z.shape[-2])
-    nfft = _next_pow2(K) if fft_length in (None, "power_of_two") else int(fft_length)
+    if onesided and fft_length in (None, "power_of_two"):
+        nfft = N
+    else:
+        nfft = _next_pow2(K) if fft_length in (None, "power_of_two") else int(fft_length)
     if overlap_length is None:
         overlap_length = N // 2
     hop = N - int(overlap_length)
+    if onesided and (nfft % 2 or K < nfft // 2 + 1):
+        raise NxSignalArgumentError(
+            f"onesided istft needs an even fft_length and fft_length // 2 + 1 = {nfft // 2 + 1} bins, got {K}")
     if nfft != N:
         raise NxSignalArgumentError(
             f"cannot broadcast frames of length {nfft} with window of length {N} "
@@ -253,10 +264,17 @@ def istft(data, window, fft_length=None, overlap_length=None, scaling=None, samp
     batch_shape = tuple(z.shape[:-2])
     Cn = int(np.prod(batch_shape, dtype=np.int64)) if batch_shape else 1
     out_len = M * hop + (N - hop)
-    y = A.empty_like_kind(z, batch_shape + (out_len,), "c64")
+    y = A.empty_like_kind(z, batch_shape + (out_len,), "f32" if onesided else "c64")
     if Cn > 0:
         ctx = _lib.context(A.device_index(z))
-        if A.is_cuda(z):
+        if onesided:
+            if A.is_cuda(z):
+                rc = _lib.lib().nxs_istft_c2r_f32_dev(ctx, A.ptr(z), Cn, M, K, A.ptr(w), N, hop, nfft, scale,
+                                                      float(sampling_rate), A.ptr(y), A.stream_of(z))
+            else:
+                rc = _lib.lib().nxs_istft_c2r_f32_host(ctx, A.ptr(z), Cn, M, K, A.ptr(w), N, hop, nfft, scale,
+                                                       float(sampling_rate), A.ptr(y))
+        elif A.is_cuda(z):
             rc = _lib.lib().nxs_istft_c64_dev(ctx, A.ptr(z), Cn, M, K, A.ptr(w), N, hop, nfft, scale,
                                               float(sampling_rate), A.ptr(y), A.stream_of(z))
         else:

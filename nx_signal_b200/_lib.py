@@ -52,6 +52,8 @@ SIGNATURES = {
     "nxs_stft_f32_host": (i32, [vp, vp, i64, i64, i64, vp, i64, i64, i64, i32, i64, i64, i32, f64, vp]),
     "nxs_istft_c64_dev": (i32, [vp, vp, i64, i64, i64, vp, i64, i64, i64, i32, f64, vp, vp]),
     "nxs_istft_c64_host": (i32, [vp, vp, i64, i64, i64, vp, i64, i64, i64, i32, f64, vp]),
+    "nxs_istft_c2r_f32_dev": (i32, [vp, vp, i64, i64, i64, vp, i64, i64, i64, i32, f64, vp, vp]),
+    "nxs_istft_c2r_f32_host": (i32, [vp, vp, i64, i64, i64, vp, i64, i64, i64, i32, f64, vp]),
     "nxs_as_windowed_dev": (i32, [vp, vp, i32, i64, i64, i64, i64, i64, i32, i64, i64, vp, vp]),
     "nxs_as_windowed_host": (i32, [vp, vp, i32, i64, i64, i64, i64, i64, i32, i64, i64, vp]),
     "nxs_overlap_and_add_f32_dev": (i32, [vp, vp, i64, i64, i64, i64, vp, vp]),

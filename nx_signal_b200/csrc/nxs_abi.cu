@@ -466,6 +466,42 @@ int nxs_istft_c64_host(nxs_ctx* ctx, const float* z, int64_t channels, int64_t n
                         });
 }
 
+static int istft_c2r_check(int64_t channels, int64_t num_frames, int64_t z_ld, int64_t frame_length, int64_t hop,
+                           int64_t fft_length, int scaling) {
+  int rc = istft_check(channels, num_frames, z_ld, frame_length, hop, fft_length, scaling);
+  if (rc) return rc;
+  if ((fft_length & 1) || z_ld < fft_length / 2 + 1) return NXS_ESHAPE;
+  return NXS_OK;
+}
+
+int nxs_istft_c2r_f32_dev(nxs_ctx* ctx, const float* z, int64_t channels, int64_t num_frames, int64_t z_ld,
+                          const float* window, int64_t frame_length, int64_t hop, int64_t fft_length,
+                          int scaling, double sampling_rate, float* y, void* stream) {
+  if (!ctx || !z || !window || !y) return NXS_EINVAL;
+  int rc = istft_c2r_check(channels, num_frames, z_ld, frame_length, hop, fft_length, scaling);
+  if (rc) return rc;
+  DeviceGuard guard(ctx->device);
+  return launch_istft_c2r(ctx, reinterpret_cast<const float2*>(z), channels, num_frames, z_ld, window,
+                          frame_length, hop, fft_length, scaling, sampling_rate, y, pick(ctx, stream));
+}
+
+int nxs_istft_c2r_f32_host(nxs_ctx* ctx, const float* z, int64_t channels, int64_t num_frames, int64_t z_ld,
+                           const float* window, int64_t frame_length, int64_t hop, int64_t fft_length,
+                           int scaling, double sampling_rate, float* y) {
+  if (!ctx || !z || !window || !y) return NXS_EINVAL;
+  int rc = istft_c2r_check(channels, num_frames, z_ld, frame_length, hop, fft_length, scaling);
+  if (rc) return rc;
+  DeviceGuard guard(ctx->device);
+  const size_t in_bytes = size_t(channels) * num_frames * z_ld * sizeof(float2);
+  const size_t out_len = size_t(num_frames) * hop + (frame_length - hop);
+  return host_roundtrip(ctx, z, in_bytes, window, size_t(frame_length) * sizeof(float), y,
+                        size_t(channels) * out_len * sizeof(float), [&](void* dz, void* dw, void* dy) {
+                          return launch_istft_c2r(ctx, (const float2*)dz, channels, num_frames, z_ld,
+                                                  (const float*)dw, frame_length, hop, fft_length, scaling,
+                                                  sampling_rate, (float*)dy, ctx->stream);
+                        });
+}
+
 // ---- stft_to_mel --------------------------------------------------------------------------------
 static int mel_check(int64_t channels, int64_t num_frames, int64_t z_ld, int64_t fft_length, int64_t mel_bins,
                      double sampling_rate, double f_sp) {

@@ -111,6 +111,9 @@ bool stft_has_exact_mirror(int64_t fft_length);
 int launch_istft(nxs_ctx* ctx, const float2* z, int64_t channels, int64_t num_frames, int64_t z_len,
                  const float* window, int64_t frame_length, int64_t hop, int64_t fft_length, int scaling,
                  double sampling_rate, float2* y, cudaStream_t st);
+int launch_istft_c2r(nxs_ctx* ctx, const float2* z, int64_t channels, int64_t num_frames, int64_t z_ld,
+                     const float* window, int64_t frame_length, int64_t hop, int64_t fft_length, int scaling,
+                     double sampling_rate, float* y, cudaStream_t st);
 int launch_as_windowed(nxs_ctx* ctx, const void* x, int elem_size, int64_t channels, int64_t length,
                        int64_t x_ld, int64_t window_length, int64_t stride, const PadGeom& g,
                        int64_t num_frames, void* out, cudaStream_t st);

@@ -863,11 +863,14 @@ static int run_istft_two_kernels(nxs_ctx* ctx, const IstftArgs& a, int64_t chann
 // does: an f64 inverse DFT of the covering frames, rounded to c64 after the ifft, the rescale,
 // the window multiply and the overlap-add, then divided by D[p].  One warp per sample.
 // ------------------------------------------------------------------------------------------
+// C2R: z holds bins 0 .. nfft/2 of a Hermitian spectrum (row stride z_len), y is real -- the real
+// part of the same computation on the conjugate-extended spectrum.
+template <bool C2R>
 __global__ void __launch_bounds__(256) istft_edge_f64_kernel(const float2* __restrict__ z, int64_t M, int64_t z_len,
                                                              int nfft, int hop, const float* __restrict__ w,
                                                              int scaling, float sr, int64_t out_len,
                                                              const double2* __restrict__ tab,
-                                                             float2* __restrict__ y) {
+                                                             void* __restrict__ y_out) {
   __shared__ double red[256];
   __shared__ float s_dmax, s_scale;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -924,7 +927,7 @@ __global__ void __launch_bounds__(256) istft_edge_f64_kernel(const float2* __res
     p_hi = out_len;
   }
   const float2* __restrict__ zc = z + (int64_t)c * M * z_len;
-  const int nin = (int)(z_len < nfft ? z_len : nfft);
+  const int nin = C2R ? nfft / 2 + 1 : (int)(z_len < nfft ? z_len : nfft);
   for (int64_t p = p_lo + warp; p < p_hi; p += blockDim.x / 32) {
     const int64_t m_lo = p - nfft + 1 <= 0 ? 0 : (p - nfft + hop) / hop;
     int64_t m_hi = p / hop;
@@ -944,10 +947,18 @@ __global__ void __launch_bounds__(256) istft_edge_f64_kernel(const float2* __res
       int idx = (int)(((int64_t)lane * n) % nfft);
       const int step = (int)(((int64_t)32 * n) % nfft);
       for (int k = lane; k < nin; k += 32) {
-        const float2 v = zf[k];
+        float2 v = zf[k];
         const double2 e = tab[idx];
-        sre += (double)v.x * e.x - (double)v.y * e.y;
-        sim += (double)v.x * e.y + (double)v.y * e.x;
+        if constexpr (C2R) {
+          // Re(Z[k] e + conj(Z[k]) conj(e)) = 2 Re(Z[k] e); DC and Nyquist count once, real parts only
+          const bool self = k == 0 || 2 * k == nfft;
+          if (self) v.y = 0.f;
+          const double term = (double)v.x * e.x - (double)v.y * e.y;
+          sre += self ? term : 2.0 * term;
+        } else {
+          sre += (double)v.x * e.x - (double)v.y * e.y;
+          sim += (double)v.x * e.y + (double)v.y * e.x;
+        }
         idx += step;
         if (idx >= nfft) idx -= nfft;
       }
@@ -967,7 +978,11 @@ __global__ void __launch_bounds__(256) istft_edge_f64_kernel(const float2* __res
     }
     if (lane == 0) {
       const float rre = (float)ore, rim = (float)oim;  // overlap_and_add -> c64
-      y[(int64_t)c * out_len + p] = make_float2((float)((double)rre / (double)D), (float)((double)rim / (double)D));
+      if constexpr (C2R)
+        reinterpret_cast<float*>(y_out)[(int64_t)c * out_len + p] = (float)((double)rre / (double)D);
+      else
+        reinterpret_cast<float2*>(y_out)[(int64_t)c * out_len + p] =
+            make_float2((float)((double)rre / (double)D), (float)((double)rim / (double)D));
     }
   }
 }
@@ -1023,7 +1038,7 @@ int launch_istft(nxs_ctx* ctx, const float2* z, int64_t channels, int64_t num_fr
   int64_t done = 0;
   while (done < channels) {  // gridDim.x limit is 2^31 - 1; channels beyond that come in slices
     const int64_t n = channels - done < (int64_t(1) << 30) ? channels - done : (int64_t(1) << 30);
-    istft_edge_f64_kernel<<<dim3((unsigned)n, 2), 256, 0, st>>>(z + done * num_frames * z_len, num_frames, z_len,
+    istft_edge_f64_kernel<false><<<dim3((unsigned)n, 2), 256, 0, st>>>(z + done * num_frames * z_len, num_frames, z_len,
                                                                 (int)fft_length, (int)hop, window, scaling,
                                                                 (float)sampling_rate, out_len, tab, y + done * out_len);
     ctx->launches++;
@@ -1114,6 +1129,414 @@ static int launch_istft_main(nxs_ctx* ctx, const float2* z, int64_t channels, in
   ctx->launches++;
   NXS_CUDA(ctx, cudaGetLastError());
   return run_ola_norm(ctx, (const float2*)ctx->d_scratch, channels, num_frames, nfft, hop, a.out_len, window, y, st);
+}
+
+
+// ==========================================================================================
+// c2r ISTFT (opt-in): z holds only bins 0 .. nfft/2 of each frame -- what
+// nxs_stft_onesided_f32_dev writes -- and y is REAL.  Defined as Re(istft(ext(z))) with ext the
+// conjugate-mirror extension (the imaginary parts of the DC and Nyquist bins do not reach the
+// real part).  For a spectrum that came from a real signal this is the reference's result with
+// its (rounding-noise) imaginary part dropped, at half the input bytes, a quarter of the
+// output bytes and half the FFT work:
+//   2 Z[k] = (X[k] + conj(X[Nh-k])) + i e^{+2 pi i k / nfft} (X[k] - conj(X[Nh-k])),  k < Nh = nfft/2
+//   sum_k 2 Z[k] e^{+2 pi i j k / Nh} = nfft (x[2j] + i x[2j+1])
+// so one Nh-point complex transform per frame yields the frame's nfft real samples packed in
+// pairs, and the register overlap-add of istft_rola_kernel runs on float2 = (even, odd) sample.
+// ==========================================================================================
+template <class PL, int THREADS>
+struct RolaC2rCfg {
+  static constexpr int G = THREADS / PL::T, NH = PL::N;
+  static constexpr size_t STAGE = size_t(NH) + 2;  // bins 0 .. Nh-1 behind 0 / 1 alignment slots
+  static constexpr size_t GROUP_BYTES = (STAGE + size_t(PL::BUF)) * sizeof(cpx);
+  static constexpr size_t WIN_OFF = size_t(G) * GROUP_BYTES;
+  static constexpr size_t TW_OFF = WIN_OFF + 2 * size_t(NH) * sizeof(float);
+  static constexpr size_t BAR_OFF = TW_OFF + size_t(PL::TW_TOTAL) * sizeof(cpx);
+  static constexpr size_t NORM_OFF = (BAR_OFF + 8 * size_t(G) + 15) / 16 * 16;  // interior normaliser, large plans
+  static constexpr size_t SMEM = NORM_OFF + (PL::P <= 8 ? 0 : size_t(NH) / 2 * sizeof(float2));
+};
+
+struct IstftC2rArgs {
+  const float2* z;  // [C][M][z_ld], bins 0 .. nfft/2
+  int64_t M, z_ld;
+  const float* wprep;  // [nfft] = w * S / nfft
+  const float* w;      // raw window
+  float* y;            // [C][out_len] real
+  int64_t out_len;
+  int seg_frames, segs_per_channel, total_segs;
+  const float2* tw;
+  const float2* pre;  // [Nh] i e^{+2 pi i k / nfft}
+};
+
+template <class PL, int THREADS, int MINB, int HOPDIV>
+__global__ void __launch_bounds__(THREADS, MINB) istft_rola_c2r_kernel(const IstftC2rArgs a) {
+  using CF = RolaC2rCfg<PL, THREADS>;
+  constexpr int NH = PL::N, NFFT = 2 * NH, T = PL::T, P = PL::P, G = CF::G;
+  constexpr int R0 = PL::R(0), B0 = P / R0;
+  constexpr int RL = PL::R(PL::NP - 1), BL = P / RL;
+  constexpr int HOP = NFFT / HOPDIV, HOP2 = HOP / 2, S = HOP2 / T;  // S packed accumulators complete per frame
+  static_assert(HOP2 % T == 0 && S >= 1 && NFFT % HOPDIV == 0, "hop / 2 must be a multiple of the group width");
+  static_assert((NH / RL) % T == 0, "last pass must leave j = t (mod T) in every thread");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tid = threadIdx.x, g = tid / T, t = tid % T;
+  cpx* const stage = reinterpret_cast<cpx*>(smem_raw + size_t(g) * CF::GROUP_BYTES);
+  cpx* const xbuf = stage + CF::STAGE;
+  float2* wsm = reinterpret_cast<float2*>(smem_raw + CF::WIN_OFF);  // (w'[2j], w'[2j+1])
+  cpx* twsm = reinterpret_cast<cpx*>(smem_raw + CF::TW_OFF);
+  const uint32_t mybar = smem_u32(smem_raw + CF::BAR_OFF) + 8 * g;
+
+  for (int i = tid; i < NFFT; i += THREADS) reinterpret_cast<float*>(wsm)[i] = a.wprep[i];
+  auto w2 = [&](int n) {
+    const float w = fabsf(__ldg(a.w + n));
+    return (float)((double)w * (double)w);
+  };
+  for (int i = tid; i < PL::TW_TOTAL; i += THREADS) twsm[i] = a.tw[i];
+  if (tid == 0) {
+    for (int i = 0; i < G; ++i) mbar_init(smem_u32(smem_raw + CF::BAR_OFF) + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  TwDerive<PL> tw;
+  tw.init(twsm, t);
+  const GroupSync<T> sync{1 + g};
+
+  // pre-pass twiddles of this thread's input points (constant across frames): registers when the
+  // plan leaves room (P <= 8), else re-read through L1 every frame
+  constexpr bool PRE_REGS = P <= 8;
+  cpx pre[PRE_REGS ? P : 1];
+  if constexpr (PRE_REGS) {
+#pragma unroll
+    for (int b = 0; b < B0; ++b)
+#pragma unroll
+      for (int q = 0; q < R0; ++q) pre[b * R0 + q] = __ldg(a.pre + fft_in_index<PL>(t, b, q));
+  }
+
+  // interior normaliser of the 2 S samples a frame completes (ascending frame order): registers
+  // for the small plans, shared memory when P = 16 leaves no room
+  constexpr bool NORM_REGS = P <= 8;
+  float2 normc[NORM_REGS ? S : 1];
+  float2* const nsm = reinterpret_cast<float2*>(smem_raw + CF::NORM_OFF);
+  auto norm_interior = [&](int i2) {  // packed index i2 < HOP2
+    float n0 = 0.f, n1 = 0.f;
+#pragma unroll
+    for (int k = HOPDIV - 1; k >= 0; --k) {
+      n0 += w2(2 * i2 + k * HOP);
+      n1 += w2(2 * i2 + 1 + k * HOP);
+    }
+    return make_float2(n0, n1);
+  };
+  if constexpr (NORM_REGS) {
+#pragma unroll
+    for (int j = 0; j < S; ++j) normc[j] = norm_interior(t + j * T);
+  } else {
+    for (int i = tid; i < HOP2; i += THREADS) nsm[i] = norm_interior(i);
+    __syncthreads();
+  }
+  auto norm_at = [&](int64_t p) {  // exact normaliser at output sample p (edges: fewer covering frames)
+    int64_t m_lo = p - NFFT + 1 <= 0 ? 0 : (p - NFFT + HOP) / HOP;
+    int64_t m_hi = p / HOP;
+    if (m_hi > a.M - 1) m_hi = a.M - 1;
+    float nr = 0.f;
+    for (int64_t m = m_lo; m <= m_hi; ++m) nr += w2((int)(p - m * HOP));
+    return nr;
+  };
+  auto guard = [](float nr) { return nr > 1.0e-10f ? nr : 1.0f; };  // select(norm > 1e-10, norm, 1.0)
+
+  const int gid = blockIdx.x * G + g, ngroups = gridDim.x * G;
+  auto seg_bounds = [&](int seg, int& c, int64_t& mb, int64_t& ms, int64_t& me) {
+    c = seg / a.segs_per_channel;
+    const int si = seg - c * a.segs_per_channel;
+    ms = (int64_t)si * a.seg_frames;
+    me = ms + a.seg_frames;
+    if (me > a.M) me = a.M;
+    mb = ms - (HOPDIV - 1);
+    if (mb < 0) mb = 0;
+  };
+  // the copy starts at the 16-byte boundary at or below the row and covers bins 0 .. Nh-1
+  auto row_of = [&](int c, int64_t m) { return a.z + ((int64_t)c * a.M + m) * a.z_ld; };
+  auto issue = [&](int c, int64_t m) {
+    const float2* row = row_of(c, m);
+    const uint32_t off = (uint32_t)((reinterpret_cast<uintptr_t>(row) >> 3) & 1);
+    const uint32_t bytes = (uint32_t)(NH * sizeof(cpx)) + 16 * off;
+    mbar_expect_tx(mybar, bytes);
+    tma_load_1d(smem_u32(stage), row - off, bytes, mybar);
+  };
+
+  uint32_t parity = 0;
+  int seg = gid;
+  int c = 0;
+  int64_t mb = 0, ms = 0, me = 0;
+  if (seg < a.total_segs) {
+    seg_bounds(seg, c, mb, ms, me);
+    if (t == 0) issue(c, mb);
+  }
+  while (seg < a.total_segs) {
+    float2* __restrict__ yc = reinterpret_cast<float2*>(a.y + (int64_t)c * a.out_len);  // out_len is even
+    cpx acc[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) acc[j] = make_float2(0.f, 0.f);
+    const int nseg = seg + ngroups;
+    int nc = 0;
+    int64_t nmb = 0, nms = 0, nme = 0;
+    if (nseg < a.total_segs) seg_bounds(nseg, nc, nmb, nms, nme);
+
+    for (int64_t m = mb; m < me; ++m) {
+      cpx v[P];
+      const float2* row = row_of(c, m);
+      const int off = (int)((reinterpret_cast<uintptr_t>(row) >> 3) & 1);
+      float nyq = 0.f;
+      if (t == 0) nyq = __ldg(&row[NH].x);  // Re X[Nh]: the one bin the copy does not bring
+      mbar_wait(mybar, parity);
+      parity ^= 1;
+      const cpx* __restrict__ sx = stage + off;
+#pragma unroll
+      for (int b = 0; b < B0; ++b)
+#pragma unroll
+        for (int q = 0; q < R0; ++q) {
+          const int k = fft_in_index<PL>(t, b, q);
+          cpx A = sx[k];
+          cpx Bc = cconj(sx[NH - k]);
+          if (b == 0 && q == 0 && t == 0) {  // k = 0 pairs DC with Nyquist, real parts only
+            A.y = 0.f;
+            Bc = make_float2(nyq, 0.f);
+          }
+          const cpx pw = PRE_REGS ? pre[PRE_REGS ? b * R0 + q : 0] : __ldg(a.pre + k);
+          const cpx Z = cadd(cadd(A, Bc), cmul(pw, csub(A, Bc)));
+          v[b * R0 + q] = make_float2(Z.y, Z.x);  // swap: ifft(x) = swap(fft(swap(x))) / n
+          // large plans: keep the compiler from hoisting all 2 P stage loads (register pressure)
+          if constexpr (P > 8) {
+            if ((q & 3) == 3) asm volatile("" ::: "memory");
+          }
+        }
+      sync();  // stage read out (and the previous frame's last exchange reads are done)
+      if (t == 0) {
+        if (m + 1 < me) issue(c, m + 1);
+        else if (nseg < a.total_segs) issue(nc, nmb);
+      }
+      block_fft_single<PL>(v, t, xbuf, tw, sync);
+      // thread t holds packed outputs j' = t + j*T at v[fft_out_reg(b, q)], j = b + q*BL:
+      // (swapped) re = x[2j'+1], im = x[2j']
+#pragma unroll
+      for (int b = 0; b < BL; ++b)
+#pragma unroll
+        for (int q = 0; q < RL; ++q) {
+          const int j = b + q * BL;
+          const cpx r = v[fft_out_reg<PL>(b, q)];
+          const float2 w = wsm[t + j * T];
+          acc[j].x += r.y * w.x;
+          acc[j].y += r.x * w.y;
+        }
+      if (m >= ms) {
+        const int64_t pos2 = m * HOP2 + t;  // packed output index: samples 2 pos2, 2 pos2 + 1
+        const bool interior = m >= HOPDIV - 1;
+#pragma unroll
+        for (int j = 0; j < S; ++j) {
+          const int64_t p2 = pos2 + j * T;
+          float2 nr = NORM_REGS ? normc[NORM_REGS ? j : 0] : nsm[t + j * T];
+          if (!interior) nr = make_float2(norm_at(2 * p2), norm_at(2 * p2 + 1));
+          __stcs(yc + p2, make_float2(acc[j].x / guard(nr.x), acc[j].y / guard(nr.y)));
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < P - S; ++j) acc[j] = acc[j + S];
+#pragma unroll
+      for (int j = P - S; j < P; ++j) acc[j] = make_float2(0.f, 0.f);
+    }
+    if (me == a.M) {  // tail of the channel: the nfft - hop samples no further frame completes
+      const int64_t pos2 = a.M * HOP2 + t;
+#pragma unroll
+      for (int j = 0; j < P - S; ++j) {
+        const int64_t p2 = pos2 + j * T;
+        __stcs(yc + p2, make_float2(acc[j].x / guard(norm_at(2 * p2)), acc[j].y / guard(norm_at(2 * p2 + 1))));
+      }
+    }
+    seg = nseg;
+    c = nc;
+    mb = nmb;
+    ms = nms;
+    me = nme;
+  }
+}
+
+// i e^{+2 pi i k / nfft}, k < nfft / 2 (double-computed), cached per context
+static int get_c2r_pre_table(nxs_ctx* ctx, int64_t nfft, float2** out) {
+  const uint64_t key = (uint64_t(6) << 32) | uint64_t(nfft);
+  auto it = ctx->dft_tables.find(key);
+  if (it != ctx->dft_tables.end()) {
+    *out = it->second;
+    return NXS_OK;
+  }
+  std::vector<float2> tab(nfft / 2);
+  for (int64_t k = 0; k < nfft / 2; ++k) {
+    const double ang = 2.0 * M_PI * double(k) / double(nfft);
+    tab[k] = make_float2((float)-sin(ang), (float)cos(ang));
+  }
+  float2* d = nullptr;
+  NXS_CUDA(ctx, cudaMalloc(&d, tab.size() * sizeof(float2)));
+  NXS_CUDA(ctx, cudaMemcpy(d, tab.data(), tab.size() * sizeof(float2), cudaMemcpyHostToDevice));
+  ctx->dft_tables[key] = d;
+  *out = d;
+  return NXS_OK;
+}
+
+template <class PL, int THREADS, int MINB, int HOPDIV>
+static int run_istft_rola_c2r(nxs_ctx* ctx, IstftC2rArgs a, int64_t channels, cudaStream_t st) {
+  using CF = RolaC2rCfg<PL, THREADS>;
+  float2* tw = nullptr;
+  int rc = get_tw_table<PL>(ctx, &tw);
+  if (rc) return rc;
+  a.tw = tw;
+  float2* pre = nullptr;
+  rc = get_c2r_pre_table(ctx, 2 * PL::N, &pre);
+  if (rc) return rc;
+  a.pre = pre;
+  auto kern = istft_rola_c2r_kernel<PL, THREADS, MINB, HOPDIV>;
+  NXS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF::SMEM));
+  int occ = 1;
+  NXS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, CF::SMEM));
+  if (occ < 1) occ = 1;
+  const int64_t groups = int64_t(ctx->sm_count) * occ * CF::G;
+  const int64_t total_frames = channels * a.M;
+  int64_t seg = (total_frames + groups * 4 - 1) / (groups * 4);
+  const int64_t seg_min = 16 * (HOPDIV - 1) > 32 ? 16 * (HOPDIV - 1) : 32;
+  if (seg < seg_min) seg = seg_min;
+  if (seg > a.M) seg = a.M;
+  a.seg_frames = (int)seg;
+  a.segs_per_channel = (int)((a.M + seg - 1) / seg);
+  const int64_t total = int64_t(a.segs_per_channel) * channels;
+  if (total >= (int64_t(1) << 31)) return NXS_EUNSUPPORTED;
+  a.total_segs = (int)total;
+  int64_t grid = (total + CF::G - 1) / CF::G;
+  if (grid > int64_t(ctx->sm_count) * occ) grid = int64_t(ctx->sm_count) * occ;
+  prof_begin(ctx, st);
+  kern<<<(unsigned)grid, THREADS, CF::SMEM, st>>>(a);
+  prof_end(ctx, st);
+  ctx->launches++;
+  NXS_CUDA(ctx, cudaGetLastError());
+  return NXS_OK;
+}
+
+template <class PL, int THREADS, int MINB>
+static int try_istft_rola_c2r(nxs_ctx* ctx, const IstftC2rArgs& a, int64_t hop, int64_t channels, cudaStream_t st,
+                              bool* done) {
+  constexpr int NFFT = 2 * PL::N;
+  *done = true;
+  if (hop * 2 == NFFT) return run_istft_rola_c2r<PL, THREADS, MINB, 2>(ctx, a, channels, st);
+  if (hop * 4 == NFFT) return run_istft_rola_c2r<PL, THREADS, MINB, 4>(ctx, a, channels, st);
+  if constexpr (NFFT / 16 >= PL::T) {
+    if (hop * 8 == NFFT) return run_istft_rola_c2r<PL, THREADS, MINB, 8>(ctx, a, channels, st);
+  }
+  *done = false;
+  return NXS_OK;
+}
+
+// other shapes: extend to the two-sided spectrum, run the c64 path, keep the real part
+__global__ void __launch_bounds__(256) hermitian_extend_kernel(const float2* __restrict__ z, int64_t frames,
+                                                               int64_t z_ld, int nfft, float2* __restrict__ full) {
+  const int64_t total = frames * nfft;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t f = i / nfft;
+    const int k = (int)(i - f * nfft);
+    const float2* row = z + f * z_ld;
+    float2 v;
+    if (2 * k <= nfft) {
+      v = row[k];
+      if (k == 0 || 2 * k == nfft) v.y = 0.f;
+    } else {
+      v = cconj(row[nfft - k]);
+    }
+    full[i] = v;
+  }
+}
+__global__ void __launch_bounds__(256) real_part_kernel(const float2* __restrict__ y, int64_t total,
+                                                        float* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = y[i].x;
+}
+
+int launch_istft_c2r(nxs_ctx* ctx, const float2* z, int64_t channels, int64_t num_frames, int64_t z_ld,
+                     const float* window, int64_t frame_length, int64_t hop, int64_t fft_length, int scaling,
+                     double sampling_rate, float* y, cudaStream_t st) {
+  if (channels <= 0) return NXS_OK;
+  const int64_t nfft = fft_length;
+  if (nfft > (int64_t(1) << 24) || (nfft & 1)) return NXS_EUNSUPPORTED;
+  const int64_t out_len = num_frames * hop + (nfft - hop);
+  const bool fast_shape = (nfft == 512 || nfft == 1024 || nfft == 2048 || nfft == 4096) &&
+                          (hop * 2 == nfft || hop * 4 == nfft || hop * 8 == nfft) &&
+                          (reinterpret_cast<uintptr_t>(z) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 7) == 0 &&
+                          num_frames < (int64_t(1) << 40) && !getenv("NXS_ISTFT_NO_C2R");
+  if (fast_shape) {
+    int rc = ensure_coef(ctx, size_t(nfft) * sizeof(float));
+    if (rc) return rc;
+    rc = launch_prep_window(ctx, window, frame_length, nfft, scaling, sampling_rate, (float)(1.0 / double(nfft)), 1,
+                            ctx->d_coef, st);
+    if (rc) return rc;
+    IstftC2rArgs a;
+    a.z = z;
+    a.M = num_frames;
+    a.z_ld = z_ld;
+    a.wprep = ctx->d_coef;
+    a.w = window;
+    a.y = y;
+    a.out_len = out_len;
+    a.seg_frames = a.segs_per_channel = a.total_segs = 0;
+    a.tw = a.pre = nullptr;
+    bool done = false;
+    switch (nfft) {
+      case 512: rc = try_istft_rola_c2r<Plan<256, 32, 8, 8, 4>, 256, 2>(ctx, a, hop, channels, st, &done); break;
+      case 1024: rc = try_istft_rola_c2r<Plan<512, 64, 8, 8, 8>, 256, 2>(ctx, a, hop, channels, st, &done); break;
+      case 2048: rc = try_istft_rola_c2r<Plan<1024, 64, 16, 8, 8>, 256, 2>(ctx, a, hop, channels, st, &done); break;
+      case 4096: rc = try_istft_rola_c2r<Plan<2048, 128, 16, 16, 8>, 256, 2>(ctx, a, hop, channels, st, &done); break;
+      default: break;
+    }
+    if (rc) return rc;
+    if (done) {
+      if (hop >= nfft || getenv("NXS_ISTFT_NO_EDGE_F64")) return NXS_OK;
+      double2* tab = nullptr;
+      rc = get_dft_table_f64(ctx, nfft, &tab);
+      if (rc) return rc;
+      int64_t cdone = 0;
+      while (cdone < channels) {
+        const int64_t n = channels - cdone < (int64_t(1) << 30) ? channels - cdone : (int64_t(1) << 30);
+        istft_edge_f64_kernel<true><<<dim3((unsigned)n, 2), 256, 0, st>>>(
+            z + cdone * num_frames * z_ld, num_frames, z_ld, (int)nfft, (int)hop, window, scaling,
+            (float)sampling_rate, out_len, tab, y + cdone * out_len);
+        ctx->launches++;
+        NXS_CUDA(ctx, cudaGetLastError());
+        cdone += n;
+      }
+      return NXS_OK;
+    }
+  }
+  // general shapes: temporaries for the two-sided spectrum and the c64 result (freed after the stream drains)
+  const int64_t frames = channels * num_frames;
+  float2 *full = nullptr, *yc = nullptr;
+  NXS_CUDA(ctx, cudaMalloc(&full, size_t(frames) * nfft * sizeof(float2)));
+  cudaError_t e = cudaMalloc(&yc, size_t(channels) * out_len * sizeof(float2));
+  if (e != cudaSuccess) {
+    cudaFree(full);
+    return set_cuda_error(ctx, e, "cudaMalloc(c2r result)");
+  }
+  int64_t grid = (frames * nfft + 255) / 256;
+  if (grid > int64_t(ctx->sm_count) * 16) grid = int64_t(ctx->sm_count) * 16;
+  hermitian_extend_kernel<<<(unsigned)grid, 256, 0, st>>>(z, frames, z_ld, (int)nfft, full);
+  ctx->launches++;
+  int rc = launch_istft(ctx, full, channels, num_frames, nfft, window, frame_length, hop, fft_length, scaling,
+                        sampling_rate, yc, st);
+  if (rc == NXS_OK) {
+    const int64_t total = channels * out_len;
+    int64_t g2 = (total + 255) / 256;
+    if (g2 > int64_t(ctx->sm_count) * 16) g2 = int64_t(ctx->sm_count) * 16;
+    real_part_kernel<<<(unsigned)g2, 256, 0, st>>>(yc, total, y);
+    ctx->launches++;
+  }
+  cudaError_t es = cudaStreamSynchronize(st);
+  cudaFree(full);
+  cudaFree(yc);
+  if (rc) return rc;
+  NXS_CUDA(ctx, es);
+  NXS_CUDA(ctx, cudaGetLastError());
+  return NXS_OK;
 }
 
 }  // namespace nxs
