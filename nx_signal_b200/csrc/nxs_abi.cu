@@ -199,6 +199,11 @@ int nxs_ctx_destroy(nxs_ctx* ctx) {
   for (auto& b : ctx->mel_banks) {
     cudaFree(b.d_wts);
     cudaFree(b.d_idx);
+    for (auto& l : b.layouts) {
+      cudaFree(l.d_w2);
+      cudaFree(l.d_desc);
+      cudaFree(l.d_ps);
+    }
   }
   cudaFree(ctx->d_coef);
   cudaFree(ctx->d_scratch);

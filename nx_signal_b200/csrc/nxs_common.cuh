@@ -19,6 +19,19 @@ struct PlanTables {
   float2* post = nullptr;  // r2c post-pass: -i * exp(-i pi k / N), k in [0, N/2]   (N = nfft/2)
 };
 
+// Bin-major form of a triangular filterbank for the fused STFT epilogue (nxs_stft.cu): every FFT
+// bin k feeds at most two consecutive filters, jl[k] (weight w2[k].x) and jl[k] + 1 (w2[k].y), and
+// jl is non-decreasing, so the bins split into segments of equal jl.  A thread owns B consecutive
+// bins and emits one partial sum ("piece") per segment it touches; filter j is then the sum of the
+// .x pieces of segment j + 1 and the .y pieces of segment j (pieces are numbered in bin order).
+struct MelLayout {
+  int B = 0;                // bins per thread
+  bool ok = false;          // false: the bank is not of that form (or too many pieces) -> gather path
+  float2* d_w2 = nullptr;   // [half] (weight for filter jl, weight for filter jl + 1), load-major (nxs_mel.cu)
+  int* d_desc = nullptr;    // [half / B] piece base | boundary mask << 12 | skip << 31
+  int* d_ps = nullptr;      // [mel_bins + 3] first piece of each segment
+};
+
 // sparse mel filterbank (nxs_mel.cu) of one parameter set, resident on the device
 struct MelBank {
   int64_t nfft = 0, mel_bins = 0;
@@ -26,13 +39,12 @@ struct MelBank {
   float* d_wts = nullptr;  // packed nonzero weights
   int nw = 0;              // their count
   int* d_idx = nullptr;    // [3][mel_bins]: start, count, offset
+  std::vector<MelLayout> layouts;
 };
 
 // fused log-mel epilogue of the STFT kernel (launch_stft): the spectrum is never stored
 struct MelEpilogue {
-  const float* wts;
-  const int* idx;
-  int mel_bins, nw;
+  MelBank* bank;
   float* out;  // [channels * num_frames][mel_bins]
   int* chmax;  // [channels]
 };
@@ -128,6 +140,8 @@ int launch_stft_mel(nxs_ctx* ctx, const float* x, int64_t channels, int64_t leng
                     const float* window, int64_t frame_length, int64_t hop, int64_t fft_length, const PadGeom& g,
                     int64_t num_frames, int scaling, double sampling_rate, int64_t mel_bins, double max_mel,
                     double f_sp, float* out, cudaStream_t st);
+// bin-major layout of `bank` for threads owning B consecutive bins (built on first use)
+int get_mel_layout(nxs_ctx* ctx, MelBank* bank, int B, const MelLayout** out);
 int launch_convolve_nd(nxs_ctx* ctx, const float* a, const int64_t* as, const float* b, const int64_t* bs,
                        int is_complex, int mode, float* out, cudaStream_t st);
 

@@ -155,6 +155,98 @@ static int get_mel_bank(nxs_ctx* ctx, int64_t nfft, int64_t mel_bins, double sr,
   return NXS_OK;
 }
 
+int get_mel_layout(nxs_ctx* ctx, MelBank* bank, int B, const MelLayout** out) {
+  for (auto& l : bank->layouts)
+    if (l.B == B) {
+      *out = &l;
+      return NXS_OK;
+    }
+  MelLayout lay;
+  lay.B = B;
+  const int64_t nfft = bank->nfft, half = nfft / 2, mel_bins = bank->mel_bins;
+  auto finish = [&]() {
+    bank->layouts.push_back(lay);
+    *out = &bank->layouts.back();
+    return NXS_OK;
+  };
+  if (B < 2 || B > 16 || (B & 1) || half % B != 0 || mel_bins + 3 > (int64_t(1) << 20)) return finish();
+  std::vector<float> dense(size_t(mel_bins) * size_t(nfft));
+  int rc = nxs_mel_filters_f32(nfft, mel_bins, bank->sr, bank->max_mel, bank->f_sp, dense.data());
+  if (rc) return rc;
+  // per bin: the (at most two, consecutive) filters it feeds; jl must not decrease
+  std::vector<int> jl(half);
+  std::vector<float2> w2(half, make_float2(0.f, 0.f));
+  int prev = -1;
+  int64_t last_nz = -1;
+  for (int64_t k = 0; k < half; ++k) {
+    int nz[3], n = 0;
+    for (int64_t j = 0; j < mel_bins && n < 3; ++j)
+      if (dense[j * nfft + k] != 0.0f) nz[n++] = (int)j;  // NaN (degenerate filter) counts as a weight
+    if (n == 0) {
+      jl[k] = prev;
+    } else if (n == 1) {
+      const float w = dense[int64_t(nz[0]) * nfft + k];
+      if (prev <= nz[0] - 1) {
+        jl[k] = nz[0] - 1;
+        w2[k].y = w;
+      } else if (prev == nz[0]) {
+        jl[k] = nz[0];
+        w2[k].x = w;
+      } else {
+        return finish();
+      }
+    } else if (n == 2 && nz[1] == nz[0] + 1 && prev <= nz[0]) {
+      jl[k] = nz[0];
+      w2[k] = make_float2(dense[int64_t(nz[0]) * nfft + k], dense[int64_t(nz[1]) * nfft + k]);
+    } else {
+      return finish();
+    }
+    if (n > 0) last_nz = k;
+    prev = jl[k];
+  }
+  // bins above the last weight form a segment of their own that no filter reads
+  for (int64_t k = last_nz + 1; k < half; ++k) jl[k] = (int)mel_bins;
+  const int64_t T = half / B;
+  std::vector<int> desc(T), ps(mel_bins + 3);
+  int pieces = 0;
+  int seg_next = 0;  // segments below this one have their first piece recorded (segment = jl + 1)
+  for (int64_t t = 0; t < T; ++t) {
+    unsigned mask = 0;
+    bool skip = true;
+    const int base = pieces;
+    for (int b = 0; b < B; ++b) {
+      const int64_t k = t * B + b;
+      const bool fresh = b == 0 || jl[k] != jl[k - 1];
+      if (b > 0 && fresh) mask |= 1u << b;
+      if (fresh) {
+        if (k == 0 || jl[k] != jl[k - 1])
+          for (; seg_next <= jl[k] + 1; ++seg_next) ps[seg_next] = pieces;
+        ++pieces;
+      }
+      if (jl[k] != (int)mel_bins) skip = false;
+    }
+    desc[t] = base | (int)(mask << 12) | (skip ? (int)0x80000000u : 0);
+  }
+  for (; seg_next < (int)mel_bins + 3; ++seg_next) ps[seg_next] = pieces;
+  if (pieces > half / 2 || pieces >= 4096) return finish();  // pieces live in half of the exchange buffer
+  NXS_CUDA(ctx, cudaMalloc(&lay.d_w2, size_t(half) * sizeof(float2)));
+  NXS_CUDA(ctx, cudaMalloc(&lay.d_desc, size_t(T) * sizeof(int)));
+  NXS_CUDA(ctx, cudaMalloc(&lay.d_ps, ps.size() * sizeof(int)));
+  // load-major order for the kernel's 128-bit reads: float4 i of thread t = bins B t + 2 i, B t + 2 i + 1
+  // sits at float4 index i * T + t (consecutive lanes -> consecutive 16-byte words)
+  std::vector<float2> w2s(half);
+  for (int64_t t = 0; t < T; ++t)
+    for (int i = 0; i < B / 2; ++i) {
+      w2s[2 * (i * T + t)] = w2[t * B + 2 * i];
+      w2s[2 * (i * T + t) + 1] = w2[t * B + 2 * i + 1];
+    }
+  NXS_CUDA(ctx, cudaMemcpy(lay.d_w2, w2s.data(), size_t(half) * sizeof(float2), cudaMemcpyHostToDevice));
+  NXS_CUDA(ctx, cudaMemcpy(lay.d_desc, desc.data(), size_t(T) * sizeof(int), cudaMemcpyHostToDevice));
+  NXS_CUDA(ctx, cudaMemcpy(lay.d_ps, ps.data(), ps.size() * sizeof(int), cudaMemcpyHostToDevice));
+  lay.ok = true;
+  return finish();
+}
+
 int launch_stft_to_mel(nxs_ctx* ctx, const float2* z, int64_t channels, int64_t num_frames, int64_t z_ld,
                        int64_t fft_length, int64_t mel_bins, double sampling_rate, double max_mel, double f_sp,
                        float* out, cudaStream_t st) {
@@ -217,7 +309,7 @@ int launch_stft_mel(nxs_ctx* ctx, const float* x, int64_t channels, int64_t leng
   if (rc) return rc;
   int* chmax = (int*)ctx->d_scratch;
   NXS_CUDA(ctx, cudaMemsetAsync(chmax, 0x80, size_t(channels) * sizeof(int), st));
-  MelEpilogue mel{bank->d_wts, bank->d_idx, (int)mel_bins, bank->nw, out, chmax};
+  MelEpilogue mel{bank, out, chmax};
   rc = launch_stft(ctx, x, channels, length, x_ld, window, frame_length, hop, fft_length, g, num_frames, scaling,
                    sampling_rate, nullptr, fft_length, 0, st, &mel);
   if (rc) return rc;

@@ -64,10 +64,12 @@ struct StftArgs {
   int reflect;
   const float2* tw;
   const float2* post;
-  // fused log-mel epilogue (MODE 2): sparse filterbank (nxs_mel.cu layout) and outputs
-  const float* mel_wts = nullptr;
-  const int* mel_idx = nullptr;  // [3][mel_bins]: start, count, offset
-  int mel_bins = 0, mel_nw = 0;  // filters, packed weights
+  // fused log-mel epilogue (MODE 2): bin-major filterbank (MelLayout, nxs_common.cuh) and outputs
+  const float2* mel_w2 = nullptr;  // [nfft / 2] per-bin weights for filters jl, jl + 1
+  const int* mel_desc = nullptr;   // [T] piece base | boundary mask << 12 | skip << 31
+  const int* mel_ps = nullptr;     // [mel_bins + 3] first piece of each segment
+  int mel_bins = 0;
+  MelBank* mel_bank = nullptr;     // host side only: the layout is resolved per plan in run_r2c_staged
   float* mel_out = nullptr;      // [total_frames][mel_bins] log10 mel power (before the clamp)
   int* mel_chmax = nullptr;      // [channels] ordered-int maximum
 };
@@ -250,11 +252,13 @@ __global__ void __launch_bounds__(CF::THREADS, MINB) stft_r2c_staged_kernel(cons
 
   constexpr bool ONESIDED = MODE == kOneSided;
   // mel epilogue tables live behind the configuration's own shared memory
-  float* const mel_w = reinterpret_cast<float*>(smem_raw + ((CF::SMEM + 15) / 16) * 16);
-  int* const mel_i = reinterpret_cast<int*>(mel_w + a.mel_nw);
+  float2* const mel_w = reinterpret_cast<float2*>(smem_raw + ((CF::SMEM + 15) / 16) * 16);  // [N] per-bin weights
+  int* const mel_ps = reinterpret_cast<int*>(mel_w + N);                                   // [mel_bins + 3]
+  int mel_d = 0;  // this thread's piece descriptor (constant across frames)
   if constexpr (MODE == kMel) {
-    for (int i = tid; i < a.mel_nw; i += THREADS) mel_w[i] = a.mel_wts[i];
-    for (int i = tid; i < 3 * a.mel_bins; i += THREADS) mel_i[i] = a.mel_idx[i];
+    for (int i = tid; i < N; i += THREADS) mel_w[i] = a.mel_w2[i];
+    for (int i = tid; i < a.mel_bins + 3; i += THREADS) mel_ps[i] = a.mel_ps[i];
+    mel_d = __ldg(a.mel_desc + t);
   }
   int mel_c = -1;            // channel the running maximum belongs to
   float mel_max = -INFINITY;  // running maximum of this thread's log-mel values
@@ -287,9 +291,19 @@ __global__ void __launch_bounds__(CF::THREADS, MINB) stft_r2c_staged_kernel(cons
   }
 
   // is this tile (PERGROUP: this group's frame) fully interior (no padding) -> staged through TMA
-  auto tile_geom = [&](int tile, int& c, int& m0, int& gact, int64_t& src0) {
-    c = tile / tpc;
-    m0 = (tile - c * tpc) * G;
+  // tiles are walked with a stride of gridDim.x: (channel, tile-in-channel) advance incrementally,
+  // one division per thread at kernel start instead of one per tile (ncu: 4-6 % of all instructions)
+  const int step_c = (int)gridDim.x / tpc, step_r = (int)gridDim.x - step_c * tpc;
+  auto advance = [&](int& cc, int& rr) {
+    cc += step_c;
+    rr += step_r;
+    if (rr >= tpc) {
+      rr -= tpc;
+      ++cc;
+    }
+  };
+  auto tile_geom = [&](int c, int r, int& m0, int& gact, int64_t& src0) {
+    m0 = r * G;
     const int64_t left = a.M - m0;
     gact = left < G ? (int)left : G;
     src0 = (int64_t)m0 * hop - a.pad_lo;
@@ -304,10 +318,10 @@ __global__ void __launch_bounds__(CF::THREADS, MINB) stft_r2c_staged_kernel(cons
   // mbarrier / stage buffer of (stage) for this thread's group
   const uint32_t mybar = CF::PERGROUP ? bar0 + 16 * g : bar0;
   float* const mystage = CF::PERGROUP ? stage0 + (size_t)g * CF::FRAME_STAGE : stage0;
-  auto issue = [&](int tile, int stage) {
-    int c, m0, gact;
+  auto issue = [&](int c, int r, int stage) {
+    int m0, gact;
     int64_t src0;
-    if (tile_geom(tile, c, m0, gact, src0)) {
+    if (tile_geom(c, r, m0, gact, src0)) {
       const uint32_t bar = mybar + 8 * stage;
       int64_t s = CF::PERGROUP ? src0 + (int64_t)g * hop : src0;
       uint32_t bytes = (uint32_t)((CF::PERGROUP ? NFFT : (gact - 1) * hop + NFFT) * sizeof(float));
@@ -323,19 +337,22 @@ __global__ void __launch_bounds__(CF::THREADS, MINB) stft_r2c_staged_kernel(cons
 
   uint32_t phase_bits = 0;  // bit s = parity to wait for on stage s
   int tile = blockIdx.x;
-  if (tile < total_tiles && issuer) issue(tile, 0);
+  int c = tile / tpc, rt = tile - c * tpc;  // this tile's channel and index inside the channel
+  if (tile < total_tiles && issuer) issue(c, rt, 0);
   for (int it = 0; tile < total_tiles; tile += gridDim.x, ++it) {
     const int stage = CF::LEAN ? 0 : (it & 1);
+    int cn = c, rn = rt;  // the tile this CTA takes next
+    advance(cn, rn);
     // stage^1 was last read in iteration it-1: PERGROUP -- this group's threads all passed that
     // iteration's barriers before the issuer gets here; else a CTA-wide barrier says so
     if constexpr (!CF::PERGROUP) __syncthreads();
     if constexpr (!CF::LEAN) {
-      if (issuer && tile + (int)gridDim.x < total_tiles) issue(tile + gridDim.x, stage ^ 1);
+      if (issuer && tile + (int)gridDim.x < total_tiles) issue(cn, rn, stage ^ 1);
     }
 
-    int c, m0, gact;
+    int m0, gact;
     int64_t src0;
-    const bool staged = tile_geom(tile, c, m0, gact, src0);
+    const bool staged = tile_geom(c, rt, m0, gact, src0);
     const int m = m0 + g;
     const bool active = g < gact;
     const int64_t f = (int64_t)c * a.M + m;
@@ -398,7 +415,7 @@ __global__ void __launch_bounds__(CF::THREADS, MINB) stft_r2c_staged_kernel(cons
       // the group has read its stage (and finished the previous frame's post-pass reads of the
       // exchange buffer): refill the stage with the next frame while this one is transformed
       sync();
-      if (issuer && tile + (int)gridDim.x < total_tiles) issue(tile + gridDim.x, 0);
+      if (issuer && tile + (int)gridDim.x < total_tiles) issue(cn, rn, 0);
       block_fft_single<PL>(v, t, bufA, tw, sync);
       sync();  // last pass's reads done before the post-pass reuses the buffer
     } else {
@@ -412,8 +429,7 @@ __global__ void __launch_bounds__(CF::THREADS, MINB) stft_r2c_staged_kernel(cons
       for (int q = 0; q < RL; ++q) pb[fft_out_index<PL>(t, b, q)] = v[fft_out_reg<PL>(b, q)];
     sync();
     if constexpr (MODE == kMel) {
-      // power of bins 0 .. N-1 (the lower half-spectrum, lib/nx_signal.ex:496) -> shared memory,
-      // then each thread owns mel bins in serpentine order (narrow low filters pair with wide high ones)
+      // power of bins 0 .. N-1 (the lower half-spectrum, lib/nx_signal.ex:496) -> shared memory in bin order
       float p0[P / 2], p1[P / 2], ph = 0.f;
       if (active) {
 #pragma unroll
@@ -432,8 +448,11 @@ __global__ void __launch_bounds__(CF::THREADS, MINB) stft_r2c_staged_kernel(cons
           }
         }
       }
-      sync();  // every read of the exchange buffer is done: it becomes the power spectrum
-      float* pw = reinterpret_cast<float*>(pb);
+      // the power spectrum goes to the exchange buffer the last pass did not use (its reads ended
+      // before the barrier above), so no barrier is needed here; with a single buffer (LEAN) every
+      // read of it must finish first
+      if constexpr (CF::LEAN) sync();
+      float* pw = reinterpret_cast<float*>(CF::LEAN ? pb : (pb == bufA ? bufB : bufA));
       if (active) {
 #pragma unroll
         for (int i = 0; i < P / 2; ++i) {
@@ -442,6 +461,39 @@ __global__ void __launch_bounds__(CF::THREADS, MINB) stft_r2c_staged_kernel(cons
           if (kk > 0) pw[N - kk] = p1[i];
           else pw[N / 2] = ph;
         }
+      }
+      sync();
+      // bin-major reduction (MelLayout): this thread owns bins [P t, P t + P) and emits one partial
+      // sum per filter segment it touches (pieces, numbered in bin order, in the buffer's upper half)
+      // (two buffers: pieces overwrite pb, whose pair reads all precede the barrier above)
+      float2* const piece = CF::LEAN ? reinterpret_cast<float2*>(pw + N) : reinterpret_cast<float2*>(pb);
+      if (active && mel_d >= 0) {
+        int r = mel_d & 0xfff;
+        const unsigned mask = ((unsigned)mel_d >> 12) & 0xffffu;
+        const float4* __restrict__ p4 = reinterpret_cast<const float4*>(pw + P * t);
+        // weights are stored load-major ([load i][thread t], MelLayout): conflict-free 128-bit reads
+        const float4* __restrict__ w4 = reinterpret_cast<const float4*>(mel_w) + t;
+        float U = 0.f, D = 0.f;
+#pragma unroll
+        for (int h = 0; h < P / 4; ++h) {
+          const float4 pv = p4[h];
+          const float4 wa = w4[(2 * h) * T], wb = w4[(2 * h + 1) * T];
+          const float pp[4] = {pv.x, pv.y, pv.z, pv.w};
+          const float wl[4] = {wa.x, wa.z, wb.x, wb.z}, wh[4] = {wa.y, wa.w, wb.y, wb.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int b = 4 * h + e;
+            if (b > 0 && ((mask >> b) & 1u)) {
+              piece[r] = make_float2(U, D);
+              ++r;
+              U = 0.f;
+              D = 0.f;
+            }
+            U = fmaf(wl[e], pp[e], U);
+            D = fmaf(wh[e], pp[e], D);
+          }
+        }
+        piece[r] = make_float2(U, D);
       }
       sync();
       if (active) {
@@ -456,27 +508,19 @@ __global__ void __launch_bounds__(CF::THREADS, MINB) stft_r2c_staged_kernel(cons
           mel_max = -INFINITY;
         }
         float* __restrict__ orow = a.mel_out + f * a.mel_bins;
-        for (int r = 0, j0 = 0; j0 < a.mel_bins; ++r, j0 += T) {
-          const int j = j0 + ((r & 1) ? T - 1 - t : t);
-          if (j < a.mel_bins) {
-            const int s0 = mel_i[j], n = mel_i[a.mel_bins + j];
-            const float* __restrict__ w = mel_w + mel_i[2 * a.mel_bins + j];
-            // four independent partial sums: the loads of one round are in flight together
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-            const float* __restrict__ pp = pw + s0;
-            int i = 0;
-            for (; i + 4 <= n; i += 4) {
-              a0 = fmaf(pp[i], w[i], a0);
-              a1 = fmaf(pp[i + 1], w[i + 1], a1);
-              a2 = fmaf(pp[i + 2], w[i + 2], a2);
-              a3 = fmaf(pp[i + 3], w[i + 3], a3);
-            }
-            for (; i < n; ++i) a0 = fmaf(pp[i], w[i], a0);
-            const float acc = (a0 + a1) + (a2 + a3);
-            const float v = __log2f(fmaxf(acc, 1.0e-10f)) * 0.30102999566f;  // log10(clip(mel, 1e-10)), :511
-            orow[j] = v;
-            mel_max = fmaxf(mel_max, v);
+        for (int j = t; j < a.mel_bins; j += T) {
+          // filter j = rising-slope pieces of segment j (.y) + falling-slope pieces of segment j + 1 (.x)
+          const int q0 = mel_ps[j], q1 = mel_ps[j + 1], q2 = mel_ps[j + 2];
+          float acc = 0.f;
+          // a handful of pieces per filter: a plain counted loop (unrolling only adds prologue code)
+#pragma unroll 1
+          for (int q = q0; q < q2; ++q) {
+            const float2 pc = piece[q];
+            acc += q < q1 ? pc.y : pc.x;
           }
+          const float v = __log2f(fmaxf(acc, 1.0e-10f)) * 0.30102999566f;  // log10(clip(mel, 1e-10)), :511
+          orow[j] = v;
+          mel_max = fmaxf(mel_max, v);
         }
       }
     } else if (active) {
@@ -506,6 +550,8 @@ __global__ void __launch_bounds__(CF::THREADS, MINB) stft_r2c_staged_kernel(cons
       bufA = bufB;
       bufB = tmp;
     }
+    c = cn;
+    rt = rn;
   }
   if constexpr (MODE == kMel) {
     if (mel_c >= 0) {  // uniform over a warp: its threads belong to one group
@@ -649,7 +695,16 @@ static int run_r2c_staged(nxs_ctx* ctx, StftArgs a, int64_t channels, cudaStream
               : a.onesided ? stft_r2c_staged_kernel<CF, MINB, kOneSided>
                            : stft_r2c_staged_kernel<CF, MINB, kTwoSided>;
   size_t smem = CF::SMEM;
-  if (a.mel_out) smem = (CF::SMEM + 15) / 16 * 16 + size_t(a.mel_nw) * sizeof(float) + 3 * size_t(a.mel_bins) * sizeof(int);
+  if (a.mel_out) {
+    const MelLayout* lay = nullptr;
+    rc = get_mel_layout(ctx, a.mel_bank, PL::P, &lay);
+    if (rc) return rc;
+    if (!lay->ok) return NXS_EUNSUPPORTED;  // not a triangular bank: the caller chains stft -> stft_to_mel
+    a.mel_w2 = lay->d_w2;
+    a.mel_desc = lay->d_desc;
+    a.mel_ps = lay->d_ps;
+    smem = (CF::SMEM + 15) / 16 * 16 + size_t(PL::N) * sizeof(float2) + size_t(a.mel_bins + 3) * sizeof(int);
+  }
   if (smem > 232448) return NXS_EUNSUPPORTED;
   NXS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 1;
@@ -722,10 +777,8 @@ int launch_stft(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, 
   a.tw = nullptr;
   a.post = nullptr;
   if (mel) {  // fused log-mel epilogue: served by the staged kernels only
-    a.mel_wts = mel->wts;
-    a.mel_idx = mel->idx;
-    a.mel_bins = mel->mel_bins;
-    a.mel_nw = mel->nw;
+    a.mel_bank = mel->bank;
+    a.mel_bins = (int)mel->bank->mel_bins;
     a.mel_out = mel->out;
     a.mel_chmax = mel->chmax;
   }

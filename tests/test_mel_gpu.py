@@ -109,6 +109,27 @@ def test_fused_stft_mel_equals_chain_and_oracle(nfft, hop, mels, padding, scalin
     np.testing.assert_allclose(fused.cpu().numpy(), want, atol=TOL, rtol=0)
 
 
+@pytest.mark.parametrize("nfft,hop,mels,sr", [(1024, 256, 80, 16000), (1024, 256, 128, 16000), (512, 128, 128, 8000),
+                                              (2048, 512, 128, 22050), (4096, 1024, 64, 11025), (1024, 256, 20, 16000),
+                                              (512, 256, 200, 16000)])
+def test_fused_stft_mel_full_band_banks(nfft, hop, mels, sr):
+    """Sampling rates at which the filters cover every FFT bin (at 48 kHz only the lowest third is
+    touched): every thread of the bin-major epilogue owns weights, filters span many threads."""
+    import torch
+
+    x = synth((2, 50 * nfft + 77), nfft + mels, fs=sr)
+    w = o.hann(nfft)
+    kw = dict(overlap_length=nfft - hop, fft_length=nfft, sampling_rate=sr)
+    xd, wd = torch.from_numpy(x).cuda(), torch.from_numpy(w).cuda()
+    fused = nx.stft_mel(xd, wd, mel_bins=mels, **kw)
+    z, _, _ = nx.stft(xd, wd, **kw)
+    chain = nx.stft_to_mel(z, sr, fft_length=nfft, mel_bins=mels)
+    assert float((fused - chain).abs().max()) <= 2e-6
+    zo, _, _ = o.stft_fast(x, w, **kw)
+    want = np.stack([o.stft_to_mel(zo[c], sr, nfft, mels) for c in range(2)])
+    np.testing.assert_allclose(fused.cpu().numpy(), want, atol=TOL, rtol=0)
+
+
 def test_fused_stft_mel_at_scale_channels_have_own_maximum():
     import torch
 
