@@ -252,15 +252,15 @@ __global__ void __launch_bounds__(THREADS, MINB) istft_rola_kernel(const IstftAr
   tw.init(twsm, t);
   const GroupSync<T> sync{1 + g};
 
-  // interior normaliser of the S samples a frame completes: all HOPDIV covering frames present,
-  // summed in ascending frame order (= descending window offset)
+  // interior normaliser of the S samples a frame completes (kept as its reciprocal): all HOPDIV
+  // covering frames present, summed in ascending frame order (= descending window offset)
   float normc[S];
 #pragma unroll
   for (int j = 0; j < S; ++j) {
     float nr = 0.f;
 #pragma unroll
     for (int k = HOPDIV - 1; k >= 0; --k) nr += w2(t + j * T + k * HOP);
-    normc[j] = nr;
+    normc[j] = 1.0f / (nr > 1.0e-10f ? nr : 1.0f);  // reciprocal of select(norm > 1e-10, norm, 1.0): one multiply per sample
   }
   // exact normaliser at output position p of a channel (edges: fewer covering frames)
   auto norm_at = [&](int64_t p) {
@@ -341,9 +341,12 @@ __global__ void __launch_bounds__(THREADS, MINB) istft_rola_kernel(const IstftAr
         const bool interior = m >= HOPDIV - 1;
 #pragma unroll
         for (int j = 0; j < S; ++j) {
-          const float nr = interior ? normc[j] : norm_at(pos + j * T);
-          const float d = nr > 1.0e-10f ? nr : 1.0f;  // select(norm > 1e-10, norm, 1.0)
-          __stcs(yc + pos + j * T, make_float2(acc[j].x / d, acc[j].y / d));
+          float rd = normc[j];
+          if (!interior) {
+            const float nr = norm_at(pos + j * T);
+            rd = 1.0f / (nr > 1.0e-10f ? nr : 1.0f);  // select(norm > 1e-10, norm, 1.0)
+          }
+          __stcs(yc + pos + j * T, make_float2(acc[j].x * rd, acc[j].y * rd));
         }
       }
 #pragma unroll
@@ -356,8 +359,8 @@ __global__ void __launch_bounds__(THREADS, MINB) istft_rola_kernel(const IstftAr
 #pragma unroll
       for (int j = 0; j < P - S; ++j) {
         const float nr = norm_at(pos + j * T);
-        const float d = nr > 1.0e-10f ? nr : 1.0f;
-        __stcs(yc + pos + j * T, make_float2(acc[j].x / d, acc[j].y / d));
+        const float rd = 1.0f / (nr > 1.0e-10f ? nr : 1.0f);
+        __stcs(yc + pos + j * T, make_float2(acc[j].x * rd, acc[j].y * rd));
       }
     }
     seg = nseg;
@@ -1211,8 +1214,9 @@ __global__ void __launch_bounds__(THREADS, MINB) istft_rola_c2r_kernel(const Ist
       for (int q = 0; q < R0; ++q) pre[b * R0 + q] = __ldg(a.pre + fft_in_index<PL>(t, b, q));
   }
 
-  // interior normaliser of the 2 S samples a frame completes (ascending frame order): registers
-  // for the small plans, shared memory when P = 16 leaves no room
+  auto guard = [](float nr) { return nr > 1.0e-10f ? nr : 1.0f; };  // select(norm > 1e-10, norm, 1.0)
+  // reciprocal interior normaliser of the 2 S samples a frame completes (ascending frame order):
+  // registers for the small plans, shared memory when P = 16 leaves no room
   constexpr bool NORM_REGS = P <= 8;
   float2 normc[NORM_REGS ? S : 1];
   float2* const nsm = reinterpret_cast<float2*>(smem_raw + CF::NORM_OFF);
@@ -1223,7 +1227,7 @@ __global__ void __launch_bounds__(THREADS, MINB) istft_rola_c2r_kernel(const Ist
       n0 += w2(2 * i2 + k * HOP);
       n1 += w2(2 * i2 + 1 + k * HOP);
     }
-    return make_float2(n0, n1);
+    return make_float2(1.0f / guard(n0), 1.0f / guard(n1));  // reciprocals: one multiply per sample
   };
   if constexpr (NORM_REGS) {
 #pragma unroll
@@ -1240,7 +1244,6 @@ __global__ void __launch_bounds__(THREADS, MINB) istft_rola_c2r_kernel(const Ist
     for (int64_t m = m_lo; m <= m_hi; ++m) nr += w2((int)(p - m * HOP));
     return nr;
   };
-  auto guard = [](float nr) { return nr > 1.0e-10f ? nr : 1.0f; };  // select(norm > 1e-10, norm, 1.0)
 
   const int gid = blockIdx.x * G + g, ngroups = gridDim.x * G;
   auto seg_bounds = [&](int seg, int& c, int64_t& mb, int64_t& ms, int64_t& me) {
@@ -1332,9 +1335,9 @@ __global__ void __launch_bounds__(THREADS, MINB) istft_rola_c2r_kernel(const Ist
 #pragma unroll
         for (int j = 0; j < S; ++j) {
           const int64_t p2 = pos2 + j * T;
-          float2 nr = NORM_REGS ? normc[NORM_REGS ? j : 0] : nsm[t + j * T];
-          if (!interior) nr = make_float2(norm_at(2 * p2), norm_at(2 * p2 + 1));
-          __stcs(yc + p2, make_float2(acc[j].x / guard(nr.x), acc[j].y / guard(nr.y)));
+          float2 rn = NORM_REGS ? normc[NORM_REGS ? j : 0] : nsm[t + j * T];
+          if (!interior) rn = make_float2(1.0f / guard(norm_at(2 * p2)), 1.0f / guard(norm_at(2 * p2 + 1)));
+          __stcs(yc + p2, make_float2(acc[j].x * rn.x, acc[j].y * rn.y));
         }
       }
 #pragma unroll
