@@ -212,7 +212,21 @@ def other_kernels(torch, nx, _lib, A, dev, local_rank, peak):
     ms = timed(lambda: _lib.check(lib.nxs_stft_to_mel_f32_dev(ctx, A.ptr(z), C5, M5, NFFT, NFFT, 128, float(FS), 3016.0,
                                                              200 / 3, A.ptr(mel), s), ctx))
     out["stft_to_mel_cfg5_spectrum"] = entry(ms, 4 * C5 * M5 * NFFT + 4 * C5 * M5 * 128, C5 * M5, "frames_per_s")
-    del z, y, mel
+    # opt-in c2r ISTFT on the same shape: one-sided spectrum in (513 bins per frame), real signal out
+    K1 = NFFT // 2 + 1
+    z1 = torch.randn(C5, M5, K1, 2, device=dev, generator=g)
+    y1 = torch.empty(C5, M5 * HOP + NFFT - HOP, device=dev)
+    ms = timed(lambda: _lib.check(lib.nxs_istft_c2r_f32_dev(ctx, A.ptr(z1), C5, M5, K1, A.ptr(w), NFFT, HOP, NFFT, 0,
+                                                           float(FS), A.ptr(y1), s), ctx))
+    out["istft_c2r_cfg5"] = entry(ms, 8 * C5 * M5 * K1 + 4 * C5 * (M5 * HOP + NFFT - HOP), C5 * M5, "frames_per_s")
+    # fused STFT -> log-mel on cfg5's signal shape (the spectrum is never stored): x in, 128 mel bins out
+    x5 = torch.randn(C5, L5, device=dev, generator=g)
+    ms = timed(lambda: _lib.check(lib.nxs_stft_mel_f32_dev(ctx, A.ptr(x5), C5, L5, L5, A.ptr(w), NFFT, HOP, NFFT,
+                                                          _lib.PAD_VALID, 0, 0, _lib.SCALE_NONE, float(FS), 128, 3016.0,
+                                                          200 / 3, A.ptr(mel), s), ctx))
+    out["stft_mel_fused_cfg5"] = entry(ms, 4 * C5 * L5 + 4 * C5 * M5 * 128, C5 * M5, "frames_per_s")
+    out["stft_mel_fused_cfg5"]["note"] = "kernel_ms = the fused STFT kernel only (the clamp/affine finalize pass adds ~0.1 ms); issue-bound, not HBM-bound"
+    del z, y, mel, z1, y1, x5
     # STFT, one GPU's shard of cfg3: 128 ch x 60 s, hann(4096), hop 1024
     C3, N3, H3 = 128, 4096, 1024
     M3 = (L5 - N3) // H3 + 1

@@ -59,6 +59,8 @@ enum {
 };
 /* :mode of convolve/correlate/fftconvolve: lib/nx_signal/convolution.ex:39-44 */
 enum { NXS_MODE_FULL = 0, NXS_MODE_SAME = 1, NXS_MODE_VALID = 2 };
+/* PeakFinding comparator: &Nx.less/2 (argrelmin), &Nx.greater/2 (argrelmax), and the two non-strict forms */
+enum { NXS_CMP_LESS = 0, NXS_CMP_GREATER = 1, NXS_CMP_LESS_EQUAL = 2, NXS_CMP_GREATER_EQUAL = 3 };
 
 typedef struct nxs_ctx nxs_ctx;
 
@@ -241,6 +243,36 @@ int nxs_convolve_nd_dev(nxs_ctx* ctx, const float* a, const int64_t a_shape[3], 
                         const int64_t b_shape[3], int is_complex, int mode, float* out, void* stream);
 int nxs_convolve_nd_host(nxs_ctx* ctx, const float* a, const int64_t a_shape[3], const float* b,
                          const int64_t b_shape[3], int is_complex, int mode, float* out);
+
+/* ---- spectrogram-adjacent operators -------------------
+ * Tensors are row-major, rank <= 3 for median / wiener (rank <= 8 for argrel*).
+ *
+ * NxSignal.Filters.median(t, kernel_shape: ks)  lib/nx_signal/filters.ex:17-56
+ *   out[i] = Nx.median of the ks-window that STARTS at i, the start clamped so
+ *   the window stays inside the tensor (Nx.slice); f32 out.  kernel_shape must
+ *   have t's rank ("kernel shape must be of the same rank as the tensor", :36)
+ *   and 1 <= ks[d] <= shape[d].
+ * NxSignal.Filters.wiener(t, kernel_size:, noise:)  filters.ex:80-110, 281-303
+ *   computed in f64 like the reference; t / out are f32 (is_f64 = 0) or f64;
+ *   has_noise = 0 estimates the noise as mean(local variance).
+ * NxSignal.PeakFinding.argrelextrema / argrelmin / argrelmax(data, axis:, order:)
+ *   lib/nx_signal/peak_finding.ex:131-391.  comparator NXS_CMP_*; indices is
+ *   s32 [prod(shape)][rank]: the multi-indices of the extrema in row-major order
+ *   followed by rows of -1; *valid_count their number (device pointer in the
+ *   _dev form).  Arbitrary comparator functions are not supported. */
+int nxs_median_f32_dev(nxs_ctx* ctx, const float* t, int rank, const int64_t* shape,
+                       const int64_t* kernel_shape, float* out, void* stream);
+int nxs_median_f32_host(nxs_ctx* ctx, const float* t, int rank, const int64_t* shape,
+                        const int64_t* kernel_shape, float* out);
+int nxs_wiener_dev(nxs_ctx* ctx, const void* t, int is_f64, int rank, const int64_t* shape,
+                   const int64_t* kernel_size, int has_noise, double noise, void* out, void* stream);
+int nxs_wiener_host(nxs_ctx* ctx, const void* t, int is_f64, int rank, const int64_t* shape,
+                    const int64_t* kernel_size, int has_noise, double noise, void* out);
+int nxs_argrelextrema_f32_dev(nxs_ctx* ctx, const float* data, int rank, const int64_t* shape, int axis,
+                              int order, int comparator, int32_t* indices, int64_t* valid_count,
+                              void* stream);
+int nxs_argrelextrema_f32_host(nxs_ctx* ctx, const float* data, int rank, const int64_t* shape, int axis,
+                               int order, int comparator, int32_t* indices, int64_t* valid_count);
 
 /* ---- multi-GPU setup: one broadcast of the coefficient block (window or FIR
  * taps) from rank 0 over NCCL; no other collective exists on this path

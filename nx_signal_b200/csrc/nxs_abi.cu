@@ -561,6 +561,119 @@ int nxs_stft_mel_f32_dev(nxs_ctx* ctx, const float* x, int64_t channels, int64_t
                          sampling_rate, mel_bins, max_mel, mel_frequency_spacing, out, pick(ctx, stream));
 }
 
+// ---- median / wiener / argrelextrema (nxs_post.cu) ------------------------------------------------
+// rank <= 3 tensors are viewed as 3-d with leading dimensions of size 1
+static int pad3(int rank, const int64_t* shape, const int64_t* kernel, int64_t s3[3], int64_t k3[3]) {
+  if (rank < 0 || rank > 3 || (rank > 0 && (!shape || !kernel))) return NXS_ESHAPE;
+  for (int i = 0; i < 3; ++i) s3[i] = k3[i] = 1;
+  for (int i = 0; i < rank; ++i) {
+    s3[3 - rank + i] = shape[i];
+    k3[3 - rank + i] = kernel[i];
+    if (shape[i] < 0 || kernel[i] < 1 || shape[i] >= (int64_t(1) << 31)) return NXS_ESHAPE;
+  }
+  return NXS_OK;
+}
+
+static int median_check(int rank, const int64_t* shape, const int64_t* kernel, int64_t s3[3], int64_t k3[3]) {
+  int rc = pad3(rank, shape, kernel, s3, k3);
+  if (rc) return rc;
+  for (int i = 0; i < 3; ++i)
+    if (s3[i] > 0 && k3[i] > s3[i]) return NXS_ESHAPE;  // Nx.slice: the window must fit inside the tensor
+  return NXS_OK;
+}
+
+int nxs_median_f32_dev(nxs_ctx* ctx, const float* t, int rank, const int64_t* shape, const int64_t* kernel_shape,
+                       float* out, void* stream) {
+  if (!ctx || !t || !out) return NXS_EINVAL;
+  int64_t s3[3], k3[3];
+  int rc = median_check(rank, shape, kernel_shape, s3, k3);
+  if (rc) return rc;
+  DeviceGuard guard(ctx->device);
+  return launch_median(ctx, t, s3, k3, out, pick(ctx, stream));
+}
+
+int nxs_median_f32_host(nxs_ctx* ctx, const float* t, int rank, const int64_t* shape, const int64_t* kernel_shape,
+                        float* out) {
+  if (!ctx || !t || !out) return NXS_EINVAL;
+  int64_t s3[3], k3[3];
+  int rc = median_check(rank, shape, kernel_shape, s3, k3);
+  if (rc) return rc;
+  DeviceGuard guard(ctx->device);
+  const size_t bytes = size_t(s3[0] * s3[1] * s3[2]) * sizeof(float);
+  return host_roundtrip(ctx, t, bytes, nullptr, 0, out, bytes, [&](void* dt, void*, void* dout) {
+    return launch_median(ctx, (const float*)dt, s3, k3, (float*)dout, ctx->stream);
+  });
+}
+
+int nxs_wiener_dev(nxs_ctx* ctx, const void* t, int is_f64, int rank, const int64_t* shape, const int64_t* kernel_size,
+                   int has_noise, double noise, void* out, void* stream) {
+  if (!ctx || !t || !out) return NXS_EINVAL;
+  int64_t s3[3], k3[3];
+  int rc = pad3(rank, shape, kernel_size, s3, k3);
+  if (rc) return rc;
+  DeviceGuard guard(ctx->device);
+  return launch_wiener(ctx, t, is_f64 != 0, s3, k3, has_noise != 0, noise, out, pick(ctx, stream));
+}
+
+int nxs_wiener_host(nxs_ctx* ctx, const void* t, int is_f64, int rank, const int64_t* shape, const int64_t* kernel_size,
+                    int has_noise, double noise, void* out) {
+  if (!ctx || !t || !out) return NXS_EINVAL;
+  int64_t s3[3], k3[3];
+  int rc = pad3(rank, shape, kernel_size, s3, k3);
+  if (rc) return rc;
+  DeviceGuard guard(ctx->device);
+  const size_t bytes = size_t(s3[0] * s3[1] * s3[2]) * (is_f64 ? sizeof(double) : sizeof(float));
+  return host_roundtrip(ctx, t, bytes, nullptr, 0, out, bytes, [&](void* dt, void*, void* dout) {
+    return launch_wiener(ctx, dt, is_f64 != 0, s3, k3, has_noise != 0, noise, dout, ctx->stream);
+  });
+}
+
+static int argrel_check(int rank, const int64_t* shape, int axis, int order, int comparator, int64_t* total) {
+  if (rank < 1 || rank > 8 || !shape) return NXS_ESHAPE;
+  if (axis < 0 || axis >= rank || order < 1) return NXS_EINVAL;
+  if (comparator < NXS_CMP_LESS || comparator > NXS_CMP_GREATER_EQUAL) return NXS_EINVAL;
+  int64_t n = 1;
+  for (int i = 0; i < rank; ++i) {
+    if (shape[i] < 0) return NXS_ESHAPE;
+    n *= shape[i];
+    if (n >= (int64_t(1) << 31)) return NXS_EUNSUPPORTED;
+  }
+  *total = n;
+  return NXS_OK;
+}
+
+int nxs_argrelextrema_f32_dev(nxs_ctx* ctx, const float* data, int rank, const int64_t* shape, int axis, int order,
+                              int comparator, int32_t* indices, int64_t* valid_count, void* stream) {
+  if (!ctx || !data || !indices || !valid_count) return NXS_EINVAL;
+  int64_t total = 0;
+  int rc = argrel_check(rank, shape, axis, order, comparator, &total);
+  if (rc) return rc;
+  DeviceGuard guard(ctx->device);
+  return launch_argrelextrema(ctx, data, rank, shape, axis, order, comparator, indices, valid_count, pick(ctx, stream));
+}
+
+int nxs_argrelextrema_f32_host(nxs_ctx* ctx, const float* data, int rank, const int64_t* shape, int axis, int order,
+                               int comparator, int32_t* indices, int64_t* valid_count) {
+  if (!ctx || !data || !indices || !valid_count) return NXS_EINVAL;
+  int64_t total = 0;
+  int rc = argrel_check(rank, shape, axis, order, comparator, &total);
+  if (rc) return rc;
+  DeviceGuard guard(ctx->device);
+  const size_t idx_bytes = size_t(total) * rank * sizeof(int32_t);
+  const size_t idx_pad = (idx_bytes + 255) / 256 * 256;
+  // staged result = indices followed by the count
+  rc = grow(ctx, &ctx->d_stage_out, &ctx->d_stage_out_bytes, idx_pad + 256, false);
+  if (rc) return rc;
+  rc = host_roundtrip(ctx, data, size_t(total) * sizeof(float), nullptr, 0, indices, idx_bytes,
+                      [&](void* dd, void*, void* dout) {
+                        return launch_argrelextrema(ctx, (const float*)dd, rank, shape, axis, order, comparator,
+                                                    (int*)dout, (int64_t*)((char*)dout + idx_pad), ctx->stream);
+                      });
+  if (rc) return rc;
+  NXS_CUDA(ctx, cudaMemcpy(valid_count, (char*)ctx->d_stage_out + idx_pad, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  return NXS_OK;
+}
+
 // ---- as_windowed ------------------------------------------------------------------------------
 static int aw_check(int elem_size, int64_t channels, int64_t length, int64_t x_ld, int64_t window_length,
                     int64_t stride, int pad_mode, int64_t pad_lo, int64_t pad_hi, PadGeom* g, int64_t* M) {

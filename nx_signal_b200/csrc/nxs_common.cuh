@@ -145,6 +145,13 @@ int get_mel_layout(nxs_ctx* ctx, MelBank* bank, int B, const MelLayout** out);
 int launch_convolve_nd(nxs_ctx* ctx, const float* a, const int64_t* as, const float* b, const int64_t* bs,
                        int is_complex, int mode, float* out, cudaStream_t st);
 
+int launch_median(nxs_ctx* ctx, const float* t, const int64_t shape[3], const int64_t kernel[3], float* out,
+                  cudaStream_t st);
+int launch_wiener(nxs_ctx* ctx, const void* t, int is_f64, const int64_t shape[3], const int64_t kernel[3],
+                  int has_noise, double noise, void* out, cudaStream_t st);
+int launch_argrelextrema(nxs_ctx* ctx, const float* data, int rank, const int64_t* shape, int axis, int order, int cmp,
+                         int* indices, int64_t* valid_dev, cudaStream_t st);
+
 // numpy-style reflect of index i into [0, L)
 __host__ __device__ inline int64_t reflect_index(int64_t i, int64_t L) {
   if (L <= 1) return 0;

@@ -831,3 +831,95 @@ def stft_to_mel(z, sampling_rate, fft_length, mel_bins=128, **kw):
     log_spec = _div(_f(np.log(_d(clipped))), _f(np.log(_d(F32(10)))))
     log_spec = np.maximum(log_spec, _sub(log_spec.max(), 8)).astype(F32)
     return _div(_add(log_spec, 4), 4)
+
+
+# ---------------------------------------------------------------------------
+# Spectrogram-adjacent ops: Filters.median / Filters.wiener
+# (lib/nx_signal/filters.ex:17-110, 281-303) and PeakFinding.argrel*
+# (lib/nx_signal/peak_finding.ex:131-391).  Pinned by the reference's own test
+# vectors (test/nx_signal/filters_test.exs:5-245, peak_finding_test.exs, the
+# doctests at filters.ex:68-78 and peak_finding.ex:36-128, 296-331).
+# ---------------------------------------------------------------------------
+def median(t, kernel_shape):
+    """filters.ex:17-56.  out[i] = Nx.median of the window that STARTS at i (Nx.slice clamps the
+    start so the window stays inside the tensor: start = min(i, dim - k) per axis), as f32."""
+    t = np.asarray(t)
+    kernel_shape = tuple(int(k) for k in kernel_shape)
+    if t.ndim != len(kernel_shape):
+        raise ValueError("kernel shape must be of the same rank as the tensor")
+    tf = t.astype(F64)
+    out = np.empty(t.shape, dtype=F32)
+    n = int(np.prod(kernel_shape))
+    for idx in np.ndindex(*t.shape):
+        sl = tuple(slice(min(i, d - k), min(i, d - k) + k) for i, d, k in zip(idx, t.shape, kernel_shape))
+        win = np.sort(tf[sl].reshape(-1))
+        if n % 2:
+            out[idx] = F32(win[n // 2])
+        else:
+            out[idx] = F32((win[n // 2 - 1] + win[n // 2]) / 2.0)
+    return out
+
+
+def _local_sum_same(a, kernel_size):
+    """correlate(a, ones(kernel_size), mode: :same) in double: the window of output i covers
+    [i - (k - 1) + (k - 1)//2, i + (k - 1)//2] per axis, zeros outside (convolution.ex:95-211)."""
+    a = np.asarray(a, dtype=F64)
+    full_shape = tuple(n + k - 1 for n, k in zip(a.shape, kernel_size))
+    full = np.zeros(full_shape, dtype=F64)
+    for idx in np.ndindex(*kernel_size):
+        sl = tuple(slice(i, i + s) for i, s in zip(idx, a.shape))
+        full[sl] += a
+    sl = tuple(slice((k - 1) // 2, (k - 1) // 2 + n) for n, k in zip(a.shape, kernel_size))
+    return full[sl]
+
+
+def wiener(t, kernel_size=3, noise=None):
+    """filters.ex:80-110, 281-303: computed in f64 (Nx.as_type(:f64)), cast back to t's type."""
+    t = np.asarray(t)
+    out_t = t.dtype if t.dtype in (np.dtype(F32), np.dtype(F64)) else np.dtype(F32)
+    if isinstance(kernel_size, (int, np.integer)):
+        kernel_size = (int(kernel_size),) * t.ndim
+    elif not isinstance(kernel_size, tuple):
+        raise ValueError("kernel_size must be an integer or tuple")
+    size = float(np.prod(kernel_size))
+    x = t.astype(F64)
+    l_mean = _local_sum_same(x, kernel_size) / size
+    l_var = _local_sum_same(x ** 2, kernel_size) / size - l_mean ** 2
+    nz = F64(np.mean(l_var)) if noise is None else F64(noise)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        res = (x - l_mean) * (1.0 - nz / l_var)
+    return np.where(l_var < nz, l_mean, res + l_mean).astype(out_t)
+
+
+def argrelextrema(data, comparator="greater", axis=0, order=1):
+    """peak_finding.ex:339-391.  comparator in {'less', 'greater', 'less_equal', 'greater_equal'}
+    (the reference takes any arity-2 function).  Returns (indices s32 {n, rank} with -1 rows after
+    the valid ones, valid_indices)."""
+    data = np.asarray(data)
+    cmp = {"less": np.less, "greater": np.greater, "less_equal": np.less_equal, "greater_equal": np.greater_equal}[comparator]
+    n = data.shape[axis]
+    locs = np.arange(n)
+    results = np.ones(data.shape, dtype=bool)
+    shift = 1
+    while shift < order + 1:
+        plus = np.take(data, np.clip(locs + shift, 0, n - 1), axis=axis)
+        minus = np.take(data, np.clip(locs - shift, 0, n - 1), axis=axis)
+        results &= cmp(data, plus)
+        results &= cmp(data, minus)
+        if not results.any():
+            break
+        shift += 1
+    flat = results.reshape(-1)
+    idx = np.stack(np.unravel_index(np.arange(flat.size), data.shape), axis=-1).astype(np.int32)
+    valid = idx[flat]
+    out = np.full((flat.size, data.ndim), -1, dtype=np.int32)
+    out[: valid.shape[0]] = valid
+    return out, int(flat.sum())
+
+
+def argrelmin(data, axis=0, order=1):
+    return argrelextrema(data, "less", axis=axis, order=order)
+
+
+def argrelmax(data, axis=0, order=1):
+    return argrelextrema(data, "greater", axis=axis, order=order)
