@@ -17,16 +17,18 @@ import numpy as np
 
 from . import _arrays as A
 from . import _lib
-from . import convolution, filters, windows
+from . import convolution, filters, peak_finding, windows
 from ._lib import NxSignalArgumentError
 
 Windows = windows
 Filters = filters
 Convolution = convolution
+PeakFinding = peak_finding
 
 __all__ = [
     "stft", "istft", "as_windowed", "overlap_and_add", "fft_frequencies", "stft_times", "mel_filters", "stft_to_mel", "stft_mel",
-    "Windows", "Filters", "Convolution", "windows", "filters", "convolution", "NxSignalArgumentError",
+    "Windows", "Filters", "Convolution", "PeakFinding", "windows", "filters", "convolution", "peak_finding",
+    "NxSignalArgumentError",
 ]
 
 _SCALING = {None: _lib.SCALE_NONE, "spectrum": _lib.SCALE_SPECTRUM, "psd": _lib.SCALE_PSD}

@@ -21,6 +21,7 @@ PAD_VALID, PAD_SAME, PAD_REFLECT, PAD_EXPLICIT = 0, 1, 2, 3
 SCALE_NONE, SCALE_SPECTRUM, SCALE_PSD = 0, 1, 2
 WIN = {"rectangular": 0, "bartlett": 1, "triangular": 2, "blackman": 3, "hamming": 4, "hann": 5, "kaiser": 6}
 MODE = {"full": 0, "same": 1, "valid": 2}
+CMP = {"less": 0, "greater": 1, "less_equal": 2, "greater_equal": 3}
 
 i64, f64, i32 = C.c_int64, C.c_double, C.c_int
 vp = C.c_void_p
@@ -54,6 +55,12 @@ SIGNATURES = {
     "nxs_istft_c64_host": (i32, [vp, vp, i64, i64, i64, vp, i64, i64, i64, i32, f64, vp]),
     "nxs_istft_c2r_f32_dev": (i32, [vp, vp, i64, i64, i64, vp, i64, i64, i64, i32, f64, vp, vp]),
     "nxs_istft_c2r_f32_host": (i32, [vp, vp, i64, i64, i64, vp, i64, i64, i64, i32, f64, vp]),
+    "nxs_median_f32_dev": (i32, [vp, vp, i32, C.POINTER(i64), C.POINTER(i64), vp, vp]),
+    "nxs_median_f32_host": (i32, [vp, vp, i32, C.POINTER(i64), C.POINTER(i64), vp]),
+    "nxs_wiener_dev": (i32, [vp, vp, i32, i32, C.POINTER(i64), C.POINTER(i64), i32, f64, vp, vp]),
+    "nxs_wiener_host": (i32, [vp, vp, i32, i32, C.POINTER(i64), C.POINTER(i64), i32, f64, vp]),
+    "nxs_argrelextrema_f32_dev": (i32, [vp, vp, i32, C.POINTER(i64), i32, i32, i32, vp, vp, vp]),
+    "nxs_argrelextrema_f32_host": (i32, [vp, vp, i32, C.POINTER(i64), i32, i32, i32, vp, C.POINTER(i64)]),
     "nxs_as_windowed_dev": (i32, [vp, vp, i32, i64, i64, i64, i64, i64, i32, i64, i64, vp, vp]),
     "nxs_as_windowed_host": (i32, [vp, vp, i32, i64, i64, i64, i64, i64, i32, i64, i64, vp]),
     "nxs_overlap_and_add_f32_dev": (i32, [vp, vp, i64, i64, i64, i64, vp, vp]),
