@@ -10,6 +10,7 @@
 // served by L1/L2 (neighbouring threads share all but one window column), every result
 // deterministic.  Tensors are rank <= 3 here (leading dimensions of size 1 for lower ranks).
 #include <math.h>
+#include <stdlib.h>
 
 #include "nxs_common.cuh"
 
@@ -74,8 +75,102 @@ __global__ void __launch_bounds__(kMedianThreads) median_kernel(const MedianArgs
   }
 }
 
+// Windows of up to 64 elements (every usual spectrogram smoothing window: 1 x 17, 31 x 1, 5 x 5 ...):
+// the window is gathered into KB registers (KB = 4 .. 64, the tail padded with +inf, which sorts last
+// and leaves the lower ranks unchanged) and sorted by a bitonic network of min/max pairs -- no
+// branches, no shared memory; neighbouring threads re-read the same lines from L1.  The window's
+// element offsets are precomputed on the host (kernel parameters = constant bank, indexed at compile
+// time after unrolling).
+template <int KB>
+struct MedianNetArgs {
+  const float* t;
+  float* out;
+  int d0, d1, d2, k0, k1, k2, n, total;
+  int off[KB];  // offset of window element e from the window's first element
+};
+
+template <int KB>
+__device__ __forceinline__ void bitonic_sort(float (&v)[KB]) {
+#pragma unroll
+  for (int k = 2; k <= KB; k <<= 1)
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1)
+#pragma unroll
+      for (int i = 0; i < KB; ++i) {
+        const int l = i ^ j;
+        if (l > i) {
+          const float a = v[i], b = v[l];
+          const bool asc = (i & k) == 0;
+          v[i] = asc ? fminf(a, b) : fmaxf(a, b);
+          v[l] = asc ? fmaxf(a, b) : fminf(a, b);
+        }
+      }
+}
+
+template <int KB>
+__global__ void __launch_bounds__(256) median_net_kernel(const MedianNetArgs<KB> a) {
+  const int r_hi = a.n / 2, r_lo = (a.n & 1) ? r_hi : r_hi - 1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.total; i += gridDim.x * blockDim.x) {
+    const int i2 = i % a.d2, q = i / a.d2;
+    const int i1 = q % a.d1, i0 = q / a.d1;
+    const int s0 = min(i0, a.d0 - a.k0), s1 = min(i1, a.d1 - a.k1), s2 = min(i2, a.d2 - a.k2);
+    const float* __restrict__ w = a.t + ((int64_t)s0 * a.d1 + s1) * a.d2 + s2;
+    float v[KB];
+#pragma unroll
+    for (int e = 0; e < KB; ++e) v[e] = e < a.n ? __ldg(w + a.off[e]) : INFINITY;
+    bitonic_sort<KB>(v);
+    float lo = 0.f, hi = 0.f;
+#pragma unroll
+    for (int e = 0; e < KB; ++e) {
+      if (e == r_lo) lo = v[e];
+      if (e == r_hi) hi = v[e];
+    }
+    // odd count: the middle element; even: Nx.median averages the two middle elements (in double, one rounding)
+    a.out[i] = (a.n & 1) ? hi : (float)(((double)lo + (double)hi) / 2.0);
+  }
+}
+
+template <int KB>
+static int run_median_net(nxs_ctx* ctx, const float* t, const int64_t shape[3], const int64_t kernel[3], float* out,
+                          cudaStream_t st) {
+  MedianNetArgs<KB> a;
+  a.t = t;
+  a.out = out;
+  a.d0 = (int)shape[0];
+  a.d1 = (int)shape[1];
+  a.d2 = (int)shape[2];
+  a.k0 = (int)kernel[0];
+  a.k1 = (int)kernel[1];
+  a.k2 = (int)kernel[2];
+  a.n = a.k0 * a.k1 * a.k2;
+  a.total = (int)(shape[0] * shape[1] * shape[2]);
+  for (int e = 0; e < KB; ++e) {
+    const int ee = e < a.n ? e : 0;
+    const int e2 = ee % a.k2, e1 = (ee / a.k2) % a.k1, e0 = ee / (a.k2 * a.k1);
+    a.off[e] = (e0 * a.d1 + e1) * a.d2 + e2;
+  }
+  int64_t grid = (int64_t(a.total) + 255) / 256;
+  if (grid > int64_t(ctx->sm_count) * 16) grid = int64_t(ctx->sm_count) * 16;
+  prof_begin(ctx, st);
+  median_net_kernel<KB><<<(unsigned)grid, 256, 0, st>>>(a);
+  prof_end(ctx, st);
+  ctx->launches++;
+  NXS_CUDA(ctx, cudaGetLastError());
+  return NXS_OK;
+}
+
 int launch_median(nxs_ctx* ctx, const float* t, const int64_t shape[3], const int64_t kernel[3], float* out,
                   cudaStream_t st) {
+  {
+    const int64_t total = shape[0] * shape[1] * shape[2], n = kernel[0] * kernel[1] * kernel[2];
+    if (total > 0 && total < (int64_t(1) << 31) - (int64_t(1) << 24) && n <= 64 && !getenv("NXS_MEDIAN_NO_NET")) {
+      if (n <= 4) return run_median_net<4>(ctx, t, shape, kernel, out, st);
+      if (n <= 8) return run_median_net<8>(ctx, t, shape, kernel, out, st);
+      if (n <= 16) return run_median_net<16>(ctx, t, shape, kernel, out, st);
+      if (n <= 32) return run_median_net<32>(ctx, t, shape, kernel, out, st);
+      return run_median_net<64>(ctx, t, shape, kernel, out, st);
+    }
+  }
   MedianArgs a;
   a.t = t;
   a.out = out;
@@ -110,8 +205,10 @@ int launch_median(nxs_ctx* ctx, const float* t, const int64_t shape[3], const in
 //   noise  = given, or mean(l_var)
 //   out    = l_var < noise ? l_mean : (t - l_mean) (1 - noise / l_var) + l_mean
 // The :same window of output i covers [i - (k-1) + (k-1)/2, i + (k-1)/2] per axis, zeros outside
-// (convolution.ex:95-211).  Pass 1 writes (l_mean, l_var) and per-block sums of l_var; a one-block
-// pass adds the block sums in a fixed order (deterministic); pass 2 applies the formula.
+// (convolution.ex:95-211).  Pass 1 writes (l_mean, l_var) and per-block sums of l_var; a one-thread
+// pass adds the block sums in a fixed order (deterministic); pass 2 applies the formula.  (Recomputing
+// the statistics in pass 2 instead of storing them was measured slower: the f64 window sums, not the
+// 32 bytes per element of scratch traffic, are the cost -- 5.5 vs 3.6 ms on a 360k x 513 spectrogram.)
 // ------------------------------------------------------------------------------------------
 struct WienerArgs {
   const void* t;
@@ -238,22 +335,24 @@ __device__ __forceinline__ bool relcmp(int cmp, float x, float y) {
 
 constexpr int kScanChunk = 1024;  // elements per compaction block
 
-__global__ void __launch_bounds__(256) relextrema_mask_kernel(const float* __restrict__ d, int64_t n, int64_t inner,
-                                                              int64_t total, int order, int cmp,
+__global__ void __launch_bounds__(256) relextrema_mask_kernel(const float* __restrict__ d, int n, int inner,
+                                                              int total, int order, int cmp,
                                                               unsigned char* __restrict__ mask,
                                                               int* __restrict__ block_count) {
   __shared__ int cnt;
-  for (int64_t blk = blockIdx.x; blk * kScanChunk < total; blk += gridDim.x) {
+  // (element counts are below 2^31 -- checked by the launcher -- so index arithmetic is 32-bit)
+  for (int blk = blockIdx.x; (int64_t)blk * kScanChunk < total; blk += gridDim.x) {
     if (threadIdx.x == 0) cnt = 0;
     __syncthreads();
     int mine = 0;
-    for (int64_t i = blk * kScanChunk + threadIdx.x; i < total && i < (blk + 1) * kScanChunk; i += blockDim.x) {
-      const int64_t pos = (i / inner) % n;
+    const int lim = (int)min((int64_t)total, (int64_t)(blk + 1) * kScanChunk);
+    for (int i = blk * kScanChunk + threadIdx.x; i < lim; i += blockDim.x) {
+      const int pos = (i / inner) % n;
       const float x = d[i];
       bool ok = true;
       for (int s = 1; s <= order && ok; ++s) {
-        const int64_t up = pos + s < n ? s : n - 1 - pos, dn = pos - s >= 0 ? s : pos;
-        ok = relcmp(cmp, x, d[i + up * inner]) && relcmp(cmp, x, d[i - dn * inner]);
+        const int up = pos + s < n ? s : n - 1 - pos, dn = pos - s >= 0 ? s : pos;
+        ok = relcmp(cmp, x, d[i + (int64_t)up * inner]) && relcmp(cmp, x, d[i - (int64_t)dn * inner]);
       }
       mask[i] = ok ? 1 : 0;
       mine += ok;
@@ -294,18 +393,19 @@ __global__ void __launch_bounds__(1024) block_scan_kernel(int* __restrict__ coun
 
 struct ShapeN {
   int rank;
-  int64_t dim[8];
+  int dim[8];
 };
 
-__global__ void __launch_bounds__(256) nonzero_scatter_kernel(const unsigned char* __restrict__ mask, int64_t total,
+__global__ void __launch_bounds__(256) nonzero_scatter_kernel(const unsigned char* __restrict__ mask, int total,
                                                               const int* __restrict__ block_offset, const ShapeN shp,
                                                               int* __restrict__ indices) {
   __shared__ int warp_tot[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int64_t blk = blockIdx.x; blk * kScanChunk < total; blk += gridDim.x) {
-    int64_t run = block_offset[blk];
-    for (int64_t base = blk * kScanChunk; base < (blk + 1) * kScanChunk && base < total; base += 256) {
-      const int64_t i = base + threadIdx.x;
+  for (int blk = blockIdx.x; (int64_t)blk * kScanChunk < total; blk += gridDim.x) {
+    int run = block_offset[blk];
+    const int lim = (int)min((int64_t)total, (int64_t)(blk + 1) * kScanChunk);
+    for (int base = blk * kScanChunk; base < lim; base += 256) {
+      const int i = base + threadIdx.x;
       const bool on = i < total && mask[i];
       const unsigned bal = __ballot_sync(0xffffffffu, on);
       if (lane == 0) warp_tot[warp] = __popc(bal);
@@ -317,10 +417,14 @@ __global__ void __launch_bounds__(256) nonzero_scatter_kernel(const unsigned cha
       }
       if (on) {
         const int64_t row = run + before + __popc(bal & ((1u << lane) - 1));
-        int64_t rem = i;
-        for (int ax = shp.rank - 1; ax >= 0; --ax) {
-          indices[row * shp.rank + ax] = (int)(rem % shp.dim[ax]);
-          rem /= shp.dim[ax];
+        int rem = i;
+#pragma unroll
+        for (int ax = 7; ax >= 0; --ax) {
+          if (ax < shp.rank) {
+            const int dd = shp.dim[ax], qq = rem / dd;
+            indices[row * shp.rank + ax] = rem - qq * dd;
+            rem = qq;
+          }
         }
       }
       run += all;
@@ -342,7 +446,7 @@ int launch_argrelextrema(nxs_ctx* ctx, const float* data, int rank, const int64_
   shp.rank = rank;
   int64_t total = 1, inner = 1;
   for (int i = 0; i < rank; ++i) {
-    shp.dim[i] = shape[i];
+    shp.dim[i] = (int)shape[i];
     total *= shape[i];
     if (i > axis) inner *= shape[i];
   }
@@ -360,9 +464,9 @@ int launch_argrelextrema(nxs_ctx* ctx, const float* data, int rank, const int64_
   int* counts = reinterpret_cast<int*>(mask + mask_bytes);
   int64_t grid = nblocks < int64_t(ctx->sm_count) * 8 ? nblocks : int64_t(ctx->sm_count) * 8;
   prof_begin(ctx, st);
-  relextrema_mask_kernel<<<(unsigned)grid, 256, 0, st>>>(data, n, inner, total, order, cmp, mask, counts);
+  relextrema_mask_kernel<<<(unsigned)grid, 256, 0, st>>>(data, (int)n, (int)inner, (int)total, order, cmp, mask, counts);
   block_scan_kernel<<<1, 1024, 0, st>>>(counts, nblocks, valid_dev);
-  nonzero_scatter_kernel<<<(unsigned)grid, 256, 0, st>>>(mask, total, counts, shp, indices);
+  nonzero_scatter_kernel<<<(unsigned)grid, 256, 0, st>>>(mask, (int)total, counts, shp, indices);
   int64_t g2 = (total * rank + 255) / 256;
   if (g2 > int64_t(ctx->sm_count) * 8) g2 = int64_t(ctx->sm_count) * 8;
   nonzero_fill_kernel<<<(unsigned)g2, 256, 0, st>>>(indices, total, rank, valid_dev);

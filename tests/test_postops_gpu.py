@@ -31,6 +31,17 @@ def test_median_vs_oracle_bit_exact(shape, ks):
     np.testing.assert_array_equal(nx.Filters.median(t, ks), o.median(t, ks))
 
 
+def test_median_large_window_and_rank_counting_kernel(monkeypatch):
+    """Windows above 64 elements use the rank-counting kernel; NXS_MEDIAN_NO_NET forces it for small ones."""
+    rng = np.random.default_rng(8)
+    t = rng.standard_normal((9, 400)).astype(np.float32)
+    np.testing.assert_array_equal(nx.Filters.median(t, (1, 129)), o.median(t, (1, 129)))
+    np.testing.assert_array_equal(nx.Filters.median(t, (9, 10)), o.median(t, (9, 10)))
+    monkeypatch.setenv("NXS_MEDIAN_NO_NET", "1")
+    np.testing.assert_array_equal(nx.Filters.median(t, (3, 5)), o.median(t, (3, 5)))
+    np.testing.assert_array_equal(nx.Filters.median(t, (1, 4)), o.median(t, (1, 4)))
+
+
 def test_median_on_a_spectrogram_stays_on_the_device():
     """HPSS-style use: median of |z| along time and along frequency, on CUDA tensors."""
     import torch
