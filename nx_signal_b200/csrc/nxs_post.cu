@@ -159,8 +159,119 @@ static int run_median_net(nxs_ctx* ctx, const float* t, const int64_t shape[3], 
   return NXS_OK;
 }
 
+// One-axis windows (1 x k, k x 1 ...: harmonic / percussive smoothing): two neighbouring outputs
+// along the axis share k - 1 of their k elements.  A thread sorts that shared core once (bitonic
+// network over KB >= k - 1 registers) and finishes each of its two outputs with a clamp: the rank-r
+// element of (sorted core c) + {x} is min(max(x, c[r-1]), c[r]) (c[-1] = -inf, c[k-1] = +inf).
+// The tensor is viewed as [outer][n][inner] around the axis; `inner` runs fastest over the threads so
+// the loads stay coalesced whichever axis carries the window.  Outputs whose window start is clamped
+// (the last k - 1 positions of the axis, Nx.slice semantics) take the plain sort of their window.
+struct MedianAxisArgs {
+  const float* t;
+  float* out;
+  int n, inner, k, pairs;  // axis length, inner size, window length, ceil(n / 2)
+  int total_threads;       // outer * pairs * inner
+};
+
+template <int KB>
+__device__ __forceinline__ float rank_with_extra(const float (&c)[KB], int r, float x) {
+  // rank r of the union of the sorted core and x
+  float below = -INFINITY, at = INFINITY;
+#pragma unroll
+  for (int e = 0; e < KB; ++e) {
+    if (e == r - 1) below = c[e];
+    if (e == r) at = c[e];
+  }
+  return fminf(fmaxf(x, below), at);
+}
+
+template <int KB>
+__global__ void __launch_bounds__(256) median_axis_kernel(const MedianAxisArgs a) {
+  const int k = a.k, core = k - 1;
+  const int r_hi = k / 2, r_lo = (k & 1) ? r_hi : r_hi - 1;
+  for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < a.total_threads; id += gridDim.x * blockDim.x) {
+    const int in = id % a.inner, q = id / a.inner;
+    const int p = q % a.pairs, o = q / a.pairs;
+    const int j0 = 2 * p;  // outputs j0 and j0 + 1 along the axis
+    const int64_t base = ((int64_t)o * a.n) * a.inner + in;
+    const float* __restrict__ col = a.t + base;
+    float* __restrict__ ocol = a.out + base;
+    const int last = a.n - k;  // last unclamped window start
+    if (j0 + 1 <= last) {
+      float c[KB];
+#pragma unroll
+      for (int e = 0; e < KB; ++e) c[e] = e < core ? __ldg(col + (int64_t)(j0 + 1 + e) * a.inner) : INFINITY;
+      bitonic_sort<KB>(c);
+      const float x0 = __ldg(col + (int64_t)j0 * a.inner), x1 = __ldg(col + (int64_t)(j0 + k) * a.inner);
+      float m0 = rank_with_extra<KB>(c, r_hi, x0), m1 = rank_with_extra<KB>(c, r_hi, x1);
+      if (!(k & 1)) {  // even window: Nx.median averages the two middle elements (in double, one rounding)
+        m0 = (float)(((double)rank_with_extra<KB>(c, r_lo, x0) + (double)m0) / 2.0);
+        m1 = (float)(((double)rank_with_extra<KB>(c, r_lo, x1) + (double)m1) / 2.0);
+      }
+      ocol[(int64_t)j0 * a.inner] = m0;
+      ocol[(int64_t)(j0 + 1) * a.inner] = m1;
+    } else {
+      // clamped starts: every output from `last` on is the median of the window [last, last + k)
+      for (int j = j0; j < j0 + 2 && j < a.n; ++j) {
+        const int s = j < last ? j : last;
+        float c[KB];
+#pragma unroll
+        for (int e = 0; e < KB; ++e) c[e] = e < core ? __ldg(col + (int64_t)(s + 1 + e) * a.inner) : INFINITY;
+        bitonic_sort<KB>(c);
+        const float x = __ldg(col + (int64_t)s * a.inner);
+        float m = rank_with_extra<KB>(c, r_hi, x);
+        if (!(k & 1)) m = (float)(((double)rank_with_extra<KB>(c, r_lo, x) + (double)m) / 2.0);
+        ocol[(int64_t)j * a.inner] = m;
+      }
+    }
+  }
+}
+
+template <int KB>
+static int run_median_axis(nxs_ctx* ctx, const MedianAxisArgs& a, cudaStream_t st) {
+  int64_t grid = (int64_t(a.total_threads) + 255) / 256;
+  if (grid > int64_t(ctx->sm_count) * 16) grid = int64_t(ctx->sm_count) * 16;
+  prof_begin(ctx, st);
+  median_axis_kernel<KB><<<(unsigned)grid, 256, 0, st>>>(a);
+  prof_end(ctx, st);
+  ctx->launches++;
+  NXS_CUDA(ctx, cudaGetLastError());
+  return NXS_OK;
+}
+
 int launch_median(nxs_ctx* ctx, const float* t, const int64_t shape[3], const int64_t kernel[3], float* out,
                   cudaStream_t st) {
+  {
+    // exactly one axis carries the window (2 <= k <= 65): shared-core kernel
+    const int64_t total = shape[0] * shape[1] * shape[2];
+    int axis = -1, nonunit = 0;
+    for (int i = 0; i < 3; ++i)
+      if (kernel[i] > 1) {
+        axis = i;
+        ++nonunit;
+      }
+    if (nonunit == 1 && kernel[axis] <= 65 && total > 0 && total < (int64_t(1) << 31) - (int64_t(1) << 24) &&
+        !getenv("NXS_MEDIAN_NO_AXIS") && !getenv("NXS_MEDIAN_NO_NET")) {
+      MedianAxisArgs a;
+      a.t = t;
+      a.out = out;
+      a.n = (int)shape[axis];
+      int64_t inner = 1, outer = 1;
+      for (int i = axis + 1; i < 3; ++i) inner *= shape[i];
+      for (int i = 0; i < axis; ++i) outer *= shape[i];
+      a.inner = (int)inner;
+      a.k = (int)kernel[axis];
+      a.pairs = (a.n + 1) / 2;
+      a.total_threads = (int)(outer * a.pairs * inner);
+      const int core = a.k - 1;
+      if (core <= 2) return run_median_axis<2>(ctx, a, st);
+      if (core <= 4) return run_median_axis<4>(ctx, a, st);
+      if (core <= 8) return run_median_axis<8>(ctx, a, st);
+      if (core <= 16) return run_median_axis<16>(ctx, a, st);
+      if (core <= 32) return run_median_axis<32>(ctx, a, st);
+      return run_median_axis<64>(ctx, a, st);
+    }
+  }
   {
     const int64_t total = shape[0] * shape[1] * shape[2], n = kernel[0] * kernel[1] * kernel[2];
     if (total > 0 && total < (int64_t(1) << 31) - (int64_t(1) << 24) && n <= 64 && !getenv("NXS_MEDIAN_NO_NET")) {

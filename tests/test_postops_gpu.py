@@ -31,12 +31,28 @@ def test_median_vs_oracle_bit_exact(shape, ks):
     np.testing.assert_array_equal(nx.Filters.median(t, ks), o.median(t, ks))
 
 
+@pytest.mark.parametrize("shape,ks", [((7, 100), (1, 2)), ((7, 100), (1, 3)), ((7, 101), (1, 4)), ((7, 101), (1, 5)),
+                                      ((7, 64), (1, 9)), ((7, 65), (1, 10)), ((7, 100), (1, 17)), ((7, 100), (1, 18)),
+                                      ((7, 100), (1, 33)), ((7, 100), (1, 34)), ((7, 100), (1, 65)), ((7, 100), (1, 100)),
+                                      ((100, 7), (17, 1)), ((101, 7), (18, 1)), ((5, 31, 6), (1, 31, 1)),
+                                      ((5, 30, 6), (1, 7, 1)), ((40, 3, 6), (9, 1, 1)), ((64,), (64,)), ((3,), (2,))])
+def test_median_one_axis_windows_bit_exact(shape, ks):
+    """The shared-core kernel: odd / even windows, odd / even axis lengths, every axis, clamped tails."""
+    rng = np.random.default_rng(sum(shape) * 31 + sum(ks))
+    t = rng.integers(-4, 5, size=shape).astype(np.float32)  # heavy ties
+    t += (rng.standard_normal(shape) * (rng.random(shape) < 0.5)).astype(np.float32)
+    np.testing.assert_array_equal(nx.Filters.median(t, ks), o.median(t, ks))
+
+
 def test_median_large_window_and_rank_counting_kernel(monkeypatch):
     """Windows above 64 elements use the rank-counting kernel; NXS_MEDIAN_NO_NET forces it for small ones."""
     rng = np.random.default_rng(8)
     t = rng.standard_normal((9, 400)).astype(np.float32)
     np.testing.assert_array_equal(nx.Filters.median(t, (1, 129)), o.median(t, (1, 129)))
     np.testing.assert_array_equal(nx.Filters.median(t, (9, 10)), o.median(t, (9, 10)))
+    monkeypatch.setenv("NXS_MEDIAN_NO_AXIS", "1")  # one-axis windows through the general network kernel
+    np.testing.assert_array_equal(nx.Filters.median(t, (1, 17)), o.median(t, (1, 17)))
+    np.testing.assert_array_equal(nx.Filters.median(t, (4, 1)), o.median(t, (4, 1)))
     monkeypatch.setenv("NXS_MEDIAN_NO_NET", "1")
     np.testing.assert_array_equal(nx.Filters.median(t, (3, 5)), o.median(t, (3, 5)))
     np.testing.assert_array_equal(nx.Filters.median(t, (1, 4)), o.median(t, (1, 4)))
