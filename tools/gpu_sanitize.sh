@@ -30,6 +30,34 @@ for K, L in [(2049, 30000), (255, 20000), (4097, 30000), (65, 5000), (600, 20001
 z = (rng.standard_normal((2, 50, 1024)) + 1j * rng.standard_normal((2, 50, 1024))).astype(np.complex64)
 m = nx.stft_to_mel(torch.from_numpy(z).cuda(), 48000, fft_length=1024, mel_bins=128)
 chk("stft_to_mel", m, np.stack([o.stft_to_mel(z[c], 48000, 1024, 128) for c in range(2)]))
+# fused log-mel at a sampling rate whose filters cover every bin (all threads of the bin-major epilogue active)
+for nfft, hop, mels in [(1024, 256, 80), (512, 128, 128), (2048, 512, 64)]:
+    x = rng.standard_normal((2, 12 * nfft)).astype(np.float32); w = o.hann(nfft)
+    kw = dict(overlap_length=nfft - hop, fft_length=nfft, sampling_rate=16000)
+    m = nx.stft_mel(torch.from_numpy(x).cuda(), torch.from_numpy(w).cuda(), mel_bins=mels, **kw)
+    zo, _, _ = o.stft_fast(x, w, **kw)
+    chk(f"stft_mel16k {nfft}/{mels}", m, np.stack([o.stft_to_mel(zo[c], 16000, nfft, mels) for c in range(2)]))
+# c2r ISTFT: packed kernels (tight odd row length: alternating 8-byte row alignment), extension path
+for nfft, hop in [(1024, 256), (1024, 512), (1024, 128), (512, 128), (2048, 512), (4096, 1024), (1024, 250), (256, 64)]:
+    K = nfft // 2 + 1
+    z1 = (rng.standard_normal((2, 40, K)) + 1j * rng.standard_normal((2, 40, K))).astype(np.complex64); w = o.hamming(nfft)
+    y = nx.istft(torch.from_numpy(z1).cuda(), torch.from_numpy(w).cuda(), overlap_length=nfft - hop, fft_length=nfft, onesided=True)
+    zz = z1.copy(); zz[..., 0] = zz[..., 0].real; zz[..., -1] = zz[..., -1].real
+    full = np.concatenate([zz, np.conj(zz[..., -2:0:-1])], axis=-1)
+    yo = o.istft_fast(full, w, overlap_length=nfft - hop, fft_length=nfft); chk(f"istft_c2r {nfft}/{hop}", y, yo.real.astype(np.float32))
+# post-ops: median (shared-core, network, rank-counting kernels), wiener, argrel
+t = rng.standard_normal((40, 70)).astype(np.float32)
+for ks in [(1, 17), (9, 1), (1, 4), (3, 3), (5, 5), (7, 10), (1, 66)]:
+    got = nx.Filters.median(torch.from_numpy(t).cuda(), ks).cpu().numpy(); assert np.array_equal(got, o.median(t, ks)), ks
+print("median OK")
+for ks, nz in [((3, 3), None), ((5, 2), 0.3)]:
+    chk(f"wiener {ks}", nx.Filters.wiener(torch.from_numpy(t).cuda(), kernel_size=ks, noise=nz), o.wiener(t, ks, nz), tol=1e-6)
+ti = rng.integers(-3, 4, size=(33, 130)).astype(np.float32)
+for axis, order in [(0, 1), (1, 3)]:
+    r = nx.PeakFinding.argrelmax(torch.from_numpy(ti).cuda(), axis=axis, order=order)
+    idx, valid = o.argrelmax(ti, axis=axis, order=order)
+    assert int(r["valid_indices"].cpu()) == valid and np.array_equal(r["indices"].cpu().numpy(), idx)
+print("argrel OK")
 torch.cuda.synchronize(); print("all cases done")
 PY
 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 1 python /tmp/san_cases.py > $OUT/memcheck.log 2>&1; echo "memcheck rc=$?" | tee -a $OUT/memcheck.log; grep -c "OK" $OUT/memcheck.log; grep -E "ERROR SUMMARY|Invalid|FAIL" $OUT/memcheck.log | head -5
