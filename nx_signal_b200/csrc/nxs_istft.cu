@@ -8,13 +8,18 @@
 //   istft_rola_kernel      hop = N/2, N/4, N/8: a group of T threads walks consecutive frames
 //                          and keeps the running overlap-add in registers (no CTA barrier, no
 //                          atomics, TMA-staged input) -- the hot path
-//   istft_kernel           any hop: a CTA owns a segment of frames, every group inverse-
-//                          transforms one frame into shared memory and the CTA gathers the
-//                          overlap-add (ascending frame order + a carry: deterministic)
+//   istft_ring_kernel      any hop <= N (at most 64 covering frames): the same per-group,
+//                          TMA-staged structure with the running overlap-add in a per-group
+//                          ring of N complex values in shared memory
+//   istft_kernel           z_len != N / unaligned rows: a CTA owns a segment of frames, every
+//                          group inverse-transforms one frame into shared memory and the CTA
+//                          gathers the overlap-add (ascending frame order + a carry: deterministic)
 //   ifft_frames_kernel /   nfft >= 4096 with an unsupported hop, and generic lengths: frames
 //   istft_dft_frames_kernel  to a scratch tensor, then istft_ola_norm_kernel gathers
 //   istft_edge_f64_kernel  always last: recomputes the ill-conditioned head / tail samples in
 //                          double, as the reference's f64 backend effectively does
+//   istft_rola_c2r_kernel  opt-in (nxs_istft_c2r_f32_*): one-sided Hermitian spectrum in, real
+//                          signal out; a half-length packed transform per frame (end of file)
 // Segments after the first recompute the few frames that overlap their start (warm-up)
 // instead of exchanging partial sums.  The normaliser is accumulated the same way from
 // |w|^2, which reproduces the reference's edge behaviour (fewer covering frames at both
