@@ -286,6 +286,18 @@ def main():
         run_reference(args, rank, world)
         return
 
+    # stdout carries exactly ONE JSON line: native libraries that write to fd 1 (NCCL prints its
+    # version banner there at communicator creation) are sent to stderr until the line is printed
+    sys.stdout.flush()
+    _stdout_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(_stdout_fd, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
+
     import torch
 
     import nx_signal_b200 as nx
@@ -475,7 +487,7 @@ def main():
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "other_kernels": other,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 

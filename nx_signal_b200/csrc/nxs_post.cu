@@ -444,38 +444,51 @@ __device__ __forceinline__ bool relcmp(int cmp, float x, float y) {
   }
 }
 
-constexpr int kScanChunk = 1024;  // elements per compaction block
+constexpr int kScanChunk = 4096;  // elements per compaction block (16 per thread)
 
+// mask bytes + per-chunk counts.  Element k * 256 + tid of a chunk belongs to thread tid in iteration k
+// (coalesced loads and byte stores); the mask buffer is padded to whole chunks and the pad is zeroed.
 __global__ void __launch_bounds__(256) relextrema_mask_kernel(const float* __restrict__ d, int n, int inner,
                                                               int total, int order, int cmp,
                                                               unsigned char* __restrict__ mask,
                                                               int* __restrict__ block_count) {
-  __shared__ int cnt;
+  __shared__ int warp_cnt[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // (element counts are below 2^31 -- checked by the launcher -- so index arithmetic is 32-bit)
   for (int blk = blockIdx.x; (int64_t)blk * kScanChunk < total; blk += gridDim.x) {
-    if (threadIdx.x == 0) cnt = 0;
-    __syncthreads();
     int mine = 0;
-    const int lim = (int)min((int64_t)total, (int64_t)(blk + 1) * kScanChunk);
-    for (int i = blk * kScanChunk + threadIdx.x; i < lim; i += blockDim.x) {
-      const int pos = (i / inner) % n;
-      const float x = d[i];
-      bool ok = true;
-      for (int s = 1; s <= order && ok; ++s) {
-        const int up = pos + s < n ? s : n - 1 - pos, dn = pos - s >= 0 ? s : pos;
-        ok = relcmp(cmp, x, d[i + (int64_t)up * inner]) && relcmp(cmp, x, d[i - (int64_t)dn * inner]);
+    const int64_t base = (int64_t)blk * kScanChunk;
+#pragma unroll 4
+    for (int k = 0; k < kScanChunk / 256; ++k) {
+      const int64_t i64 = base + k * 256 + threadIdx.x;
+      bool ok = false;
+      if (i64 < total) {
+        const int i = (int)i64;
+        const int pos = (i / inner) % n;
+        const float x = d[i];
+        ok = true;
+        for (int s = 1; s <= order && ok; ++s) {
+          const int up = pos + s < n ? s : n - 1 - pos, dn = pos - s >= 0 ? s : pos;
+          ok = relcmp(cmp, x, d[i + (int64_t)up * inner]) && relcmp(cmp, x, d[i - (int64_t)dn * inner]);
+        }
       }
-      mask[i] = ok ? 1 : 0;
+      mask[i64] = ok ? 1 : 0;
       mine += ok;
     }
-    atomicAdd(&cnt, mine);  // integer: order-independent
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if (lane == 0) warp_cnt[warp] = mine;
     __syncthreads();
-    if (threadIdx.x == 0) block_count[blk] = cnt;
+    if (threadIdx.x == 0) {
+      int c = 0;
+      for (int w = 0; w < 8; ++w) c += warp_cnt[w];
+      block_count[blk] = c;
+    }
     __syncthreads();
   }
 }
 
-// exclusive scan of the block counts by one block (chunks of 1024 with a running carry)
+// exclusive scan of the chunk counts by one block (1024 at a time with a running carry)
 __global__ void __launch_bounds__(1024) block_scan_kernel(int* __restrict__ counts, int64_t nblocks,
                                                           int64_t* __restrict__ total_out) {
   __shared__ int64_t buf[1024];
@@ -507,48 +520,66 @@ struct ShapeN {
   int dim[8];
 };
 
+// A thread owns 16 consecutive mask bytes of the chunk (one 128-bit load); one block-wide exclusive
+// scan of the 256 per-thread counts places every thread's rows, which it then writes in element order.
 __global__ void __launch_bounds__(256) nonzero_scatter_kernel(const unsigned char* __restrict__ mask, int total,
                                                               const int* __restrict__ block_offset, const ShapeN shp,
                                                               int* __restrict__ indices) {
   __shared__ int warp_tot[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int blk = blockIdx.x; (int64_t)blk * kScanChunk < total; blk += gridDim.x) {
-    int run = block_offset[blk];
-    const int lim = (int)min((int64_t)total, (int64_t)(blk + 1) * kScanChunk);
-    for (int base = blk * kScanChunk; base < lim; base += 256) {
-      const int i = base + threadIdx.x;
-      const bool on = i < total && mask[i];
-      const unsigned bal = __ballot_sync(0xffffffffu, on);
-      if (lane == 0) warp_tot[warp] = __popc(bal);
-      __syncthreads();
-      int before = 0, all = 0;
-      for (int w = 0; w < 8; ++w) {
-        if (w < warp) before += warp_tot[w];
-        all += warp_tot[w];
-      }
-      if (on) {
-        const int64_t row = run + before + __popc(bal & ((1u << lane) - 1));
-        int rem = i;
+    const int64_t first = (int64_t)blk * kScanChunk + threadIdx.x * 16;
+    const uint4 m = *reinterpret_cast<const uint4*>(mask + first);  // padded buffer: always in bounds
+    const unsigned words[4] = {m.x, m.y, m.z, m.w};
+    const int mine = __popc(m.x) + __popc(m.y) + __popc(m.z) + __popc(m.w);  // bytes are 0 / 1
+    int incl = mine;
 #pragma unroll
-        for (int ax = 7; ax >= 0; --ax) {
-          if (ax < shp.rank) {
-            const int dd = shp.dim[ax], qq = rem / dd;
-            indices[row * shp.rank + ax] = rem - qq * dd;
-            rem = qq;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    int before = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w)
+      if (w < warp) before += warp_tot[w];
+    int64_t row = (int64_t)block_offset[blk] + before + incl - mine;
+    if (mine) {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        if ((words[e >> 2] >> (8 * (e & 3))) & 1u) {
+          int rem = (int)(first + e);
+#pragma unroll
+          for (int ax = 7; ax >= 0; --ax) {
+            if (ax < shp.rank) {
+              const int dd = shp.dim[ax], qq = rem / dd;
+              indices[row * shp.rank + ax] = rem - qq * dd;
+              rem = qq;
+            }
           }
+          ++row;
         }
       }
-      run += all;
-      __syncthreads();
     }
+    __syncthreads();
   }
 }
 
 __global__ void __launch_bounds__(256) nonzero_fill_kernel(int* __restrict__ indices, int64_t total, int rank,
                                                            const int64_t* __restrict__ valid) {
   const int64_t first = *valid * rank, end = total * rank;
-  for (int64_t i = first + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < end; i += (int64_t)gridDim.x * blockDim.x)
-    indices[i] = -1;
+  // scalar head up to the next 16-byte boundary, 128-bit stores over the body, scalar tail
+  const int64_t body0 = (first + 3) & ~(int64_t)3, body1 = end & ~(int64_t)3;
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
+  if (body0 >= body1) {
+    for (int64_t i = first + tid; i < end; i += nthr) indices[i] = -1;
+    return;
+  }
+  for (int64_t i = first + tid; i < body0; i += nthr) indices[i] = -1;
+  int4* __restrict__ v = reinterpret_cast<int4*>(indices);
+  for (int64_t i = body0 / 4 + tid; i < body1 / 4; i += nthr) v[i] = make_int4(-1, -1, -1, -1);
+  for (int64_t i = body1 + tid; i < end; i += nthr) indices[i] = -1;
 }
 
 int launch_argrelextrema(nxs_ctx* ctx, const float* data, int rank, const int64_t* shape, int axis, int order, int cmp,
@@ -568,7 +599,7 @@ int launch_argrelextrema(nxs_ctx* ctx, const float* data, int rank, const int64_
   if (total >= (int64_t(1) << 31)) return NXS_EUNSUPPORTED;
   const int64_t n = shape[axis];
   const int64_t nblocks = (total + kScanChunk - 1) / kScanChunk;
-  const size_t mask_bytes = (size_t(total) + 255) / 256 * 256;
+  const size_t mask_bytes = size_t(nblocks) * kScanChunk;  // whole chunks: the kernels read / write the pad
   int rc = ensure_scratch(ctx, mask_bytes + size_t(nblocks) * sizeof(int));
   if (rc) return rc;
   unsigned char* mask = reinterpret_cast<unsigned char*>(ctx->d_scratch);
