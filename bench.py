@@ -438,6 +438,31 @@ def main():
             torch.cuda.synchronize(dev)
             e2e["host_equals_device_bitwise"] = bool(torch.equal(torch.view_as_real(step_dev2).cpu(),
                                                                  torch.view_as_real(zh[CHANNELS - 1, M - 4096:])))
+        # the same workload through the fused STFT -> log-mel host entry: 128 mel bins per frame come back
+        # instead of the spectrum; one rank only, reported beside the headline e2e
+        if world == 1:
+            try:
+                melh = torch.empty((CHANNELS, M, 128), dtype=torch.float32, pin_memory=True)
+
+                def step_mel_host():
+                    rc = lib.nxs_stft_mel_f32_host(ctx, A.ptr(xh), CHANNELS, L, L, wh.ctypes.data, NFFT, HOP, NFFT,
+                                                   _lib.PAD_VALID, 0, 0, _lib.SCALE_NONE, float(FS), 128, 3016.0,
+                                                   200 / 3, A.ptr(melh))
+                    _lib.check(rc, ctx, "stft_mel(host)")
+
+                step_mel_host()
+                te = time.perf_counter()
+                for _ in range(args.e2e_steps):
+                    step_mel_host()
+                mel_s = (time.perf_counter() - te) / args.e2e_steps
+                e2e["log_mel_host_call"] = {
+                    "value": FRAMES_PER_GPU / mel_s, "unit": "frames/s", "ms_per_step": 1e3 * mel_s,
+                    "h2d_bytes_per_step": int(xh.numel() * 4 + NFFT * 4), "d2h_bytes_per_step": int(melh.numel() * 4),
+                    "path": "nxs_stft_mel_f32_host on pinned host buffers: H2D | fused STFT -> log-mel kernel | D2H of "
+                            "[frames][128] f32 (the spectrum never leaves the SM)"}
+                del melh
+            except Exception as ex:
+                e2e["log_mel_host_call"] = {"error": repr(ex)[:200]}
     except Exception as ex:  # report, never fake
         e2e = {"value": None, "unit": "frames/s", "error": repr(ex)[:200]}
 

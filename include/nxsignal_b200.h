@@ -172,6 +172,13 @@ int nxs_stft_mel_f32_dev(nxs_ctx* ctx, const float* x, int64_t channels, int64_t
                          int pad_mode, int64_t pad_lo, int64_t pad_hi, int scaling, double sampling_rate,
                          int64_t mel_bins, double max_mel, double mel_frequency_spacing, float* out,
                          void* stream);
+/* host form: x / window / out are host pointers (H2D -> kernels -> D2H inside, synchronous).  0.13x the
+ * PCIe bytes of the STFT host entry (4 mel_bins bytes per frame come back instead of 4 (fft_length + 2));
+ * configurations the fused kernel does not serve are chained on the device inside the call. */
+int nxs_stft_mel_f32_host(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, int64_t x_ld,
+                         const float* window, int64_t frame_length, int64_t hop, int64_t fft_length,
+                         int pad_mode, int64_t pad_lo, int64_t pad_hi, int scaling, double sampling_rate,
+                         int64_t mel_bins, double max_mel, double mel_frequency_spacing, float* out);
 
 /* ---- ISTFT: NxSignal.istft(data, window, opts)  lib/nx_signal.ex:582-638 ---
  * z      [channels][num_frames][z_len] c64; Nx.ifft(length: fft_length) pads /

@@ -192,10 +192,9 @@ def stft_to_mel(z, sampling_rate, fft_length=None, mel_bins=128, max_mel=3016, m
 def stft_mel(data, window, overlap_length=None, fft_length="power_of_two", window_padding="valid",
              sampling_rate=100, scaling=None, mel_bins=128, max_mel=3016, mel_frequency_spacing=200 / 3):
     """``stft_to_mel(stft(data, window, ...)[0], sampling_rate, ...)`` in one pass (extension,
-    SURVEY 8f rank 1): CUDA tensors, f32 [..., M, mel_bins].  The fused kernel keeps each frame's
-    spectrum on chip; configurations it does not serve chain the two device entries instead."""
-    if not A.is_cuda(data):
-        raise NotImplementedError("stft_mel takes CUDA tensors")
+    SURVEY 8f rank 1): f32 [..., M, mel_bins].  The fused kernel keeps each frame's spectrum on chip;
+    configurations it does not serve chain the two device entries instead.  numpy arrays go through
+    the host entry (H2D of the signal, D2H of the mel tensor only)."""
     scale = _scaling_code(scaling)
     x = A.to_real_f32(data, "data")
     w = A.like_device(x, A.to_real_f32(window, "window"))
@@ -214,6 +213,12 @@ def stft_mel(data, window, overlap_length=None, fft_length="power_of_two", windo
     out = A.empty_like_kind(x, batch_shape + (M, int(mel_bins)), "f32")
     if M > 0 and Cn > 0:
         ctx = _lib.context(A.device_index(x))
+        if not A.is_cuda(x):
+            rc = _lib.lib().nxs_stft_mel_f32_host(ctx, A.ptr(x), Cn, L, L, A.ptr(w), N, hop, nfft, mode, lo, hi, scale,
+                                                  float(sampling_rate), int(mel_bins), float(max_mel),
+                                                  float(mel_frequency_spacing), A.ptr(out))
+            _lib.check(rc, ctx, "stft_mel")
+            return out
         rc = _lib.lib().nxs_stft_mel_f32_dev(ctx, A.ptr(x), Cn, L, L, A.ptr(w), N, hop, nfft, mode, lo, hi, scale,
                                              float(sampling_rate), int(mel_bins), float(max_mel),
                                              float(mel_frequency_spacing), A.ptr(out), A.stream_of(x))

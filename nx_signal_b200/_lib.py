@@ -46,6 +46,7 @@ SIGNATURES = {
     "nxs_stft_to_mel_f32_dev": (i32, [vp, vp, i64, i64, i64, i64, i64, f64, f64, f64, vp, vp]),
     "nxs_stft_to_mel_f32_host": (i32, [vp, vp, i64, i64, i64, i64, i64, f64, f64, f64, vp]),
     "nxs_stft_mel_f32_dev": (i32, [vp, vp, i64, i64, i64, vp, i64, i64, i64, i32, i64, i64, i32, f64, i64, f64, f64, vp, vp]),
+    "nxs_stft_mel_f32_host": (i32, [vp, vp, i64, i64, i64, vp, i64, i64, i64, i32, i64, i64, i32, f64, i64, f64, f64, vp]),
     "nxs_stft_times_f32": (i32, [i64, f64, i64, vp]),
     "nxs_num_frames": (i32, [i64, i64, i64, i32, i64, i64, C.POINTER(i64)]),
     "nxs_stft_f32_dev": (i32, [vp, vp, i64, i64, i64, vp, i64, i64, i64, i32, i64, i64, i32, f64, vp, vp]),

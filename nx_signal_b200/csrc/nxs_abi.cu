@@ -561,6 +561,45 @@ int nxs_stft_mel_f32_dev(nxs_ctx* ctx, const float* x, int64_t channels, int64_t
                          sampling_rate, mel_bins, max_mel, mel_frequency_spacing, out, pick(ctx, stream));
 }
 
+int nxs_stft_mel_f32_host(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, int64_t x_ld,
+                          const float* window, int64_t frame_length, int64_t hop, int64_t fft_length, int pad_mode,
+                          int64_t pad_lo, int64_t pad_hi, int scaling, double sampling_rate, int64_t mel_bins,
+                          double max_mel, double mel_frequency_spacing, float* out) {
+  if (!ctx || !x || !window || !out) return NXS_EINVAL;
+  PadGeom g;
+  int64_t M = 0;
+  int rc = stft_check(channels, length, x_ld, frame_length, hop, fft_length, pad_mode, pad_lo, pad_hi, scaling,
+                      sampling_rate, &g, &M);
+  if (rc) return rc;
+  if (M <= 0 || channels <= 0) return NXS_OK;
+  rc = mel_check(channels, M, fft_length, fft_length, mel_bins, sampling_rate, mel_frequency_spacing);
+  if (rc) return rc;
+  DeviceGuard guard(ctx->device);
+  const size_t in_bytes = (size_t(channels - 1) * x_ld + length) * sizeof(float);
+  const size_t out_bytes = size_t(channels) * M * mel_bins * sizeof(float);
+  return host_roundtrip(ctx, x, in_bytes, window, size_t(frame_length) * sizeof(float), out, out_bytes,
+                        [&](void* dx, void* dw, void* dout) {
+    int r = launch_stft_mel(ctx, (const float*)dx, channels, length, x_ld, (const float*)dw, frame_length, hop,
+                            fft_length, g, M, scaling, sampling_rate, mel_bins, max_mel, mel_frequency_spacing,
+                            (float*)dout, ctx->stream);
+    if (r != NXS_EUNSUPPORTED) return r;
+    // not served by the fused kernel: spectrum (one-sided when the length allows) to a temporary, then the mel kernel
+    const bool one = stft_has_exact_mirror(fft_length);
+    const int64_t z_ld = one ? fft_length / 2 + 1 : fft_length;
+    float2* z = nullptr;
+    cudaError_t e = cudaMalloc(&z, size_t(channels) * M * z_ld * sizeof(float2));
+    if (e != cudaSuccess) return set_cuda_error(ctx, e, "cudaMalloc(stft_mel spectrum)");
+    r = launch_stft(ctx, (const float*)dx, channels, length, x_ld, (const float*)dw, frame_length, hop, fft_length, g, M,
+                    scaling, sampling_rate, z, z_ld, one ? 1 : 0, ctx->stream);
+    if (r == NXS_OK)
+      r = launch_stft_to_mel(ctx, z, channels, M, z_ld, fft_length, mel_bins, sampling_rate, max_mel,
+                             mel_frequency_spacing, (float*)dout, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(z);
+    return r;
+  });
+}
+
 // ---- median / wiener / argrelextrema (nxs_post.cu) ------------------------------------------------
 // rank <= 3 tensors are viewed as 3-d with leading dimensions of size 1
 static int pad3(int rank, const int64_t* shape, const int64_t* kernel, int64_t s3[3], int64_t k3[3]) {

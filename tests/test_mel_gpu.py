@@ -130,6 +130,28 @@ def test_fused_stft_mel_full_band_banks(nfft, hop, mels, sr):
     np.testing.assert_allclose(fused.cpu().numpy(), want, atol=TOL, rtol=0)
 
 
+@pytest.mark.parametrize("nfft,hop,mels,padding", [(1024, 256, 128, "valid"), (512, 128, 40, "reflect"), (1024, 250, 80, "valid"),
+                                                   (400, 160, 40, "valid"), (1024, 64, 300, "same")])
+def test_stft_mel_host_entry_equals_device_entry(nfft, hop, mels, padding):
+    """numpy in / numpy out through nxs_stft_mel_f32_host: the fused kernel where it applies, the
+    chained kernels (inside the C call) elsewhere; same values as the device entries."""
+    import torch
+
+    sr = 16000
+    x = synth((3, 30 * nfft + 19), nfft + hop + mels, fs=sr)
+    w = o.hann(nfft)
+    kw = dict(overlap_length=nfft - hop, fft_length=nfft, sampling_rate=sr, window_padding=padding, mel_bins=mels)
+    host = nx.stft_mel(x, w, **kw)
+    assert isinstance(host, np.ndarray) and host.dtype == np.float32
+    dev = nx.stft_mel(torch.from_numpy(x).cuda(), torch.from_numpy(w).cuda(), **kw).cpu().numpy()
+    assert host.shape == dev.shape
+    assert np.abs(host - dev).max() <= 2e-6
+    kw.pop("mel_bins")
+    zo, _, _ = o.stft_fast(x, w, **kw) if nfft & (nfft - 1) == 0 else o.stft(x, w, **kw)
+    want = np.stack([o.stft_to_mel(zo[c], sr, nfft, mels) for c in range(3)])
+    np.testing.assert_allclose(host, want, atol=TOL, rtol=0)
+
+
 def test_fused_stft_mel_at_scale_channels_have_own_maximum():
     import torch
 
