@@ -576,28 +576,77 @@ int nxs_stft_mel_f32_host(nxs_ctx* ctx, const float* x, int64_t channels, int64_
   if (rc) return rc;
   DeviceGuard guard(ctx->device);
   const size_t in_bytes = (size_t(channels - 1) * x_ld + length) * sizeof(float);
-  const size_t out_bytes = size_t(channels) * M * mel_bins * sizeof(float);
-  return host_roundtrip(ctx, x, in_bytes, window, size_t(frame_length) * sizeof(float), out, out_bytes,
-                        [&](void* dx, void* dw, void* dout) {
-    int r = launch_stft_mel(ctx, (const float*)dx, channels, length, x_ld, (const float*)dw, frame_length, hop,
-                            fft_length, g, M, scaling, sampling_rate, mel_bins, max_mel, mel_frequency_spacing,
-                            (float*)dout, ctx->stream);
-    if (r != NXS_EUNSUPPORTED) return r;
-    // not served by the fused kernel: spectrum (one-sided when the length allows) to a temporary, then the mel kernel
+  const size_t w_bytes = size_t(frame_length) * sizeof(float);
+  const size_t row_out = size_t(M) * mel_bins;  // floats per channel
+  const size_t out_bytes = size_t(channels) * row_out * sizeof(float);
+  rc = grow(ctx, &ctx->d_stage_in, &ctx->d_stage_in_bytes, in_bytes + w_bytes + 512, false);
+  if (rc) return rc;
+  rc = grow(ctx, &ctx->d_stage_out, &ctx->d_stage_out_bytes, out_bytes + 256, false);
+  if (rc) return rc;
+  float* dx = (float*)ctx->d_stage_in;
+  float* dw = (float*)((char*)ctx->d_stage_in + (in_bytes + 255) / 256 * 256);
+  float* dout = (float*)ctx->d_stage_out;
+  NXS_CUDA(ctx, cudaMemcpyAsync(dw, window, w_bytes, cudaMemcpyHostToDevice, ctx->stream));
+
+  // Channels are independent (the clamp's maximum is per channel), so the call is pipelined over
+  // channel chunks: H2D of chunk k+1 | kernels of chunk k | D2H of chunk k-1 on three streams.
+  const int64_t nchunks = channels < 8 ? channels : 8;
+  const int64_t per = (channels + nchunks - 1) / nchunks;
+  bool chained = false;
+  for (int64_t c0 = 0, k = 0; c0 < channels && !chained; c0 += per, ++k) {
+    const int64_t nc = channels - c0 < per ? channels - c0 : per;
+    while ((size_t)(2 * k + 2) > ctx->slab_events.size()) {
+      cudaEvent_t e;
+      NXS_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      ctx->slab_events.push_back(e);
+    }
+    const size_t cb = (size_t(nc - 1) * x_ld + length) * sizeof(float);
+    NXS_CUDA(ctx, cudaMemcpyAsync(dx + c0 * x_ld, x + c0 * x_ld, cb, cudaMemcpyHostToDevice, ctx->copy_stream));
+    NXS_CUDA(ctx, cudaEventRecord(ctx->slab_events[2 * k], ctx->copy_stream));
+    NXS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->slab_events[2 * k], 0));
+    rc = launch_stft_mel(ctx, dx + c0 * x_ld, nc, length, x_ld, dw, frame_length, hop, fft_length, g, M, scaling,
+                         sampling_rate, mel_bins, max_mel, mel_frequency_spacing, dout + c0 * row_out, ctx->stream);
+    if (rc == NXS_EUNSUPPORTED && k == 0) {
+      chained = true;  // the fused kernel does not serve this configuration: one unpipelined chained pass below
+      break;
+    }
+    if (rc) break;
+    NXS_CUDA(ctx, cudaEventRecord(ctx->slab_events[2 * k + 1], ctx->stream));
+    NXS_CUDA(ctx, cudaStreamWaitEvent(ctx->out_stream, ctx->slab_events[2 * k + 1], 0));
+    NXS_CUDA(ctx, cudaMemcpyAsync(out + c0 * row_out, dout + c0 * row_out, size_t(nc) * row_out * sizeof(float),
+                                  cudaMemcpyDeviceToHost, ctx->out_stream));
+  }
+  if (chained) {
+    NXS_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    NXS_CUDA(ctx, cudaMemcpyAsync(dx, x, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    // spectrum (one-sided when the length allows) to a temporary, then the mel kernel
     const bool one = stft_has_exact_mirror(fft_length);
     const int64_t z_ld = one ? fft_length / 2 + 1 : fft_length;
     float2* z = nullptr;
     cudaError_t e = cudaMalloc(&z, size_t(channels) * M * z_ld * sizeof(float2));
     if (e != cudaSuccess) return set_cuda_error(ctx, e, "cudaMalloc(stft_mel spectrum)");
-    r = launch_stft(ctx, (const float*)dx, channels, length, x_ld, (const float*)dw, frame_length, hop, fft_length, g, M,
-                    scaling, sampling_rate, z, z_ld, one ? 1 : 0, ctx->stream);
-    if (r == NXS_OK)
-      r = launch_stft_to_mel(ctx, z, channels, M, z_ld, fft_length, mel_bins, sampling_rate, max_mel,
-                             mel_frequency_spacing, (float*)dout, ctx->stream);
+    rc = launch_stft(ctx, dx, channels, length, x_ld, dw, frame_length, hop, fft_length, g, M, scaling, sampling_rate, z,
+                     z_ld, one ? 1 : 0, ctx->stream);
+    if (rc == NXS_OK)
+      rc = launch_stft_to_mel(ctx, z, channels, M, z_ld, fft_length, mel_bins, sampling_rate, max_mel,
+                              mel_frequency_spacing, dout, ctx->stream);
+    if (rc == NXS_OK) {
+      cudaError_t e2 = cudaMemcpyAsync(out, dout, out_bytes, cudaMemcpyDeviceToHost, ctx->stream);
+      if (e2 != cudaSuccess) rc = set_cuda_error(ctx, e2, "cudaMemcpyAsync(mel result)");
+    }
     cudaStreamSynchronize(ctx->stream);
     cudaFree(z);
-    return r;
-  });
+    return rc;
+  }
+  // nothing of ours may still read or write the caller's buffers when the call returns
+  cudaError_t e1 = cudaStreamSynchronize(ctx->copy_stream);
+  cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+  cudaError_t e3 = cudaStreamSynchronize(ctx->out_stream);
+  if (rc) return rc;
+  NXS_CUDA(ctx, e1);
+  NXS_CUDA(ctx, e2);
+  NXS_CUDA(ctx, e3);
+  return NXS_OK;
 }
 
 // ---- median / wiener / argrelextrema (nxs_post.cu) ------------------------------------------------
