@@ -35,8 +35,8 @@ template <int T>
 struct GroupSync {
   int id;
   __device__ __forceinline__ void operator()() const {
-    if constexpr (T >= 32) asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(T) : "memory");
-    else __syncwarp();
+    if constexpr (T > 32) asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(T) : "memory");
+    else __syncwarp();  // a group of one warp (or less) needs no barrier unit
   }
 };
 

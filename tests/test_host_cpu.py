@@ -158,3 +158,44 @@ def test_mel_filters_doctest_row():  # lib/nx_signal.ex:384-394
     np.testing.assert_array_equal(m[0], np.array([0.0, 8.129208e-4, 0, 0, 0, 0, 0, 0, 0, 0], np.float32))
     np.testing.assert_array_equal(m[4, 4:], np.array([7.329034e-5, 2.3422057e-4, 3.8295105e-4, 2.871204e-4,
                                                       1.9128979e-4, 9.545916e-5], np.float32))
+
+
+def test_postop_and_onesided_argument_errors_need_no_device():
+    """Option validation of the extension heads happens on the host, before any context is created:
+    the reference's messages where it has them (filters_test.exs:99-117)."""
+    with pytest.raises(nx.NxSignalArgumentError, match="kernel shape must be of the same rank as the tensor"):
+        nx.Filters.median(np.arange(10), (5, 5))
+    with pytest.raises(nx.NxSignalArgumentError, match="kernel shape must be of the same rank as the tensor"):
+        nx.Filters.median(np.arange(25).reshape(5, 5), (5, 5, 5))
+    with pytest.raises(nx.NxSignalArgumentError, match="does not fit"):
+        nx.Filters.median(np.arange(10), (11,))
+    with pytest.raises(nx.NxSignalArgumentError, match="kernel_size must be an integer or tuple"):
+        nx.Filters.wiener(np.zeros((3, 3), np.float32), kernel_size=[3, 3])
+    with pytest.raises(nx.NxSignalArgumentError, match="rank"):
+        nx.Filters.wiener(np.zeros((3, 3), np.float32), kernel_size=(3,))
+    with pytest.raises(NotImplementedError, match="comparator"):
+        nx.PeakFinding.argrelextrema(np.arange(4), lambda a, b: a > b)
+    with pytest.raises(nx.NxSignalArgumentError, match="axis"):
+        nx.PeakFinding.argrelmin(np.arange(4), axis=2)
+    with pytest.raises(nx.NxSignalArgumentError, match="order"):
+        nx.PeakFinding.argrelmax(np.arange(4), order=0)
+    with pytest.raises(nx.NxSignalArgumentError, match="onesided istft"):
+        nx.istft(np.zeros((1, 4, 512), np.complex64), nx.windows.hann(1024), onesided=True, overlap_length=768,
+                 fft_length=1024)
+
+
+def test_post_op_entries_reject_bad_shapes_without_compute():
+    """The C entries validate before touching the device: NXS_ESHAPE / NXS_EINVAL with a null context is
+    NXS_EINVAL first (no crash), the shape rules are reachable through the Python checks above."""
+    lib = _lib.lib()
+    shape = (C.c_int64 * 1)(10)
+    ks = (C.c_int64 * 1)(3)
+    buf = np.zeros(10, np.float32)
+    assert lib.nxs_median_f32_host(None, buf.ctypes.data, 1, shape, ks, buf.ctypes.data) == _lib.NXS_EINVAL
+    assert lib.nxs_wiener_host(None, buf.ctypes.data, 0, 1, shape, ks, 0, 0.0, buf.ctypes.data) == _lib.NXS_EINVAL
+    cnt = C.c_int64(0)
+    idx = np.zeros((10, 1), np.int32)
+    assert lib.nxs_argrelextrema_f32_host(None, buf.ctypes.data, 1, shape, 0, 1, 0, idx.ctypes.data,
+                                          C.byref(cnt)) == _lib.NXS_EINVAL
+    assert lib.nxs_istft_c2r_f32_host(None, buf.ctypes.data, 1, 1, 3, buf.ctypes.data, 4, 2, 4, 0, 1.0,
+                                      buf.ctypes.data) == _lib.NXS_EINVAL

@@ -10,7 +10,7 @@ from tests.util import TOL, frame_rel_err, synth
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("nfft,variant", [(1024, v) for v in "012345"] + [(2048, v) for v in "012"] +
+@pytest.mark.parametrize("nfft,variant", [(1024, v) for v in "012345678"] + [(2048, v) for v in "012"] +
                          [(4096, v) for v in "0123"] + [(8192, v) for v in "01"])
 @pytest.mark.parametrize("padding", ["valid", "reflect"])
 def test_variant_parity(nfft, variant, padding, monkeypatch):
