@@ -483,11 +483,14 @@ int launch_fir(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, i
   a.H = nullptr;
   a.tw = nullptr;
   const int64_t K = num_taps;
-  if (K >= 16 && K <= 129) return run_fir<Plan<256, 16, 16, 16>, 256, 2>(ctx, a, channels, taps, st);
   const bool pg = !getenv("NXS_FIR_NO_PG");
   const char* var = getenv("NXS_FIR_VARIANT");  // tuning variants (tests/test_fir_conv_gpu.py)
   const int variant = var ? atoi(var) : 0;
-  if (K > 129 && K <= 513) {
+  // short filters: F = 256 blocks keep only 256 - K + 1 of every 256 samples; on long rows the
+  // per-group F = 1024 kernel (V = 1025 - K, 88 - 98 % kept) is the better trade
+  const bool short_on_long_rows = K >= 16 && K <= 129 && pg && variant != 2 && a.out_len >= 8192;
+  if (K >= 16 && K <= 129 && !short_on_long_rows) return run_fir<Plan<256, 16, 16, 16>, 256, 2>(ctx, a, channels, taps, st);
+  if (short_on_long_rows || (K > 129 && K <= 513)) {
     if (pg && variant == 1) return run_fir_pg<Plan<1024, 64, 8, 16, 8>, 256, 2>(ctx, a, channels, taps, st);
     if (pg) return run_fir_pg<Plan<1024, 64, 8, 16, 8>, 384, 2>(ctx, a, channels, taps, st);
     return run_fir<Plan<1024, 64, 8, 16, 8>, 256, 2>(ctx, a, channels, taps, st);
