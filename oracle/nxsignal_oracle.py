@@ -34,7 +34,11 @@ known-answer vector the reference holds for the path:
 81-85,246-250``, ``test/nx_signal/filters_test.exs:248-416``,
 ``test/nx_signal/convolutions_test.exs``.  STFT/ISTFT at nfft >= 32 is NOT
 pinned by any reference vector (the reference has none); there the oracle
-itself is the anchor.
+itself is the anchor.  ``median`` / ``wiener`` / ``argrel*`` (end of file) are
+pinned by ``tests/test_postops_oracle.py`` to
+``test/nx_signal/filters_test.exs:5-245`` and the doctests at
+``lib/nx_signal/filters.ex:68-78``, ``lib/nx_signal/peak_finding.ex:36-128,
+158-250`` (bit-exact, including the f64 wiener digits).
 
 Each function cites the reference file:line it follows.
 """
