@@ -435,6 +435,24 @@ int launch_wiener(nxs_ctx* ctx, const void* t, int is_f64, const int64_t shape[3
 // of -1, plus the count -- an order-preserving compaction (block counts -> one-block scan ->
 // scatter), deterministic.
 // ------------------------------------------------------------------------------------------
+// division of a non-negative 32-bit numerator by a divisor fixed at launch: one multiply-high and a
+// shift instead of the ~20-instruction emulated division (valid for numerators below 2^31)
+struct FastDiv {
+  unsigned mul = 0, shr = 0;
+  int d = 1;
+  FastDiv() {}
+  explicit FastDiv(int denom) : d(denom) {
+    if (denom > 1) {
+      unsigned lg = 0;
+      while ((1u << lg) < (unsigned)denom) ++lg;  // ceil(log2 denom)
+      const unsigned p = 31 + lg;
+      mul = (unsigned)((((uint64_t)1 << p) + (uint64_t)denom - 1) / (uint64_t)denom);
+      shr = p - 32;
+    }
+  }
+  __device__ __forceinline__ int div(int n) const { return d == 1 ? n : (int)(__umulhi((unsigned)n, mul) >> shr); }
+};
+
 __device__ __forceinline__ bool relcmp(int cmp, float x, float y) {
   switch (cmp) {
     case NXS_CMP_LESS: return x < y;
@@ -449,6 +467,7 @@ constexpr int kScanChunk = 4096;  // elements per compaction block (16 per threa
 // mask bytes + per-chunk counts.  Element k * 256 + tid of a chunk belongs to thread tid in iteration k
 // (coalesced loads and byte stores); the mask buffer is padded to whole chunks and the pad is zeroed.
 __global__ void __launch_bounds__(256) relextrema_mask_kernel(const float* __restrict__ d, int n, int inner,
+                                                              const FastDiv div_inner, const FastDiv div_n,
                                                               int total, int order, int cmp,
                                                               unsigned char* __restrict__ mask,
                                                               int* __restrict__ block_count) {
@@ -464,7 +483,8 @@ __global__ void __launch_bounds__(256) relextrema_mask_kernel(const float* __res
       bool ok = false;
       if (i64 < total) {
         const int i = (int)i64;
-        const int pos = (i / inner) % n;
+        const int row = div_inner.div(i);          // i / inner
+        const int pos = row - div_n.div(row) * n;  // (i / inner) % n
         const float x = d[i];
         ok = true;
         for (int s = 1; s <= order && ok; ++s) {
@@ -518,6 +538,7 @@ __global__ void __launch_bounds__(1024) block_scan_kernel(int* __restrict__ coun
 struct ShapeN {
   int rank;
   int dim[8];
+  FastDiv fd[8];
 };
 
 // A thread owns 16 consecutive mask bytes of the chunk (one 128-bit load); one block-wide exclusive
@@ -553,7 +574,7 @@ __global__ void __launch_bounds__(256) nonzero_scatter_kernel(const unsigned cha
 #pragma unroll
           for (int ax = 7; ax >= 0; --ax) {
             if (ax < shp.rank) {
-              const int dd = shp.dim[ax], qq = rem / dd;
+              const int dd = shp.dim[ax], qq = shp.fd[ax].div(rem);
               indices[row * shp.rank + ax] = rem - qq * dd;
               rem = qq;
             }
@@ -589,6 +610,7 @@ int launch_argrelextrema(nxs_ctx* ctx, const float* data, int rank, const int64_
   int64_t total = 1, inner = 1;
   for (int i = 0; i < rank; ++i) {
     shp.dim[i] = (int)shape[i];
+    shp.fd[i] = FastDiv((int)shape[i]);
     total *= shape[i];
     if (i > axis) inner *= shape[i];
   }
@@ -606,7 +628,8 @@ int launch_argrelextrema(nxs_ctx* ctx, const float* data, int rank, const int64_
   int* counts = reinterpret_cast<int*>(mask + mask_bytes);
   int64_t grid = nblocks < int64_t(ctx->sm_count) * 8 ? nblocks : int64_t(ctx->sm_count) * 8;
   prof_begin(ctx, st);
-  relextrema_mask_kernel<<<(unsigned)grid, 256, 0, st>>>(data, (int)n, (int)inner, (int)total, order, cmp, mask, counts);
+  relextrema_mask_kernel<<<(unsigned)grid, 256, 0, st>>>(data, (int)n, (int)inner, FastDiv((int)inner), FastDiv((int)n),
+                                                         (int)total, order, cmp, mask, counts);
   block_scan_kernel<<<1, 1024, 0, st>>>(counts, nblocks, valid_dev);
   nonzero_scatter_kernel<<<(unsigned)grid, 256, 0, st>>>(mask, (int)total, counts, shp, indices);
   int64_t g2 = (total * rank + 255) / 256;
