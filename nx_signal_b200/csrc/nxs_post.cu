@@ -16,6 +16,24 @@
 
 namespace nxs {
 
+// division of a non-negative 32-bit numerator by a divisor fixed at launch: one multiply-high and a
+// shift instead of the ~20-instruction emulated division (valid for numerators below 2^31)
+struct FastDiv {
+  unsigned mul = 0, shr = 0;
+  int d = 1;
+  FastDiv() {}
+  explicit FastDiv(int denom) : d(denom) {
+    if (denom > 1) {
+      unsigned lg = 0;
+      while ((1u << lg) < (unsigned)denom) ++lg;  // ceil(log2 denom)
+      const unsigned p = 31 + lg;
+      mul = (unsigned)((((uint64_t)1 << p) + (uint64_t)denom - 1) / (uint64_t)denom);
+      shr = p - 32;
+    }
+  }
+  __device__ __forceinline__ int div(int n) const { return d == 1 ? n : (int)(__umulhi((unsigned)n, mul) >> shr); }
+};
+
 // ------------------------------------------------------------------------------------------
 // median: out[i] = Nx.median of the window that STARTS at i, the start clamped per axis so the
 // window stays inside the tensor (Nx.slice semantics, filters.ex:25-27); f32 out.
@@ -86,6 +104,7 @@ struct MedianNetArgs {
   const float* t;
   float* out;
   int d0, d1, d2, k0, k1, k2, n, total;
+  FastDiv div_d2, div_d1;
   int off[KB];  // offset of window element e from the window's first element
 };
 
@@ -111,8 +130,8 @@ template <int KB>
 __global__ void __launch_bounds__(256) median_net_kernel(const MedianNetArgs<KB> a) {
   const int r_hi = a.n / 2, r_lo = (a.n & 1) ? r_hi : r_hi - 1;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.total; i += gridDim.x * blockDim.x) {
-    const int i2 = i % a.d2, q = i / a.d2;
-    const int i1 = q % a.d1, i0 = q / a.d1;
+    const int q = a.div_d2.div(i), i2 = i - q * a.d2;
+    const int i0 = a.div_d1.div(q), i1 = q - i0 * a.d1;
     const int s0 = min(i0, a.d0 - a.k0), s1 = min(i1, a.d1 - a.k1), s2 = min(i2, a.d2 - a.k2);
     const float* __restrict__ w = a.t + ((int64_t)s0 * a.d1 + s1) * a.d2 + s2;
     float v[KB];
@@ -144,6 +163,8 @@ static int run_median_net(nxs_ctx* ctx, const float* t, const int64_t shape[3], 
   a.k2 = (int)kernel[2];
   a.n = a.k0 * a.k1 * a.k2;
   a.total = (int)(shape[0] * shape[1] * shape[2]);
+  a.div_d2 = FastDiv(a.d2);
+  a.div_d1 = FastDiv(a.d1);
   for (int e = 0; e < KB; ++e) {
     const int ee = e < a.n ? e : 0;
     const int e2 = ee % a.k2, e1 = (ee / a.k2) % a.k1, e0 = ee / (a.k2 * a.k1);
@@ -171,6 +192,7 @@ struct MedianAxisArgs {
   float* out;
   int n, inner, k, pairs;  // axis length, inner size, window length, ceil(n / 2)
   int total_threads;       // outer * pairs * inner
+  FastDiv div_inner, div_pairs;
 };
 
 template <int KB>
@@ -190,8 +212,8 @@ __global__ void __launch_bounds__(256) median_axis_kernel(const MedianAxisArgs a
   const int k = a.k, core = k - 1;
   const int r_hi = k / 2, r_lo = (k & 1) ? r_hi : r_hi - 1;
   for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < a.total_threads; id += gridDim.x * blockDim.x) {
-    const int in = id % a.inner, q = id / a.inner;
-    const int p = q % a.pairs, o = q / a.pairs;
+    const int q = a.div_inner.div(id), in = id - q * a.inner;
+    const int o = a.div_pairs.div(q), p = q - o * a.pairs;
     const int j0 = 2 * p;  // outputs j0 and j0 + 1 along the axis
     const int64_t base = ((int64_t)o * a.n) * a.inner + in;
     const float* __restrict__ col = a.t + base;
@@ -263,6 +285,8 @@ int launch_median(nxs_ctx* ctx, const float* t, const int64_t shape[3], const in
       a.k = (int)kernel[axis];
       a.pairs = (a.n + 1) / 2;
       a.total_threads = (int)(outer * a.pairs * inner);
+      a.div_inner = FastDiv(a.inner);
+      a.div_pairs = FastDiv(a.pairs);
       const int core = a.k - 1;
       if (core <= 2) return run_median_axis<2>(ctx, a, st);
       if (core <= 4) return run_median_axis<4>(ctx, a, st);
@@ -435,24 +459,6 @@ int launch_wiener(nxs_ctx* ctx, const void* t, int is_f64, const int64_t shape[3
 // of -1, plus the count -- an order-preserving compaction (block counts -> one-block scan ->
 // scatter), deterministic.
 // ------------------------------------------------------------------------------------------
-// division of a non-negative 32-bit numerator by a divisor fixed at launch: one multiply-high and a
-// shift instead of the ~20-instruction emulated division (valid for numerators below 2^31)
-struct FastDiv {
-  unsigned mul = 0, shr = 0;
-  int d = 1;
-  FastDiv() {}
-  explicit FastDiv(int denom) : d(denom) {
-    if (denom > 1) {
-      unsigned lg = 0;
-      while ((1u << lg) < (unsigned)denom) ++lg;  // ceil(log2 denom)
-      const unsigned p = 31 + lg;
-      mul = (unsigned)((((uint64_t)1 << p) + (uint64_t)denom - 1) / (uint64_t)denom);
-      shr = p - 32;
-    }
-  }
-  __device__ __forceinline__ int div(int n) const { return d == 1 ? n : (int)(__umulhi((unsigned)n, mul) >> shr); }
-};
-
 __device__ __forceinline__ bool relcmp(int cmp, float x, float y) {
   switch (cmp) {
     case NXS_CMP_LESS: return x < y;
