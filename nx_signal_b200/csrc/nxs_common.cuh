@@ -152,6 +152,24 @@ int launch_wiener(nxs_ctx* ctx, const void* t, int is_f64, const int64_t shape[3
 int launch_argrelextrema(nxs_ctx* ctx, const float* data, int rank, const int64_t* shape, int axis, int order, int cmp,
                          int* indices, int64_t* valid_dev, cudaStream_t st);
 
+// division of a non-negative 32-bit numerator by a divisor fixed at launch: one multiply-high and a
+// shift instead of the ~20-instruction emulated division (valid for numerators below 2^31)
+struct FastDiv {
+  unsigned mul = 0, shr = 0;
+  int d = 1;
+  FastDiv() {}
+  explicit FastDiv(int denom) : d(denom) {
+    if (denom > 1) {
+      unsigned lg = 0;
+      while ((1u << lg) < (unsigned)denom) ++lg;  // ceil(log2 denom)
+      const unsigned p = 31 + lg;
+      mul = (unsigned)((((uint64_t)1 << p) + (uint64_t)denom - 1) / (uint64_t)denom);
+      shr = p - 32;
+    }
+  }
+  __device__ __forceinline__ int div(int n) const { return d == 1 ? n : (int)(__umulhi((unsigned)n, mul) >> shr); }
+};
+
 // numpy-style reflect of index i into [0, L)
 __host__ __device__ inline int64_t reflect_index(int64_t i, int64_t L) {
   if (L <= 1) return 0;

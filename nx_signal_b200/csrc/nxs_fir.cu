@@ -32,6 +32,7 @@ struct FirArgs {
   int V;  // valid outputs per block = F - K + 1
   int64_t b_lo;
   int pairs_per_channel;
+  FastDiv div_ppc;  // tile / pairs_per_channel without the emulated division (twice per block pair per thread)
   int total_tiles;
   const float2* H;  // [F], already divided by F
   const float2* tw;
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fir_ols_kernel(const FirArgs a)
     const bool active = tile < a.total_tiles;
     int c = 0, pi = 0;
     if (active) {
-      c = tile / a.pairs_per_channel;
+      c = a.div_ppc.div(tile);
       pi = tile - c * a.pairs_per_channel;
     }
     const float* __restrict__ xrow = a.x + (int64_t)c * a.x_ld;
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fir_ols_pg_kernel(const FirArgs
 
   // geometry of a block pair; returns whether its span can be staged by TMA
   auto geom = [&](int tile, int& c, int64_t& n0, int64_t& s0a, int& off, uint32_t& bytes) {
-    c = tile / a.pairs_per_channel;
+    c = a.div_ppc.div(tile);
     const int pi = tile - c * a.pairs_per_channel;
     n0 = (a.b_lo + 2 * (int64_t)pi) * a.V;
     const int64_t s0 = n0 - K1;
@@ -359,6 +360,7 @@ static int run_fir(nxs_ctx* ctx, FirArgs a, int64_t channels, const float* taps,
   const int64_t tiles = pairs * channels;
   if (tiles >= (int64_t(1) << 31)) return NXS_EUNSUPPORTED;
   a.pairs_per_channel = (int)pairs;
+  a.div_ppc = FastDiv((int)pairs);
   a.total_tiles = (int)tiles;
   const size_t smem = size_t(G) * 2 * PL::BUF * sizeof(cpx) + size_t(PL::TW_TOTAL) * sizeof(cpx);
   auto kern = fir_ols_kernel<PL, THREADS, MINB>;
@@ -419,6 +421,7 @@ static int run_fir_pg(nxs_ctx* ctx, FirArgs a, int64_t channels, const float* ta
   const int64_t tiles = pairs * channels;
   if (tiles >= (int64_t(1) << 31)) return NXS_EUNSUPPORTED;
   a.pairs_per_channel = (int)pairs;
+  a.div_ppc = FastDiv((int)pairs);
   a.total_tiles = (int)tiles;
   auto kern = fir_ols_pg_kernel<PL, THREADS, MINB>;
   const size_t smem = CF::smem(a.V);

@@ -27,9 +27,24 @@ __global__ void __launch_bounds__(256) as_windowed_kernel(const E* __restrict__ 
   }
 }
 
-struct Zero2 {
-  float x, y;
-};
+// the same gather with 32-bit indices and multiply-high divisions (outputs of fewer than 2^31
+// elements -- every BASELINE shape): the emulated 64-bit divisions above cost ~200 instructions per
+// copied element
+template <typename E>
+__global__ void __launch_bounds__(256) as_windowed_kernel32(const E* __restrict__ x, int L, int64_t x_ld, int N,
+                                                            int stride, int lo, int reflect, int M,
+                                                            const FastDiv div_n, const FastDiv div_m, int total,
+                                                            E* __restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int fm = div_n.div(i), n = i - fm * N;
+    const int c = div_m.div(fm), m = fm - c * M;
+    const int64_t src = (int64_t)m * stride + n - lo;
+    E v = E();
+    if (src >= 0 && src < L) v = x[c * x_ld + src];
+    else if (reflect) v = x[c * x_ld + reflect_index(src, L)];
+    out[i] = v;
+  }
+}
 
 int launch_as_windowed(nxs_ctx* ctx, const void* x, int elem_size, int64_t channels, int64_t length,
                        int64_t x_ld, int64_t window_length, int64_t stride, const PadGeom& g,
@@ -39,7 +54,17 @@ int launch_as_windowed(nxs_ctx* ctx, const void* x, int elem_size, int64_t chann
   int64_t grid = (total + 255) / 256;
   const int64_t cap = int64_t(ctx->sm_count) * 16;
   if (grid > cap) grid = cap;
-  if (elem_size == 4)
+  const bool small = total < (int64_t(1) << 31) - (int64_t(1) << 24) && length < (int64_t(1) << 31) &&
+                     stride < (int64_t(1) << 31) && g.lo < (int64_t(1) << 31);
+  if (small && elem_size == 4)
+    as_windowed_kernel32<float><<<(unsigned)grid, 256, 0, st>>>(
+        (const float*)x, (int)length, x_ld, (int)window_length, (int)stride, (int)g.lo, g.reflect, (int)num_frames,
+        FastDiv((int)window_length), FastDiv((int)num_frames), (int)total, (float*)out);
+  else if (small)
+    as_windowed_kernel32<double><<<(unsigned)grid, 256, 0, st>>>(
+        (const double*)x, (int)length, x_ld, (int)window_length, (int)stride, (int)g.lo, g.reflect, (int)num_frames,
+        FastDiv((int)window_length), FastDiv((int)num_frames), (int)total, (double*)out);
+  else if (elem_size == 4)
     as_windowed_kernel<float><<<(unsigned)grid, 256, 0, st>>>((const float*)x, channels, length, x_ld,
                                                               window_length, stride, g.lo, g.reflect,
                                                               num_frames, (float*)out);
@@ -80,6 +105,32 @@ __global__ void __launch_bounds__(256) overlap_add_kernel(const float* __restric
   }
 }
 
+// 32-bit / multiply-high form for inputs and outputs of fewer than 2^31 elements
+template <int CPLX>
+__global__ void __launch_bounds__(256) overlap_add_kernel32(const float* __restrict__ t, int M, int N, int hop,
+                                                            int out_len, const FastDiv div_out, const FastDiv div_hop,
+                                                            int total, float* __restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int b = div_out.div(i), n = i - b * out_len;
+    int m_hi = div_hop.div(n);
+    if (m_hi > M - 1) m_hi = M - 1;
+    const int m_lo = n - N + 1 <= 0 ? 0 : div_hop.div(n - N + hop);
+    float re = 0.f, im = 0.f;
+    int64_t idx = ((int64_t)b * M + m_lo) * N + (n - m_lo * hop);
+    for (int m = m_lo; m <= m_hi; ++m, idx += N - hop) {  // ascending m, as the reference's indexed_add visits them
+      if (CPLX) {
+        const float2 v = reinterpret_cast<const float2*>(t)[idx];
+        re += v.x;
+        im += v.y;
+      } else {
+        re += t[idx];
+      }
+    }
+    if (CPLX) reinterpret_cast<float2*>(out)[i] = make_float2(re, im);
+    else out[i] = re;
+  }
+}
+
 int launch_overlap_and_add(nxs_ctx* ctx, const float* t, int complex_, int64_t batch, int64_t num_frames,
                            int64_t frame_length, int64_t overlap, float* out, cudaStream_t st) {
   const int64_t hop = frame_length - overlap;
@@ -89,7 +140,14 @@ int launch_overlap_and_add(nxs_ctx* ctx, const float* t, int complex_, int64_t b
   int64_t grid = (total + 255) / 256;
   const int64_t cap = int64_t(ctx->sm_count) * 16;
   if (grid > cap) grid = cap;
-  if (complex_)
+  const int64_t lim = (int64_t(1) << 31) - (int64_t(1) << 24);
+  if (total < lim && out_len + frame_length < lim && complex_)
+    overlap_add_kernel32<1><<<(unsigned)grid, 256, 0, st>>>(t, (int)num_frames, (int)frame_length, (int)hop, (int)out_len,
+                                                            FastDiv((int)out_len), FastDiv((int)hop), (int)total, out);
+  else if (total < lim && out_len + frame_length < lim)
+    overlap_add_kernel32<0><<<(unsigned)grid, 256, 0, st>>>(t, (int)num_frames, (int)frame_length, (int)hop, (int)out_len,
+                                                            FastDiv((int)out_len), FastDiv((int)hop), (int)total, out);
+  else if (complex_)
     overlap_add_kernel<1><<<(unsigned)grid, 256, 0, st>>>(t, batch, num_frames, frame_length, hop, out_len, out);
   else
     overlap_add_kernel<0><<<(unsigned)grid, 256, 0, st>>>(t, batch, num_frames, frame_length, hop, out_len, out);

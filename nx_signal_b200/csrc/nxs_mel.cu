@@ -31,6 +31,8 @@ struct MelArgs {
   const int* offs;   // [mel_bins] offset of the run in wts
   float* out;        // [C][M][mel_bins]
   int* chmax;        // [C] ordered-int maximum of log_spec per channel
+  FastDiv div_m;     // f / M when total_frames < 2^31 (use_fastdiv)
+  int use_fastdiv;
 };
 
 __device__ __forceinline__ int float_key(float v) {
@@ -46,7 +48,7 @@ __global__ void __launch_bounds__(256) mel_logspec_kernel(const MelArgs a) {
   int64_t cur_c = -1;
   float cur_max = -INFINITY;
   for (int64_t f = (int64_t)blockIdx.x * wpb + warp; f < a.total_frames; f += (int64_t)gridDim.x * wpb) {
-    const int64_t c = f / a.M;
+    const int64_t c = a.use_fastdiv ? (int64_t)a.div_m.div((int)f) : f / a.M;
     if (c != cur_c) {
       if (cur_c >= 0 && lane == 0) atomicMax(a.chmax + cur_c, float_key(cur_max));
       cur_c = c;
@@ -266,6 +268,8 @@ int launch_stft_to_mel(nxs_ctx* ctx, const float2* z, int64_t channels, int64_t 
   a.M = num_frames;
   a.z_ld = z_ld;
   a.total_frames = channels * num_frames;
+  a.use_fastdiv = a.total_frames < (int64_t(1) << 31) && num_frames < (int64_t(1) << 31);
+  a.div_m = FastDiv(a.use_fastdiv ? (int)num_frames : 1);
   a.half = (int)half;
   a.mel_bins = (int)mel_bins;
   a.wts = bank->d_wts;

@@ -16,24 +16,6 @@
 
 namespace nxs {
 
-// division of a non-negative 32-bit numerator by a divisor fixed at launch: one multiply-high and a
-// shift instead of the ~20-instruction emulated division (valid for numerators below 2^31)
-struct FastDiv {
-  unsigned mul = 0, shr = 0;
-  int d = 1;
-  FastDiv() {}
-  explicit FastDiv(int denom) : d(denom) {
-    if (denom > 1) {
-      unsigned lg = 0;
-      while ((1u << lg) < (unsigned)denom) ++lg;  // ceil(log2 denom)
-      const unsigned p = 31 + lg;
-      mul = (unsigned)((((uint64_t)1 << p) + (uint64_t)denom - 1) / (uint64_t)denom);
-      shr = p - 32;
-    }
-  }
-  __device__ __forceinline__ int div(int n) const { return d == 1 ? n : (int)(__umulhi((unsigned)n, mul) >> shr); }
-};
-
 // ------------------------------------------------------------------------------------------
 // median: out[i] = Nx.median of the window that STARTS at i, the start clamped per axis so the
 // window stays inside the tensor (Nx.slice semantics, filters.ex:25-27); f32 out.
