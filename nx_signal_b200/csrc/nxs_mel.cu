@@ -97,12 +97,42 @@ __global__ void __launch_bounds__(256) mel_logspec_kernel(const MelArgs a) {
 }
 
 // log_spec = max(log_spec, reduce_max(log_spec) - 8); (log_spec + 4) / 4   (lib/nx_signal.ex:512-513)
-__global__ void __launch_bounds__(256) mel_finalize_kernel(float* __restrict__ out, int64_t per_channel, int64_t total,
-                                                           const int* __restrict__ chmax) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const float floor_v = key_float(chmax[i / per_channel]) - 8.0f;
-    out[i] = (fmaxf(out[i], floor_v) + 4.0f) / 4.0f;
+// blockIdx.y walks the channels (no per-element division), 128-bit accesses when the rows allow
+__global__ void __launch_bounds__(256) mel_finalize_kernel(float* __restrict__ out, int64_t per_channel, int64_t channels,
+                                                           const int* __restrict__ chmax, int vec4) {
+  for (int64_t c = blockIdx.y; c < channels; c += gridDim.y) {
+    const float floor_v = key_float(chmax[c]) - 8.0f;
+    float* __restrict__ row = out + c * per_channel;
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
+    if (vec4) {
+      float4* __restrict__ r4 = reinterpret_cast<float4*>(row);
+      for (int64_t i = tid; i < per_channel / 4; i += nthr) {
+        float4 v = r4[i];
+        v.x = (fmaxf(v.x, floor_v) + 4.0f) / 4.0f;
+        v.y = (fmaxf(v.y, floor_v) + 4.0f) / 4.0f;
+        v.z = (fmaxf(v.z, floor_v) + 4.0f) / 4.0f;
+        v.w = (fmaxf(v.w, floor_v) + 4.0f) / 4.0f;
+        r4[i] = v;
+      }
+    } else {
+      for (int64_t i = tid; i < per_channel; i += nthr) row[i] = (fmaxf(row[i], floor_v) + 4.0f) / 4.0f;
+    }
   }
+}
+
+static int launch_mel_finalize(nxs_ctx* ctx, float* out, int64_t per_channel, int64_t channels, const int* chmax,
+                               cudaStream_t st) {
+  const int vec4 = per_channel % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  const int64_t work = vec4 ? per_channel / 4 : per_channel;
+  int64_t gy = channels < 65535 ? channels : 65535;
+  int64_t gx = (work + 255) / 256;
+  const int64_t cap = (int64_t(ctx->sm_count) * 16 + gy - 1) / gy;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  mel_finalize_kernel<<<dim3((unsigned)gx, (unsigned)gy), 256, 0, st>>>(out, per_channel, channels, chmax, vec4);
+  ctx->launches++;
+  NXS_CUDA(ctx, cudaGetLastError());
+  return NXS_OK;
 }
 
 // sparse filterbank of one (fft_length, mel_bins, sampling_rate, max_mel, f_sp) on the device
@@ -288,14 +318,9 @@ int launch_stft_to_mel(nxs_ctx* ctx, const float2* z, int64_t channels, int64_t 
   mel_logspec_kernel<<<(unsigned)grid, wpb * 32, smem, st>>>(a);
   ctx->launches++;
   NXS_CUDA(ctx, cudaGetLastError());
-  const int64_t per_channel = num_frames * mel_bins, total = per_channel * channels;
-  int64_t g2 = (total + 255) / 256;
-  if (g2 > int64_t(ctx->sm_count) * 16) g2 = int64_t(ctx->sm_count) * 16;
-  mel_finalize_kernel<<<(unsigned)g2, 256, 0, st>>>(out, per_channel, total, chmax);
+  rc = launch_mel_finalize(ctx, out, num_frames * mel_bins, channels, chmax, st);
   prof_end(ctx, st);  // both kernels count
-  ctx->launches++;
-  NXS_CUDA(ctx, cudaGetLastError());
-  return NXS_OK;
+  return rc;
 }
 
 // stft -> log-mel in one pass: the STFT kernel's epilogue reduces each frame's spectrum to mel
@@ -317,13 +342,7 @@ int launch_stft_mel(nxs_ctx* ctx, const float* x, int64_t channels, int64_t leng
   rc = launch_stft(ctx, x, channels, length, x_ld, window, frame_length, hop, fft_length, g, num_frames, scaling,
                    sampling_rate, nullptr, fft_length, 0, st, &mel);
   if (rc) return rc;
-  const int64_t per_channel = num_frames * mel_bins, total = per_channel * channels;
-  int64_t g2 = (total + 255) / 256;
-  if (g2 > int64_t(ctx->sm_count) * 16) g2 = int64_t(ctx->sm_count) * 16;
-  mel_finalize_kernel<<<(unsigned)g2, 256, 0, st>>>(out, per_channel, total, chmax);
-  ctx->launches++;
-  NXS_CUDA(ctx, cudaGetLastError());
-  return NXS_OK;
+  return launch_mel_finalize(ctx, out, num_frames * mel_bins, channels, chmax, st);
 }
 
 }  // namespace nxs
