@@ -52,3 +52,43 @@ def test_argrelextrema_non_strict_comparator():  # the doctest's custom comparat
     x = np.array([0, 1, 1, 0, 2, 2, 2, 0], dtype=np.int32)
     idx, valid = o.argrelextrema(x, "greater_equal")
     np.testing.assert_array_equal(idx[:valid, 0], [1, 2, 4, 5, 6])  # edges compare with themselves and their one neighbour
+
+
+# ---- independent cross-checks against scipy (the reference's docs name scipy as the model) --------
+@pytest.mark.parametrize("shape,ks,noise", [((200,), 5, None), ((40, 50), (3, 5), None), ((40, 50), 3, 0.2),
+                                            ((6, 20, 30), (3, 3, 3), None), ((31, 17), (4, 2), None)])
+def test_wiener_matches_scipy(shape, ks, noise):
+    from scipy.signal import wiener as sp_wiener
+
+    rng = np.random.default_rng(sum(shape))
+    t = rng.standard_normal(shape) + 1.0
+    want = sp_wiener(t, ks, noise)
+    got = o.wiener(t, ks if isinstance(ks, tuple) else int(ks), noise)
+    np.testing.assert_allclose(got, want, rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize("shape,axis,order", [((300,), 0, 1), ((300,), 0, 5), ((20, 31), 0, 2), ((20, 31), 1, 1),
+                                              ((4, 9, 11), 1, 2)])
+@pytest.mark.parametrize("cmp", ["less", "greater", "less_equal", "greater_equal"])
+def test_argrelextrema_matches_scipy(shape, axis, order, cmp):
+    from scipy.signal import argrelextrema as sp_arg
+
+    rng = np.random.default_rng(sum(shape) + order)
+    x = rng.integers(-4, 5, size=shape)
+    fn = {"less": np.less, "greater": np.greater, "less_equal": np.less_equal, "greater_equal": np.greater_equal}[cmp]
+    want = np.stack(sp_arg(x, fn, axis=axis, order=order, mode="clip"), axis=-1)
+    idx, valid = o.argrelextrema(x, cmp, axis=axis, order=order)
+    assert valid == want.shape[0]
+    np.testing.assert_array_equal(idx[:valid], want.astype(np.int32))
+
+
+def test_median_equals_a_sliding_numpy_median_inside_the_tensor():
+    """Away from the clamped tail the reference's window [i, i + k) is numpy's sliding window."""
+    rng = np.random.default_rng(2)
+    t = rng.standard_normal((5, 64)).astype(np.float32)
+    k = 7
+    win = np.lib.stride_tricks.sliding_window_view(t, k, axis=1)
+    want = np.median(win.astype(np.float64), axis=-1).astype(np.float32)
+    got = o.median(t, (1, k))
+    np.testing.assert_array_equal(got[:, : 64 - k + 1], want)
+    assert (got[:, 64 - k + 1:] == want[:, -1:]).all()  # clamped starts repeat the last full window
