@@ -143,6 +143,69 @@ static ERL_NIF_TERM stft_to_mel(ErlNifEnv* env, int argc, const ERL_NIF_TERM arg
   return enif_make_tuple2(env, enif_make_atom(env, "ok"), mt);
 }
 
+/* stft_mel(ctx, x_bin, channels, length, window_bin, hop, fft_length, pad_mode, lo, hi, scaling, sr,
+ *          mel_bins, max_mel, f_sp) -- NxSignal.stft/3 |> NxSignal.stft_to_mel/3 in one call
+ * (lib/nx_signal.ex:68-130, 486-513): only the [frames][mel_bins] tensor comes back over PCIe */
+static ERL_NIF_TERM stft_mel(ErlNifEnv* env, int argc, const ERL_NIF_TERM argv[]) {
+  ctx_res* r;
+  ErlNifBinary x, w;
+  ErlNifSInt64 ch, len, hop, nfft, lo, hi, mels;
+  int pad, scal;
+  double sr, max_mel, f_sp;
+  if (argc != 15 || !enif_get_resource(env, argv[0], CTX_TYPE, (void**)&r) ||
+      !enif_inspect_binary(env, argv[1], &x) || !enif_get_int64(env, argv[2], &ch) ||
+      !enif_get_int64(env, argv[3], &len) || !enif_inspect_binary(env, argv[4], &w) ||
+      !enif_get_int64(env, argv[5], &hop) || !enif_get_int64(env, argv[6], &nfft) ||
+      !enif_get_int(env, argv[7], &pad) || !enif_get_int64(env, argv[8], &lo) ||
+      !enif_get_int64(env, argv[9], &hi) || !enif_get_int(env, argv[10], &scal) ||
+      !enif_get_double(env, argv[11], &sr) || !enif_get_int64(env, argv[12], &mels) ||
+      !enif_get_double(env, argv[13], &max_mel) || !enif_get_double(env, argv[14], &f_sp))
+    return enif_make_badarg(env);
+  const ErlNifSInt64 n = (ErlNifSInt64)(w.size / sizeof(float));
+  int64_t frames = 0;
+  int rc = nxs_num_frames(len, n, hop, pad, lo, hi, &frames);
+  if (rc) return mk_error(env, rc);
+  ERL_NIF_TERM mt;
+  float* mel = (float*)enif_make_new_binary(env, (size_t)(ch * frames * mels) * sizeof(float), &mt);
+  rc = nxs_stft_mel_f32_host(r->ctx, (const float*)x.data, ch, len, len, (const float*)w.data, n, hop, nfft, pad, lo,
+                             hi, scal, sr, mels, max_mel, f_sp, mel);
+  if (rc) return mk_error(env, rc);
+  return enif_make_tuple3(env, enif_make_atom(env, "ok"), mt, enif_make_int64(env, frames));
+}
+
+/* median(ctx, t_bin, shape_list, kernel_shape_list) -- NxSignal.Filters.median/2, lib/nx_signal/filters.ex:17-56 */
+static ERL_NIF_TERM median(ErlNifEnv* env, int argc, const ERL_NIF_TERM argv[]) {
+  ctx_res* r;
+  ErlNifBinary t;
+  int64_t shape[3], ks[3];
+  unsigned rank = 0, krank = 0;
+  ERL_NIF_TERM head, tail;
+  if (argc != 4 || !enif_get_resource(env, argv[0], CTX_TYPE, (void**)&r) || !enif_inspect_binary(env, argv[1], &t) ||
+      !enif_get_list_length(env, argv[2], &rank) || !enif_get_list_length(env, argv[3], &krank) || rank > 3)
+    return enif_make_badarg(env);
+  if (rank != krank) return mk_error(env, NXS_ESHAPE); /* "kernel shape must be of the same rank as the tensor" */
+  size_t total = 1;
+  tail = argv[2];
+  for (unsigned i = 0; i < rank; ++i) {
+    ErlNifSInt64 v;
+    if (!enif_get_list_cell(env, tail, &head, &tail) || !enif_get_int64(env, head, &v)) return enif_make_badarg(env);
+    shape[i] = v;
+    total *= (size_t)v;
+  }
+  tail = argv[3];
+  for (unsigned i = 0; i < rank; ++i) {
+    ErlNifSInt64 v;
+    if (!enif_get_list_cell(env, tail, &head, &tail) || !enif_get_int64(env, head, &v)) return enif_make_badarg(env);
+    ks[i] = v;
+  }
+  if (t.size < total * sizeof(float)) return enif_make_badarg(env);
+  ERL_NIF_TERM ot;
+  float* out = (float*)enif_make_new_binary(env, total * sizeof(float), &ot);
+  int rc = nxs_median_f32_host(r->ctx, (const float*)t.data, (int)rank, shape, ks, out);
+  if (rc) return mk_error(env, rc);
+  return enif_make_tuple2(env, enif_make_atom(env, "ok"), ot);
+}
+
 /* window(kind, n, periodic, beta, eps) -- host-side, bit-compatible with Nx.BinaryBackend */
 static ERL_NIF_TERM window(ErlNifEnv* env, int argc, const ERL_NIF_TERM argv[]) {
   int kind, periodic;
@@ -171,6 +234,8 @@ static ErlNifFunc funcs[] = {
     {"istft", 10, istft, ERL_NIF_DIRTY_JOB_IO_BOUND},
     {"fir", 6, fir, ERL_NIF_DIRTY_JOB_IO_BOUND},
     {"stft_to_mel", 10, stft_to_mel, ERL_NIF_DIRTY_JOB_IO_BOUND},
+    {"stft_mel", 15, stft_mel, ERL_NIF_DIRTY_JOB_IO_BOUND},
+    {"median", 4, median, ERL_NIF_DIRTY_JOB_IO_BOUND},
     {"window", 5, window, 0},
 };
 

@@ -9,6 +9,10 @@ defmodule NxSignalB200.NIF do
   def istft(_c, _z, _ch, _frames, _zlen, _w, _hop, _nfft, _scal, _sr), do: :erlang.nif_error(:not_loaded)
   def fir(_c, _x, _ch, _len, _h, _mode), do: :erlang.nif_error(:not_loaded)
   def stft_to_mel(_c, _z, _ch, _frames, _zlen, _nfft, _mels, _sr, _max_mel, _f_sp), do: :erlang.nif_error(:not_loaded)
+  def stft_mel(_c, _x, _ch, _len, _w, _hop, _nfft, _pad, _lo, _hi, _scal, _sr, _mels, _max_mel, _f_sp),
+    do: :erlang.nif_error(:not_loaded)
+
+  def median(_c, _t, _shape, _kernel_shape), do: :erlang.nif_error(:not_loaded)
   def window(_kind, _n, _periodic, _beta, _eps), do: :erlang.nif_error(:not_loaded)
 end
 
@@ -180,6 +184,61 @@ defmodule NxSignalB200 do
 
       err ->
         raise_nif(err)
+    end
+  end
+  @doc """
+  `NxSignal.stft/3 |> NxSignal.stft_to_mel/3` in one device call (the spectrum is never stored and only
+  the `{frames, mel}` tensor crosses PCIe).  Options: those of `stft/3` plus `:mel_bins`, `:max_mel`,
+  `:mel_frequency_spacing`; `:window_padding` is `:valid | :same | :reflect` here.
+  """
+  def stft_mel(data, window, opts \\ []) do
+    {frame_length} = Nx.shape(window)
+
+    opts =
+      Keyword.validate!(opts, [
+        :overlap_length,
+        :scaling,
+        :max_mel,
+        :mel_frequency_spacing,
+        window_padding: :valid,
+        sampling_rate: 100,
+        fft_length: :power_of_two,
+        mel_bins: 128
+      ])
+
+    overlap = opts[:overlap_length] || div(frame_length, 2)
+    nfft = if opts[:fft_length] == :power_of_two, do: next_pow2(frame_length), else: opts[:fft_length]
+    vec_axes = data.vectorized_axes
+    x = Nx.devectorize(data)
+    len = Nx.axis_size(x, -1)
+    ch = div(Nx.size(x), len)
+
+    case NxSignalB200.NIF.stft_mel(ctx(), Nx.to_binary(Nx.as_type(x, :f32)), ch, len,
+           Nx.to_binary(Nx.as_type(window, :f32)), frame_length - overlap, nfft, @pad[opts[:window_padding]], 0, 0,
+           @scaling[opts[:scaling]], opts[:sampling_rate] * 1.0, opts[:mel_bins], (opts[:max_mel] || 3016) * 1.0,
+           (opts[:mel_frequency_spacing] || 200 / 3) * 1.0) do
+      {:ok, mel, frames} ->
+        shape = x |> Nx.shape() |> Tuple.to_list() |> Enum.drop(-1) |> Kernel.++([frames, opts[:mel_bins]]) |> List.to_tuple()
+        mel |> Nx.from_binary(:f32) |> Nx.reshape(shape) |> Nx.vectorize(vec_axes) |> Nx.rename([:frames, :mel])
+
+      err ->
+        raise_nif(err)
+    end
+  end
+
+  defp next_pow2(n), do: Bitwise.bsl(1, ceil(:math.log2(n)))
+
+  @doc "`NxSignal.Filters.median/2` (lib/nx_signal/filters.ex:17-56) for tensors of rank <= 3."
+  def median(t, opts) do
+    opts = Keyword.validate!(opts, [:kernel_shape])
+
+    if Nx.rank(t) != tuple_size(opts[:kernel_shape]),
+      do: raise(ArgumentError, "kernel shape must be of the same rank as the tensor")
+
+    case NxSignalB200.NIF.median(ctx(), Nx.to_binary(Nx.as_type(t, :f32)), Tuple.to_list(Nx.shape(t)),
+           Tuple.to_list(opts[:kernel_shape])) do
+      {:ok, out} -> out |> Nx.from_binary(:f32) |> Nx.reshape(Nx.shape(t))
+      err -> raise_nif(err)
     end
   end
 end
