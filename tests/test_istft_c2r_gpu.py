@@ -153,3 +153,18 @@ def test_argument_errors():
     z = np.zeros((1, 4, 512), dtype=np.complex64)  # one bin short
     with pytest.raises(nx.NxSignalArgumentError):
         nx.istft(z, w, onesided=True, overlap_length=768, fft_length=1024)
+
+
+@pytest.mark.parametrize("M", [1, 2, 3, 5, 9])
+@pytest.mark.parametrize("nfft,hopdiv", [(1024, 4), (512, 2), (2048, 8)])
+def test_very_few_frames(nfft, hopdiv, M):
+    """Fewer frames than cover an interior sample: every output is an edge sample (exact normaliser path)."""
+    rng = np.random.default_rng(100 * M + hopdiv)
+    hop = nfft // hopdiv
+    z, _ = onesided_random(rng, (2, M), nfft)
+    w = o.hamming(nfft)
+    kw = dict(overlap_length=nfft - hop, fft_length=nfft)
+    y = nx.istft(z, w, onesided=True, **kw)
+    yo = o.istft_fast(ext(z, nfft), w, **kw)
+    assert y.shape == yo.shape == (2, M * hop + nfft - hop)
+    assert rel(y, yo.real) <= TOL

@@ -293,3 +293,18 @@ def test_ring_many_segments_matches_gather_kernel(monkeypatch):
     yo = o.istft_fast(z[1, m0:m1].cpu().numpy(), o.hann(nfft), **kw)
     lo, hi = nfft, (m1 - m0) * hop - nfft
     assert np.abs(a[1, m0 * hop + lo: m0 * hop + hi] - yo[lo:hi]).max() / np.abs(yo).max() <= TOL
+
+
+@pytest.mark.parametrize("M", [1, 2, 3, 5, 9])
+@pytest.mark.parametrize("nfft,hopdiv", [(1024, 4), (512, 2), (2048, 8), (4096, 4), (256, 4)])
+def test_register_overlap_add_with_very_few_frames(nfft, hopdiv, M):
+    """Fewer frames than cover an interior sample: every output is an edge sample (exact normaliser path)."""
+    rng = np.random.default_rng(100 * M + hopdiv + nfft)
+    hop = nfft // hopdiv
+    z = (rng.standard_normal((2, M, nfft)) + 1j * rng.standard_normal((2, M, nfft))).astype(np.complex64)
+    w = o.hamming(nfft)
+    kw = dict(overlap_length=nfft - hop, fft_length=nfft)
+    y = nx.istft(z, w, **kw)
+    yo = o.istft_fast(z, w, **kw)
+    assert y.shape == yo.shape == (2, M * hop + nfft - hop)
+    assert rel(y, yo) <= TOL
