@@ -46,6 +46,34 @@ __global__ void __launch_bounds__(256) as_windowed_kernel32(const E* __restrict_
   }
 }
 
+// f32 frames whose every group of 4 samples is 16-byte aligned in both tensors (N, stride, lo, x_ld
+// multiples of 4): one 128-bit load and store per thread; groups that touch the padding fall back to
+// the per-sample rule
+__global__ void __launch_bounds__(256) as_windowed_kernel_v4(const float* __restrict__ x, int L, int64_t x_ld, int N4,
+                                                             int stride, int lo, int reflect, int M,
+                                                             const FastDiv div_n4, const FastDiv div_m, int total4,
+                                                             float4* __restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += gridDim.x * blockDim.x) {
+    const int fm = div_n4.div(i), n = (i - fm * N4) * 4;
+    const int c = div_m.div(fm), m = fm - c * M;
+    const int64_t src = (int64_t)m * stride + n - lo;
+    const float* __restrict__ row = x + c * x_ld;
+    float4 v;
+    if (src >= 0 && src + 3 < L) {
+      v = *reinterpret_cast<const float4*>(row + src);
+    } else {
+      float e[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int64_t sk = src + k;
+        e[k] = (sk >= 0 && sk < L) ? row[sk] : (reflect ? row[reflect_index(sk, L)] : 0.f);
+      }
+      v = make_float4(e[0], e[1], e[2], e[3]);
+    }
+    out[i] = v;
+  }
+}
+
 int launch_as_windowed(nxs_ctx* ctx, const void* x, int elem_size, int64_t channels, int64_t length,
                        int64_t x_ld, int64_t window_length, int64_t stride, const PadGeom& g,
                        int64_t num_frames, void* out, cudaStream_t st) {
@@ -56,7 +84,17 @@ int launch_as_windowed(nxs_ctx* ctx, const void* x, int elem_size, int64_t chann
   if (grid > cap) grid = cap;
   const bool small = total < (int64_t(1) << 31) - (int64_t(1) << 24) && length < (int64_t(1) << 31) &&
                      stride < (int64_t(1) << 31) && g.lo < (int64_t(1) << 31);
-  if (small && elem_size == 4)
+  const bool vec4 = small && elem_size == 4 && window_length % 4 == 0 && stride % 4 == 0 && g.lo % 4 == 0 &&
+                    x_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  if (vec4) {
+    const int64_t total4 = total / 4;
+    int64_t g4 = (total4 + 255) / 256;
+    if (g4 > cap) g4 = cap;
+    as_windowed_kernel_v4<<<(unsigned)g4, 256, 0, st>>>((const float*)x, (int)length, x_ld, (int)(window_length / 4),
+                                                        (int)stride, (int)g.lo, g.reflect, (int)num_frames,
+                                                        FastDiv((int)(window_length / 4)), FastDiv((int)num_frames),
+                                                        (int)total4, (float4*)out);
+  } else if (small && elem_size == 4)
     as_windowed_kernel32<float><<<(unsigned)grid, 256, 0, st>>>(
         (const float*)x, (int)length, x_ld, (int)window_length, (int)stride, (int)g.lo, g.reflect, (int)num_frames,
         FastDiv((int)window_length), FastDiv((int)num_frames), (int)total, (float*)out);

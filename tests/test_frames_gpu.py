@@ -64,3 +64,14 @@ def test_device_tensors():
     np.testing.assert_array_equal(fr.cpu().numpy(), o.as_windowed(x.cpu().numpy(), 8, 3))
     y = nx.overlap_and_add(fr, overlap_length=5)
     np.testing.assert_allclose(y.cpu().numpy(), o.overlap_and_add(fr.cpu().numpy(), 5), rtol=1e-6)
+
+
+@pytest.mark.parametrize("padding", ["valid", "reflect", [(8, 12)], [(3, 5)], "same"])
+@pytest.mark.parametrize("N,stride,L", [(64, 16, 1000), (64, 16, 1003), (8, 4, 64), (1024, 256, 9000), (64, 12, 1000)])
+def test_as_windowed_vector_path_and_its_fallbacks(padding, N, stride, L):
+    """f32 with N, stride, lo and the row length multiples of 4 takes the 128-bit kernel (padding groups
+    handled per sample); anything else the scalar kernel -- same result either way."""
+    rng = np.random.default_rng(N + stride + L)
+    x = rng.standard_normal((3, L)).astype(np.float32)
+    got = nx.as_windowed(x, window_length=N, stride=stride, padding=padding)
+    np.testing.assert_array_equal(got, o.as_windowed(x, N, stride, padding))
