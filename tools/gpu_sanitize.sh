@@ -58,6 +58,21 @@ for axis, order in [(0, 1), (1, 3)]:
     idx, valid = o.argrelmax(ti, axis=axis, order=order)
     assert int(r["valid_indices"].cpu()) == valid and np.array_equal(r["indices"].cpu().numpy(), idx)
 print("argrel OK")
+# standalone framing ops (32-bit / 128-bit kernels) and the log-mel host entry's chunk pipeline
+xf = rng.standard_normal((3, 4000)).astype(np.float32)
+for N, st_, pad in [(64, 16, "valid"), (64, 16, "reflect"), (64, 12, "same"), (8, 4, [(8, 12)])]:
+    assert np.array_equal(nx.as_windowed(torch.from_numpy(xf).cuda(), window_length=N, stride=st_, padding=pad).cpu().numpy(), o.as_windowed(xf, N, st_, pad))
+tf = rng.standard_normal((2, 50, 128)).astype(np.float32)
+for ov in (0, 64, 96, 127):
+    chk(f"overlap_and_add {ov}", nx.overlap_and_add(torch.from_numpy(tf).cuda(), overlap_length=ov), o.overlap_and_add(tf, ov))
+tc = (tf + 1j * rng.standard_normal(tf.shape)).astype(np.complex64)
+chk("overlap_and_add c64", torch.view_as_real(nx.overlap_and_add(torch.from_numpy(tc).cuda(), overlap_length=96)), np.stack([o.overlap_and_add(tc, 96).real, o.overlap_and_add(tc, 96).imag], -1))
+print("framing OK")
+xm = rng.standard_normal((11, 20 * 1024)).astype(np.float32); wm = o.hann(1024)
+kwm = dict(overlap_length=768, fft_length=1024, sampling_rate=16000)
+mh = nx.stft_mel(xm, wm, mel_bins=80, **kwm)
+zo, _, _ = o.stft_fast(xm, wm, **kwm)
+chk("stft_mel host entry (11 channels -> 8 chunks)", mh, np.stack([o.stft_to_mel(zo[c], 16000, 1024, 80) for c in range(11)]))
 torch.cuda.synchronize(); print("all cases done")
 PY
 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 1 python /tmp/san_cases.py > $OUT/memcheck.log 2>&1; echo "memcheck rc=$?" | tee -a $OUT/memcheck.log; grep -c "OK" $OUT/memcheck.log; grep -E "ERROR SUMMARY|Invalid|FAIL" $OUT/memcheck.log | head -5
