@@ -278,7 +278,20 @@ struct SyncWarp {
 // ---------------------------------------------------------------------------------------
 // SINGLE: buf0 == buf1 (one exchange buffer): a barrier separates a pass's reads from its
 // writes, at the price of one more sync per middle pass.
-template <class PL, int PASS, class TW, class SYNC, bool SINGLE = false>
+// PAIRED: the LAST pass assigns butterflies to threads in conjugate pairs (paired_bfly): slot
+// b < B/2 takes butterfly j = t + b*T and slot b + B/2 the butterfly J - j that holds X[N - k] for
+// every X[k] of the first, so a real-FFT split pass (or any k <-> N-k combination) needs no
+// further exchange -- one shared-memory round trip less per transform.
+template <class PL>
+__device__ __forceinline__ int paired_bfly(int t, int b) {
+  constexpr int RL = PL::R(PL::NP - 1), J = PL::N / RL, B = PL::P / RL;
+  static_assert(B >= 2 && B % 2 == 0, "PAIRED needs an even number of last-pass butterflies per thread");
+  if (b < B / 2) return t + b * PL::T;
+  const int j = t + (b - B / 2) * PL::T;
+  return j == 0 ? J / 2 : J - j;  // butterflies 0 and J/2 are their own partners: thread 0 takes both
+}
+
+template <class PL, int PASS, class TW, class SYNC, bool SINGLE = false, bool PAIRED = false>
 struct PassRunner {
   static __device__ __forceinline__ void run(cpx (&v)[PL::P], int t, cpx* buf0, cpx* buf1,
                                              const TW& tw, const SYNC& sync) {
@@ -291,19 +304,25 @@ struct PassRunner {
       constexpr int unit = (A < 0) ? 1 : (1 << (A < 0 ? 0 : A));
       // pad(t + X) splits into pad(t) + pad(X) when every X is a multiple of 2^A
       constexpr bool split = (A < 0) || (T % unit == 0 && (N / R) % unit == 0);
+      constexpr bool LASTP = PAIRED && PASS + 1 == PL::NP;
       const int tb = pad_idx<A, C>(t);
 #pragma unroll
-      for (int b = 0; b < B; ++b)
+      for (int b = 0; b < B; ++b) {
+        int jb = 0;
+        if constexpr (LASTP) jb = paired_bfly<PL>(t, b);
 #pragma unroll
         for (int q = 0; q < R; ++q) {
           const int X = b * T + q * (N / R);
-          if constexpr (split) v[b * R + q] = in[tb + pad_idx<A, C>(X)];
+          if constexpr (LASTP) v[b * R + q] = in[pad_idx<A, C>(jb + q * (N / R))];
+          else if constexpr (split) v[b * R + q] = in[tb + pad_idx<A, C>(X)];
           else v[b * R + q] = in[pad_idx<A, C>(t + X)];
         }
+      }
       if constexpr (SINGLE && PASS + 1 < PL::NP) sync();  // reads done before this pass overwrites the buffer
 #pragma unroll
       for (int b = 0; b < B; ++b) {
-        const int k = (t + b * T) % NS;
+        int k = (t + b * T) % NS;
+        if constexpr (LASTP) k = paired_bfly<PL>(t, b) % NS;
         cpx w[R];
         tw.template fill<PASS>(b, k, w);
 #pragma unroll
@@ -326,7 +345,7 @@ struct PassRunner {
         for (int q = 0; q < R; ++q) out[base + q * NS] = v[b * R + bitrev(q, ilog2(R))];
       }
       sync();
-      PassRunner<PL, PASS + 1, TW, SYNC, SINGLE>::run(v, t, buf0, buf1, tw, sync);
+      PassRunner<PL, PASS + 1, TW, SYNC, SINGLE, PAIRED>::run(v, t, buf0, buf1, tw, sync);
     }
   }
 };
@@ -340,9 +359,15 @@ __device__ __forceinline__ void block_fft(cpx (&v)[PL::P], int t, cpx* buf0, cpx
   PassRunner<PL, 0, TW, SYNC>::run(v, t, buf0, buf1, tw, sync);
 }
 // one exchange buffer of PL::BUF complex (see PassRunner's SINGLE)
-template <class PL, class TW, class SYNC>
+template <class PL, class TW, class SYNC, bool PAIRED = false>
 __device__ __forceinline__ void block_fft_single(cpx (&v)[PL::P], int t, cpx* buf, const TW& tw, const SYNC& sync) {
-  PassRunner<PL, 0, TW, SYNC, true>::run(v, t, buf, buf, tw, sync);
+  PassRunner<PL, 0, TW, SYNC, true, PAIRED>::run(v, t, buf, buf, tw, sync);
+}
+// two exchange buffers, conjugate-paired last pass (see PassRunner's PAIRED)
+template <class PL, class TW, class SYNC>
+__device__ __forceinline__ void block_fft_paired(cpx (&v)[PL::P], int t, cpx* buf0, cpx* buf1, const TW& tw,
+                                                 const SYNC& sync) {
+  PassRunner<PL, 0, TW, SYNC, false, true>::run(v, t, buf0, buf1, tw, sync);
 }
 
 // logical index of the element the caller must preload into v[b*R0 + q]

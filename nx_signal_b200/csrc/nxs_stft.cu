@@ -211,13 +211,17 @@ __global__ void __launch_bounds__(THREADS) stft_r2c_kernel(const StftArgs a) {
 // whole FFT; halves the shared memory of the large plans (2 CTAs/SM instead of 1) for one
 // extra group barrier per middle pass.
 // WINREG: the thread's P window values (constant across frames) live in registers.
+// PAIRED: conjugate-paired last pass (nxs_fft.cuh): thread t ends up holding Z[k] and Z[N - k] for each
+// of its bins, so the split pass runs out of registers -- no exchange, and no misaligned descending
+// shared-memory reads (ncu: they were 10 % excess wavefronts on the nfft = 4096 plan).
 template <class PL_, int THREADS_, int HOPDIV_, bool TWREG_, bool PERGROUP_ = false, bool LEAN_ = false,
-          bool WINREG_ = false>
+          bool WINREG_ = false, bool PAIRED_ = false>
 struct StagedCfg {
   using PL = PL_;
   static constexpr int THREADS = THREADS_, HOPDIV = HOPDIV_;
-  static constexpr bool TWREG = TWREG_, PERGROUP = PERGROUP_, LEAN = LEAN_, WINREG = WINREG_;
+  static constexpr bool TWREG = TWREG_, PERGROUP = PERGROUP_, LEAN = LEAN_, WINREG = WINREG_, PAIRED = PAIRED_;
   static_assert(!LEAN || PERGROUP, "LEAN needs per-group staging");
+  static_assert(!PAIRED || !TWREG, "the paired last pass reads its twiddles from the table");
   static constexpr int G = THREADS / PL::T, NFFT = 2 * PL::N;
   static constexpr int NSTAGE = LEAN ? 1 : 2, NXBUF = LEAN ? 1 : 2;
   // floats per stage: one tile span, or G private frames
@@ -276,9 +280,48 @@ __global__ void __launch_bounds__(CF::THREADS, MINB) stft_r2c_staged_kernel(cons
   TW tw;
   if constexpr (CF::TWREG) tw.init(a.tw, t);
   else tw.init(reinterpret_cast<const cpx*>(smem_raw + CF::TW_OFF), t);
+  constexpr int JL = N / RL;  // butterflies of the last pass
+  // split-pass twiddles of this thread's P / 2 bin pairs: bins t + i T, or (PAIRED) slot b's bins j_b + q JL
   cpx wpost[P / 2];
 #pragma unroll
-  for (int i = 0; i < P / 2; ++i) wpost[i] = __ldg(a.post + t + i * T);
+  for (int i = 0; i < P / 2; ++i) {
+    if constexpr (CF::PAIRED) wpost[i] = __ldg(a.post + t + (i / RL) * T + (i % RL) * JL);
+    else wpost[i] = __ldg(a.post + t + i * T);
+  }
+  // the pair (Z[kk], conj Z[N - kk]) number i of this thread, its twiddle and (kk == 0 only) Z[N / 2]
+  auto load_pair = [&](const cpx (&v)[P], const cpx* pb, int i, int& kk, cpx& A, cpx& Bc, cpx& w, cpx& Zh) {
+    if constexpr (CF::PAIRED) {
+      constexpr int LB = ilog2(RL);
+      const int b = i / RL, q = i % RL;
+      if (b == 0 && t == 0) {
+        // thread 0, slot 0: butterflies 0 (bins q JL, partner R - q) and JL / 2 (partner R - 1 - q) pair with themselves
+        if (q < RL / 2) {
+          kk = q * JL;
+          A = v[bitrev(q, LB)];
+          Bc = cconj(v[bitrev((RL - q) % RL, LB)]);
+          w = wpost[i];
+          Zh = v[bitrev(RL / 2, LB)];
+        } else {
+          const int q2 = q - RL / 2;
+          kk = JL / 2 + q2 * JL;
+          A = v[(BL / 2) * RL + bitrev(q2, LB)];
+          Bc = cconj(v[(BL / 2) * RL + bitrev(RL - 1 - q2, LB)]);
+          w = __ldg(a.post + kk);
+        }
+      } else {
+        kk = t + b * T + q * JL;
+        A = v[b * RL + bitrev(q, LB)];
+        Bc = cconj(v[(b + BL / 2) * RL + bitrev(RL - 1 - q, LB)]);
+        w = wpost[i];
+      }
+    } else {
+      kk = t + i * T;
+      A = pb[kk];
+      Bc = cconj(pb[(N - kk) & (N - 1)]);
+      w = wpost[i];
+      if (kk == 0) Zh = pb[N / 2];
+    }
+  };
   const GroupSync<T> sync{1 + g};
   const int hop = (int)a.hop;
   float2 wreg[CF::WINREG ? P : 1];
@@ -416,47 +459,50 @@ __global__ void __launch_bounds__(CF::THREADS, MINB) stft_r2c_staged_kernel(cons
       // exchange buffer): refill the stage with the next frame while this one is transformed
       sync();
       if (issuer && tile + (int)gridDim.x < total_tiles) issue(cn, rn, 0);
-      block_fft_single<PL>(v, t, bufA, tw, sync);
-      sync();  // last pass's reads done before the post-pass reuses the buffer
+      block_fft_single<PL, TW, GroupSync<T>, CF::PAIRED>(v, t, bufA, tw, sync);
+      if constexpr (!CF::PAIRED) sync();  // last pass's reads done before the post-pass reuses the buffer
+    } else if constexpr (CF::PAIRED) {
+      block_fft_paired<PL>(v, t, bufA, bufB, tw, sync);
     } else {
       block_fft<PL>(v, t, bufA, bufB, tw, sync);
     }
 
     cpx* pb = ((PL::NP - 1) & 1) ? bufB : bufA;
+    if constexpr (!CF::PAIRED) {
 #pragma unroll
-    for (int b = 0; b < BL; ++b)
+      for (int b = 0; b < BL; ++b)
 #pragma unroll
-      for (int q = 0; q < RL; ++q) pb[fft_out_index<PL>(t, b, q)] = v[fft_out_reg<PL>(b, q)];
-    sync();
+        for (int q = 0; q < RL; ++q) pb[fft_out_index<PL>(t, b, q)] = v[fft_out_reg<PL>(b, q)];
+      sync();
+    }
     if constexpr (MODE == kMel) {
       // power of bins 0 .. N-1 (the lower half-spectrum, lib/nx_signal.ex:496) -> shared memory in bin order
       float p0[P / 2], p1[P / 2], ph = 0.f;
+      int kks[P / 2];
       if (active) {
 #pragma unroll
         for (int i = 0; i < P / 2; ++i) {
-          const int kk = t + i * T;
-          const cpx A = pb[kk];
-          const cpx Bc = cconj(pb[(N - kk) & (N - 1)]);
+          int kk;
+          cpx A, Bc, w, Zh = make_float2(0.f, 0.f);
+          load_pair(v, pb, i, kk, A, Bc, w, Zh);
+          kks[i] = kk;
           const cpx E = cadd(A, Bc), O = csub(A, Bc);
-          const cpx Tm = cmul(wpost[i], O);
+          const cpx Tm = cmul(w, O);
           const cpx X0 = cadd(E, Tm), X1 = csub(E, Tm);
           p0[i] = X0.x * X0.x + X0.y * X0.y;  // bin kk
           p1[i] = X1.x * X1.x + X1.y * X1.y;  // bin N - kk (|conj| = |.|)
-          if (kk == 0) {
-            const cpx Zh = pb[N / 2];
-            ph = 4.f * (Zh.x * Zh.x + Zh.y * Zh.y);  // bin N / 2
-          }
+          if (kk == 0) ph = 4.f * (Zh.x * Zh.x + Zh.y * Zh.y);  // bin N / 2
         }
       }
       // the power spectrum goes to the exchange buffer the last pass did not use (its reads ended
-      // before the barrier above), so no barrier is needed here; with a single buffer (LEAN) every
-      // read of it must finish first
-      if constexpr (CF::LEAN) sync();
+      // before the barrier above), so no barrier is needed here; with a single buffer (LEAN) or
+      // without the split pass's barrier (PAIRED) every read of it must finish first
+      if constexpr (CF::LEAN || CF::PAIRED) sync();
       float* pw = reinterpret_cast<float*>(CF::LEAN ? pb : (pb == bufA ? bufB : bufA));
       if (active) {
 #pragma unroll
         for (int i = 0; i < P / 2; ++i) {
-          const int kk = t + i * T;
+          const int kk = kks[i];
           pw[kk] = p0[i];
           if (kk > 0) pw[N - kk] = p1[i];
           else pw[N / 2] = ph;
@@ -527,11 +573,11 @@ __global__ void __launch_bounds__(CF::THREADS, MINB) stft_r2c_staged_kernel(cons
       float2* __restrict__ zf = a.z + f * (ONESIDED ? a.z_ld : (int64_t)NFFT);
 #pragma unroll
       for (int i = 0; i < P / 2; ++i) {
-        const int kk = t + i * T;
-        const cpx A = pb[kk];
-        const cpx Bc = cconj(pb[(N - kk) & (N - 1)]);
+        int kk;
+        cpx A, Bc, w, Zh = make_float2(0.f, 0.f);
+        load_pair(v, pb, i, kk, A, Bc, w, Zh);
         const cpx E = cadd(A, Bc), O = csub(A, Bc);
-        const cpx Tm = cmul(wpost[i], O);
+        const cpx Tm = cmul(w, O);
         const cpx X0 = cadd(E, Tm), X1 = csub(E, Tm);
         __stcs(zf + kk, X0);
         if (!ONESIDED || kk == 0) __stcs(zf + N + kk, X1);
@@ -539,7 +585,6 @@ __global__ void __launch_bounds__(CF::THREADS, MINB) stft_r2c_staged_kernel(cons
           __stcs(zf + N - kk, cconj(X1));
           if constexpr (!ONESIDED) __stcs(zf + NFFT - kk, cconj(X0));
         } else {
-          const cpx Zh = pb[N / 2];
           __stcs(zf + N / 2, make_float2(2.f * Zh.x, -2.f * Zh.y));
           if constexpr (!ONESIDED) __stcs(zf + N + N / 2, make_float2(2.f * Zh.x, 2.f * Zh.y));
         }
@@ -615,8 +660,8 @@ static int get_tables(nxs_ctx* ctx, PlanTables* out) {
         tw[PL::twOffset(p) + (q - 1) * NS + k] = make_float2((float)cos(ang), (float)sin(ang));
       }
   }
-  std::vector<float2> post(PL::N / 2 + 1);
-  for (int k = 0; k <= PL::N / 2; ++k) {
+  std::vector<float2> post(PL::N + 1);  // the paired split pass indexes bins up to N - 1
+  for (int k = 0; k <= PL::N; ++k) {
     const double th = M_PI * double(k) / double(PL::N);
     post[k] = make_float2((float)(-sin(th)), (float)(-cos(th)));
   }
@@ -825,7 +870,8 @@ int launch_stft(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, 
         using PL = Plan<1024, 64, 16, 8, 8>;
         if (variant_env() == 1) { using CF = StagedCfg<PL, 512, 2, false, false>; NXS_TRY_STAGED(CF, 1); }
         if (variant_env() == 2) { using CF = StagedCfg<PL, 256, 2, false, true>; NXS_TRY_STAGED(CF, 2); }
-        { using CF = StagedCfg<PL, 256, 2, false, true, true>; NXS_TRY_STAGED(CF, 2); }
+        if (variant_env() == 3) { using CF = StagedCfg<PL, 256, 2, false, true, true>; NXS_TRY_STAGED(CF, 2); }
+        { using CF = StagedCfg<PL, 256, 2, false, true, true, false, true>; NXS_TRY_STAGED(CF, 2); }
         return run_r2c<PL, TwTable<PL>, 512>(ctx, a, st);
       }
       case 4096: {
@@ -833,7 +879,8 @@ int launch_stft(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, 
         if (variant_env() == 1) { using CF = StagedCfg<PL, 512, 4, false, false>; NXS_TRY_STAGED(CF, 1); }
         if (variant_env() == 2) { using CF = StagedCfg<PL, 256, 4, false, true>; NXS_TRY_STAGED(CF, 1); }
         if (variant_env() == 3) { using CF = StagedCfg<PL, 512, 4, false, true, true>; NXS_TRY_STAGED(CF, 1); }
-        { using CF = StagedCfg<PL, 256, 4, false, true, true>; NXS_TRY_STAGED(CF, 2); }
+        if (variant_env() == 4) { using CF = StagedCfg<PL, 256, 4, false, true, true>; NXS_TRY_STAGED(CF, 2); }
+        { using CF = StagedCfg<PL, 256, 4, false, true, true, false, true>; NXS_TRY_STAGED(CF, 2); }
         return run_r2c<PL, TwTable<PL>, 512>(ctx, a, st);
       }
       case 8192: {
