@@ -22,6 +22,12 @@
  *     caller pointer past return (_host) / past stream completion (_dev).
  *   - one nxs_ctx is single-threaded; distinct contexts may be used from
  *     distinct threads concurrently.
+ *   - a context may be used from several CUDA streams in turn: its internal
+ *     device state (prepared window, scratch) is ordered behind the previous
+ *     call with an event, so a call on stream B issued after a call on stream A
+ *     starts after A's call on the device (the host never blocks).  Two calls
+ *     on one context therefore never overlap on the device; use one context
+ *     per stream for concurrency.
  */
 #ifndef NXSIGNAL_B200_H
 #define NXSIGNAL_B200_H
@@ -89,6 +95,18 @@ int nxs_ctx_profile_read(nxs_ctx* ctx, double* total_ms, int64_t* launches);
  * [0] all copies/kernels enqueued, [1] first result slab in host memory, [2] last slab in host
  * memory, [3] host mirror threads done (= result complete).  bench.py reports them. */
 int nxs_ctx_host_timeline(const nxs_ctx* ctx, double out_seconds[4]);
+
+/* nxs_stft_f32_host moves the result in one of three ways, reported by nxs_ctx_host_mode for the
+ * last call: 0 = both spectrum halves over PCIe; 1 = bins 0 .. fft_length/2 over PCIe straight into
+ * the caller's rows, host threads write the conjugate-mirror bins; 2 = the result buffer is pageable
+ * (not cudaHostRegister'ed -- e.g. a BEAM binary): the lower half lands in the context's pinned ring
+ * and host threads copy it out and write the mirror half in one pass.  +16: the input was pageable
+ * and went through the pinned input ring.  For pinned results the context measures the cost of
+ * modes 0 and 1 on its own calls and uses the cheaper one (which one depends on whether the box is
+ * short of PCIe or of host memory bandwidth); nxs_ctx_set_host_mode pins it: -1 auto (default),
+ * 0 or 1.  All modes give bit-identical results. */
+int nxs_ctx_set_host_mode(nxs_ctx* ctx, int mode);
+int nxs_ctx_host_mode(const nxs_ctx* ctx, int* mode);
 
 /* ---- host-side closed forms (O(n); no GPU needed) ----------------------- */
 /* NxSignal.Windows.{rectangular,bartlett,triangular,blackman,hamming,hann,kaiser}(n, opts)

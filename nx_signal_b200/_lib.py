@@ -39,6 +39,8 @@ SIGNATURES = {
     "nxs_ctx_profile": (i32, [vp, i32]),
     "nxs_ctx_profile_read": (i32, [vp, C.POINTER(f64), C.POINTER(i64)]),
     "nxs_ctx_host_timeline": (i32, [vp, C.POINTER(f64 * 4)]),
+    "nxs_ctx_set_host_mode": (i32, [vp, i32]),
+    "nxs_ctx_host_mode": (i32, [vp, C.POINTER(i32)]),
     "nxs_window_f32": (i32, [i32, i64, i32, f64, f64, vp]),
     "nxs_firwin_f32": (i32, [i64, C.POINTER(f64), i32, i32, f64, i32, i32, f64, vp]),
     "nxs_fft_frequencies_f32": (i32, [f64, i64, vp]),
@@ -160,3 +162,19 @@ def host_timeline(device=0):
     t = (f64 * 4)()
     check(lib().nxs_ctx_host_timeline(context(device), C.byref(t)))
     return [float(v) for v in t]
+
+
+HOST_MODES = {0: "full_d2h", 1: "onesided_d2h+host_mirror", 2: "onesided_d2h+pinned_ring_unstage"}
+
+
+def host_mode(device=0):
+    """How the last nxs_stft_f32_host call moved its result (see nxs_ctx_host_mode) and whether the
+    input went through the pinned input ring."""
+    m = i32()
+    check(lib().nxs_ctx_host_mode(context(device), C.byref(m)))
+    return {"result": HOST_MODES.get(m.value & 15, str(m.value & 15)), "input_staged": bool(m.value & 16)}
+
+
+def set_host_mode(mode, device=0):
+    """-1: the context picks the cheaper mode from its own measurements (default); 0 / 1: pin it."""
+    check(lib().nxs_ctx_set_host_mode(context(device), int(mode)))

@@ -8,7 +8,7 @@
 #include <atomic>
 #include <chrono>
 
-#include "nxs_common.cuh"
+#include "nxs_hostio.cuh"
 
 namespace nxs {
 
@@ -20,7 +20,7 @@ int set_cuda_error(nxs_ctx* ctx, cudaError_t e, const char* where) {
   return e == cudaErrorMemoryAllocation ? NXS_ENOMEM : NXS_ECUDA;
 }
 
-static int grow(nxs_ctx* ctx, void** p, size_t* have, size_t need, bool host) {
+int grow_buf(nxs_ctx* ctx, void** p, size_t* have, size_t need, bool host) {
   if (*have >= need) return NXS_OK;
   if (*p) {
     if (host) cudaFreeHost(*p);
@@ -58,13 +58,13 @@ void prof_end(nxs_ctx* ctx, cudaStream_t st) {
 
 int ensure_coef(nxs_ctx* ctx, size_t bytes) {
   void* p = ctx->d_coef;
-  int rc = grow(ctx, &p, &ctx->d_coef_bytes, bytes < 4096 ? 4096 : bytes, false);
+  int rc = grow_buf(ctx, &p, &ctx->d_coef_bytes, bytes < 4096 ? 4096 : bytes, false);
   ctx->d_coef = (float*)p;
   return rc;
 }
 
 int ensure_scratch(nxs_ctx* ctx, size_t bytes) {
-  return grow(ctx, &ctx->d_scratch, &ctx->d_scratch_bytes, bytes, false);
+  return grow_buf(ctx, &ctx->d_scratch, &ctx->d_scratch_bytes, bytes, false);
 }
 
 int resolve_padding(int64_t length, int64_t window_length, int pad_mode, int64_t pad_lo, int64_t pad_hi,
@@ -94,32 +94,16 @@ int64_t frames_for(int64_t length, int64_t window_length, int64_t stride, const 
   return padded < window_length ? 0 : (padded - window_length) / stride + 1;
 }
 
-static double wall_seconds() {
-  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
-}
-
 // _dev entries run on the caller's stream; NULL is CUDA's (legacy) default stream, as everywhere in CUDA
 static cudaStream_t pick(nxs_ctx*, void* stream) { return (cudaStream_t)stream; }
-
-struct DeviceGuard {
-  int prev = -1;
-  bool ok = true;
-  explicit DeviceGuard(int dev) {
-    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
-    if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
-  }
-  ~DeviceGuard() {
-    if (prev >= 0) cudaSetDevice(prev);
-  }
-};
 
 // host-pointer helper: stage in -> run -> stage out, on the context's stream
 template <class F>
 static int host_roundtrip(nxs_ctx* ctx, const void* in, size_t in_bytes, const void* in2, size_t in2_bytes,
                           void* out, size_t out_bytes, F&& run) {
-  int rc = grow(ctx, &ctx->d_stage_in, &ctx->d_stage_in_bytes, in_bytes + in2_bytes + 512, false);
+  int rc = grow_buf(ctx, &ctx->d_stage_in, &ctx->d_stage_in_bytes, in_bytes + in2_bytes + 512, false);
   if (rc) return rc;
-  rc = grow(ctx, &ctx->d_stage_out, &ctx->d_stage_out_bytes, out_bytes + 256, false);
+  rc = grow_buf(ctx, &ctx->d_stage_out, &ctx->d_stage_out_bytes, out_bytes + 256, false);
   if (rc) return rc;
   char* d_in = (char*)ctx->d_stage_in;
   const size_t off2 = (in_bytes + 255) / 256 * 256;
@@ -130,6 +114,20 @@ static int host_roundtrip(nxs_ctx* ctx, const void* in, size_t in_bytes, const v
   if (rc) return rc;
   if (out_bytes) NXS_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_stage_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
   NXS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return NXS_OK;
+}
+
+int stft_check(int64_t channels, int64_t length, int64_t x_ld, int64_t frame_length, int64_t hop,
+                      int64_t fft_length, int pad_mode, int64_t pad_lo, int64_t pad_hi, int scaling,
+                      double sampling_rate, PadGeom* g, int64_t* M) {
+  if (channels < 0 || length < 1 || x_ld < length || frame_length < 1 || fft_length < 1) return NXS_ESHAPE;
+  if (hop < 1) return NXS_EINVAL;  // stride must be an integer >= 1 (lib/nx_signal.ex:279-284)
+  if (scaling != NXS_SCALE_NONE && scaling != NXS_SCALE_SPECTRUM && scaling != NXS_SCALE_PSD)
+    return NXS_EINVAL;  // lib/nx_signal.ex:124-126
+  if (!(sampling_rate == sampling_rate)) return NXS_EINVAL;
+  int rc = resolve_padding(length, frame_length, pad_mode, pad_lo, pad_hi, g);
+  if (rc) return rc;
+  *M = frames_for(length, frame_length, hop, *g);
   return NXS_OK;
 }
 
@@ -213,6 +211,7 @@ int nxs_ctx_destroy(nxs_ctx* ctx) {
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
   for (auto& e : ctx->prof_events) cudaEventDestroy(e);
   for (auto& e : ctx->slab_events) cudaEventDestroy(e);
+  if (ctx->order_event) cudaEventDestroy(ctx->order_event);
   delete ctx->pool;
   cudaStreamDestroy(ctx->stream);
   cudaStreamDestroy(ctx->copy_stream);
@@ -261,20 +260,6 @@ int nxs_ctx_host_timeline(const nxs_ctx* ctx, double out_seconds[4]) {
 }
 
 // ---- STFT -----------------------------------------------------------------------------------
-static int stft_check(int64_t channels, int64_t length, int64_t x_ld, int64_t frame_length, int64_t hop,
-                      int64_t fft_length, int pad_mode, int64_t pad_lo, int64_t pad_hi, int scaling,
-                      double sampling_rate, PadGeom* g, int64_t* M) {
-  if (channels < 0 || length < 1 || x_ld < length || frame_length < 1 || fft_length < 1) return NXS_ESHAPE;
-  if (hop < 1) return NXS_EINVAL;  // stride must be an integer >= 1 (lib/nx_signal.ex:279-284)
-  if (scaling != NXS_SCALE_NONE && scaling != NXS_SCALE_SPECTRUM && scaling != NXS_SCALE_PSD)
-    return NXS_EINVAL;  // lib/nx_signal.ex:124-126
-  if (!(sampling_rate == sampling_rate)) return NXS_EINVAL;
-  int rc = resolve_padding(length, frame_length, pad_mode, pad_lo, pad_hi, g);
-  if (rc) return rc;
-  *M = frames_for(length, frame_length, hop, *g);
-  return NXS_OK;
-}
-
 int nxs_stft_f32_dev(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, int64_t x_ld,
                      const float* window, int64_t frame_length, int64_t hop, int64_t fft_length,
                      int pad_mode, int64_t pad_lo, int64_t pad_hi, int scaling, double sampling_rate,
@@ -286,6 +271,7 @@ int nxs_stft_f32_dev(nxs_ctx* ctx, const float* x, int64_t channels, int64_t len
                       scaling, sampling_rate, &g, &M);
   if (rc) return rc;
   DeviceGuard guard(ctx->device);
+  StreamOrder stream_order(ctx, pick(ctx, stream));
   return launch_stft(ctx, x, channels, length, x_ld, window, frame_length, hop, fft_length, g, M, scaling,
                      sampling_rate, reinterpret_cast<float2*>(z), fft_length, 0, pick(ctx, stream));
 }
@@ -302,134 +288,12 @@ int nxs_stft_onesided_f32_dev(nxs_ctx* ctx, const float* x, int64_t channels, in
   if (rc) return rc;
   if (z_ld < fft_length / 2 + 1) return NXS_ESHAPE;
   DeviceGuard guard(ctx->device);
+  StreamOrder stream_order(ctx, pick(ctx, stream));
   return launch_stft(ctx, x, channels, length, x_ld, window, frame_length, hop, fft_length, g, M, scaling,
                      sampling_rate, reinterpret_cast<float2*>(z), z_ld, 1, pick(ctx, stream));
 }
 
-int nxs_stft_f32_host(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, int64_t x_ld,
-                      const float* window, int64_t frame_length, int64_t hop, int64_t fft_length,
-                      int pad_mode, int64_t pad_lo, int64_t pad_hi, int scaling, double sampling_rate,
-                      float* z) {
-  if (!ctx || !x || !window || !z) return NXS_EINVAL;
-  PadGeom g;
-  int64_t M = 0;
-  int rc = stft_check(channels, length, x_ld, frame_length, hop, fft_length, pad_mode, pad_lo, pad_hi,
-                      scaling, sampling_rate, &g, &M);
-  if (rc) return rc;
-  DeviceGuard guard(ctx->device);
-  if (channels == 0 || M == 0) return NXS_OK;
-  const double t_start = wall_seconds();
-  for (double& t : ctx->host_t) t = 0.0;
-  // Chunked pipeline over channels: H2D(chunk i+1) | kernels(chunk i) | D2H(chunk i-1) on three
-  // streams.  The D2H of the 8x larger spectrum dominates, so overlapping it with the H2D and
-  // the kernels hides everything but PCIe's D2H time -- and that time is halved by moving only
-  // bins 0 .. nfft/2 of each frame (a pitched copy straight into the caller's rows) and letting
-  // host threads write the conjugate-mirror half while later slabs are still in flight.
-  const bool mirror = stft_has_exact_mirror(fft_length) && !getenv("NXS_HOST_NO_MIRROR");
-  const int64_t nout = mirror ? fft_length / 2 + 1 : fft_length;
-  const int64_t z_ld = mirror ? (nout + 3) / 4 * 4 : fft_length;  // device row stride (32-byte multiple)
-  const size_t in_bytes = size_t((channels - 1) * x_ld + length) * sizeof(float);
-  const size_t dev_per_ch = size_t(M) * size_t(z_ld) * sizeof(float2);
-  int rc2 = grow(ctx, &ctx->d_stage_in, &ctx->d_stage_in_bytes, in_bytes + size_t(frame_length) * sizeof(float) + 512, false);
-  if (rc2) return rc2;
-  rc2 = grow(ctx, &ctx->d_stage_out, &ctx->d_stage_out_bytes, dev_per_ch * size_t(channels) + 256, false);
-  if (rc2) return rc2;
-  if (!ctx->out_stream) NXS_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->out_stream, cudaStreamNonBlocking));
-  if (mirror && !ctx->pool) ctx->pool = new HostPool(HostPool::default_threads());
-  float* d_x = (float*)ctx->d_stage_in;
-  float* d_w = (float*)((char*)ctx->d_stage_in + (in_bytes + 255) / 256 * 256);
-  float2* d_z = (float2*)ctx->d_stage_out;
-  float2* hz = reinterpret_cast<float2*>(z);
-  int64_t cc = int64_t((size_t(128) << 20) / (dev_per_ch ? dev_per_ch : 1));
-  if (cc < 1) cc = 1;
-  if (cc > channels) cc = channels;
-  // D2H slabs: whole frames, a few MiB on the wire each (small enough that the mirror threads
-  // read a slab while it is still cache-resident, large enough to keep the copy engine busy)
-  size_t slab_bytes = size_t(8) << 20;
-  if (const char* e = getenv("NXS_HOST_SLAB_KB")) {
-    if (atol(e) > 0) slab_bytes = size_t(atol(e)) << 10;
-  }
-  int64_t slab_rows = int64_t(slab_bytes / (size_t(nout) * sizeof(float2)));
-  slab_rows = slab_rows < 64 ? 64 : slab_rows / 64 * 64;  // whole mirror work items (64 frames)
-  // host threads: work item b mirrors frames [64 b, 64 b + 64); it may start once its slab landed
-  struct Job { float* z; int64_t nfft, rows; };
-  Job job{z, fft_length, channels * M};
-  std::atomic<int64_t> gate{0};
-  const int64_t items = (job.rows + 63) / 64;
-  std::vector<int64_t> slab_end;  // frames landed once slab s is complete
-  if (mirror) {
-    ctx->pool->begin(items, [](void* p, int64_t b) {
-      const Job* j = static_cast<const Job*>(p);
-      const int64_t a0 = b * 64;
-      const int64_t a1 = a0 + 64 < j->rows ? a0 + 64 : j->rows;
-      mirror_rows_c64(j->z, j->nfft, a0, a1);
-    }, &job, &gate);
-  }
-  // from here on every exit must join the workers
-  auto enqueue = [&]() -> int {
-    NXS_CUDA(ctx, cudaMemcpyAsync(d_w, window, size_t(frame_length) * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_stream));
-    int i = 0;
-    for (int64_t c0 = 0; c0 < channels; c0 += cc, ++i) {
-      const int64_t n = channels - c0 < cc ? channels - c0 : cc;
-      const size_t xb = size_t((n - 1) * x_ld + length) * sizeof(float);
-      NXS_CUDA(ctx, cudaMemcpyAsync(d_x + c0 * x_ld, x + c0 * x_ld, xb, cudaMemcpyHostToDevice, ctx->copy_stream));
-      NXS_CUDA(ctx, cudaEventRecord(ctx->ev[i & 1], ctx->copy_stream));
-      NXS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev[i & 1], 0));
-      int rcl = launch_stft(ctx, d_x + c0 * x_ld, n, length, x_ld, d_w, frame_length, hop, fft_length, g, M, scaling,
-                            sampling_rate, d_z + size_t(c0) * M * z_ld, z_ld, mirror ? 1 : 0, ctx->stream);
-      if (rcl) return rcl;
-      NXS_CUDA(ctx, cudaEventRecord(ctx->ev[2 + (i & 1)], ctx->stream));
-      NXS_CUDA(ctx, cudaStreamWaitEvent(ctx->out_stream, ctx->ev[2 + (i & 1)], 0));
-      const int64_t r_end = (c0 + n) * M;
-      int64_t r0 = c0 * M;
-      while (r0 < r_end) {
-        // slabs end on multiples of 64 frames (work-item boundaries) except at the chunk's end
-        int64_t r1 = (r0 / 64 + slab_rows / 64) * 64;
-        if (r1 > r_end) r1 = r_end;
-        if (mirror) {
-          NXS_CUDA(ctx, cudaMemcpy2DAsync(hz + size_t(r0) * fft_length, size_t(fft_length) * sizeof(float2),
-                                          d_z + size_t(r0) * z_ld, size_t(z_ld) * sizeof(float2),
-                                          size_t(nout) * sizeof(float2), size_t(r1 - r0), cudaMemcpyDeviceToHost,
-                                          ctx->out_stream));
-          if (slab_end.size() >= ctx->slab_events.size()) {
-            cudaEvent_t e = nullptr;
-            NXS_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-            ctx->slab_events.push_back(e);
-          }
-          NXS_CUDA(ctx, cudaEventRecord(ctx->slab_events[slab_end.size()], ctx->out_stream));
-          slab_end.push_back(r1);
-        } else {
-          NXS_CUDA(ctx, cudaMemcpyAsync(hz + size_t(r0) * fft_length, d_z + size_t(r0) * fft_length,
-                                        size_t(r1 - r0) * fft_length * sizeof(float2), cudaMemcpyDeviceToHost,
-                                        ctx->out_stream));
-        }
-        r0 = r1;
-      }
-    }
-    // raise the gate as slabs land: item b is runnable once frames [64 b, 64 b + 64) are in host memory
-    ctx->host_t[0] = wall_seconds() - t_start;  // everything enqueued
-    for (size_t s = 0; s < slab_end.size(); ++s) {
-      NXS_CUDA(ctx, cudaEventSynchronize(ctx->slab_events[s]));
-      if (s == 0) ctx->host_t[1] = wall_seconds() - t_start;  // first slab landed
-      const int64_t landed = slab_end[s];
-      gate.store(landed == job.rows ? items : landed / 64, std::memory_order_release);
-    }
-    return NXS_OK;
-  };
-  rc = enqueue();
-  ctx->host_t[2] = wall_seconds() - t_start;  // last slab landed
-  if (mirror) ctx->pool->finish(rc != NXS_OK);
-  ctx->host_t[3] = wall_seconds() - t_start;  // mirror complete
-  if (rc) {
-    cudaStreamSynchronize(ctx->out_stream);  // nothing of ours may still write the caller's buffer
-    cudaStreamSynchronize(ctx->stream);
-    cudaStreamSynchronize(ctx->copy_stream);
-    return rc;
-  }
-  NXS_CUDA(ctx, cudaStreamSynchronize(ctx->out_stream));
-  NXS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return NXS_OK;
-}
+// nxs_stft_f32_host: nxs_hostio.cu (channel-chunk pipeline, one-sided transfer + host mirror, pinned rings)
 
 // ---- ISTFT ----------------------------------------------------------------------------------
 static int istft_check(int64_t channels, int64_t num_frames, int64_t z_len, int64_t frame_length, int64_t hop,
@@ -449,6 +313,7 @@ int nxs_istft_c64_dev(nxs_ctx* ctx, const float* z, int64_t channels, int64_t nu
   int rc = istft_check(channels, num_frames, z_len, frame_length, hop, fft_length, scaling);
   if (rc) return rc;
   DeviceGuard guard(ctx->device);
+  StreamOrder stream_order(ctx, pick(ctx, stream));
   return launch_istft(ctx, reinterpret_cast<const float2*>(z), channels, num_frames, z_len, window,
                       frame_length, hop, fft_length, scaling, sampling_rate, reinterpret_cast<float2*>(y),
                       pick(ctx, stream));
@@ -461,14 +326,20 @@ int nxs_istft_c64_host(nxs_ctx* ctx, const float* z, int64_t channels, int64_t n
   int rc = istft_check(channels, num_frames, z_len, frame_length, hop, fft_length, scaling);
   if (rc) return rc;
   DeviceGuard guard(ctx->device);
-  const size_t in_bytes = size_t(channels) * num_frames * z_len * sizeof(float2);
-  const size_t out_len = size_t(num_frames) * hop + (frame_length - hop);
-  return host_roundtrip(ctx, z, in_bytes, window, size_t(frame_length) * sizeof(float), y,
-                        size_t(channels) * out_len * sizeof(float2), [&](void* dz, void* dw, void* dy) {
-                          return launch_istft(ctx, (const float2*)dz, channels, num_frames, z_len,
-                                              (const float*)dw, frame_length, hop, fft_length, scaling,
-                                              sampling_rate, (float2*)dy, ctx->stream);
-                        });
+  StreamOrder stream_order(ctx, ctx->stream);
+  // channels are independent: H2D of the spectrum | kernels | D2H of the signal, chunk by chunk
+  PipeSpec ps;
+  ps.in = z;
+  ps.in_row_bytes = ps.in_pitch = size_t(num_frames) * z_len * sizeof(float2);
+  ps.out = y;
+  ps.out_row_bytes = ps.out_pitch = (size_t(num_frames) * hop + (frame_length - hop)) * sizeof(float2);
+  ps.rows = channels;
+  ps.aux = window;
+  ps.aux_bytes = size_t(frame_length) * sizeof(float);
+  return host_pipeline(ctx, ps, [&](int64_t, int64_t n, void* dz, void* dw, void* dy) {
+    return launch_istft(ctx, (const float2*)dz, n, num_frames, z_len, (const float*)dw, frame_length, hop, fft_length,
+                        scaling, sampling_rate, (float2*)dy, ctx->stream);
+  });
 }
 
 static int istft_c2r_check(int64_t channels, int64_t num_frames, int64_t z_ld, int64_t frame_length, int64_t hop,
@@ -486,6 +357,7 @@ int nxs_istft_c2r_f32_dev(nxs_ctx* ctx, const float* z, int64_t channels, int64_
   int rc = istft_c2r_check(channels, num_frames, z_ld, frame_length, hop, fft_length, scaling);
   if (rc) return rc;
   DeviceGuard guard(ctx->device);
+  StreamOrder stream_order(ctx, pick(ctx, stream));
   return launch_istft_c2r(ctx, reinterpret_cast<const float2*>(z), channels, num_frames, z_ld, window,
                           frame_length, hop, fft_length, scaling, sampling_rate, y, pick(ctx, stream));
 }
@@ -497,14 +369,19 @@ int nxs_istft_c2r_f32_host(nxs_ctx* ctx, const float* z, int64_t channels, int64
   int rc = istft_c2r_check(channels, num_frames, z_ld, frame_length, hop, fft_length, scaling);
   if (rc) return rc;
   DeviceGuard guard(ctx->device);
-  const size_t in_bytes = size_t(channels) * num_frames * z_ld * sizeof(float2);
-  const size_t out_len = size_t(num_frames) * hop + (frame_length - hop);
-  return host_roundtrip(ctx, z, in_bytes, window, size_t(frame_length) * sizeof(float), y,
-                        size_t(channels) * out_len * sizeof(float), [&](void* dz, void* dw, void* dy) {
-                          return launch_istft_c2r(ctx, (const float2*)dz, channels, num_frames, z_ld,
-                                                  (const float*)dw, frame_length, hop, fft_length, scaling,
-                                                  sampling_rate, (float*)dy, ctx->stream);
-                        });
+  StreamOrder stream_order(ctx, ctx->stream);
+  PipeSpec ps;
+  ps.in = z;
+  ps.in_row_bytes = ps.in_pitch = size_t(num_frames) * z_ld * sizeof(float2);
+  ps.out = y;
+  ps.out_row_bytes = ps.out_pitch = (size_t(num_frames) * hop + (frame_length - hop)) * sizeof(float);
+  ps.rows = channels;
+  ps.aux = window;
+  ps.aux_bytes = size_t(frame_length) * sizeof(float);
+  return host_pipeline(ctx, ps, [&](int64_t, int64_t n, void* dz, void* dw, void* dy) {
+    return launch_istft_c2r(ctx, (const float2*)dz, n, num_frames, z_ld, (const float*)dw, frame_length, hop,
+                            fft_length, scaling, sampling_rate, (float*)dy, ctx->stream);
+  });
 }
 
 // ---- stft_to_mel --------------------------------------------------------------------------------
@@ -523,6 +400,7 @@ int nxs_stft_to_mel_f32_dev(nxs_ctx* ctx, const float* z, int64_t channels, int6
   int rc = mel_check(channels, num_frames, z_ld, fft_length, mel_bins, sampling_rate, mel_frequency_spacing);
   if (rc) return rc;
   DeviceGuard guard(ctx->device);
+  StreamOrder stream_order(ctx, pick(ctx, stream));
   return launch_stft_to_mel(ctx, reinterpret_cast<const float2*>(z), channels, num_frames, z_ld, fft_length, mel_bins,
                             sampling_rate, max_mel, mel_frequency_spacing, out, pick(ctx, stream));
 }
@@ -534,10 +412,15 @@ int nxs_stft_to_mel_f32_host(nxs_ctx* ctx, const float* z, int64_t channels, int
   int rc = mel_check(channels, num_frames, z_ld, fft_length, mel_bins, sampling_rate, mel_frequency_spacing);
   if (rc) return rc;
   DeviceGuard guard(ctx->device);
-  const size_t in_bytes = size_t(channels) * num_frames * z_ld * sizeof(float2);
-  const size_t out_bytes = size_t(channels) * num_frames * mel_bins * sizeof(float);
-  return host_roundtrip(ctx, z, in_bytes, nullptr, 0, out, out_bytes, [&](void* dz, void*, void* dout) {
-    return launch_stft_to_mel(ctx, (const float2*)dz, channels, num_frames, z_ld, fft_length, mel_bins, sampling_rate,
+  StreamOrder stream_order(ctx, ctx->stream);
+  PipeSpec ps;  // the clamp's maximum is per channel, so channels are independent rows
+  ps.in = z;
+  ps.in_row_bytes = ps.in_pitch = size_t(num_frames) * z_ld * sizeof(float2);
+  ps.out = out;
+  ps.out_row_bytes = ps.out_pitch = size_t(num_frames) * mel_bins * sizeof(float);
+  ps.rows = channels;
+  return host_pipeline(ctx, ps, [&](int64_t, int64_t n, void* dz, void*, void* dout) {
+    return launch_stft_to_mel(ctx, (const float2*)dz, n, num_frames, z_ld, fft_length, mel_bins, sampling_rate,
                               max_mel, mel_frequency_spacing, (float*)dout, ctx->stream);
   });
 }
@@ -557,6 +440,7 @@ int nxs_stft_mel_f32_dev(nxs_ctx* ctx, const float* x, int64_t channels, int64_t
     if (rc) return rc;
   }
   DeviceGuard guard(ctx->device);
+  StreamOrder stream_order(ctx, pick(ctx, stream));
   return launch_stft_mel(ctx, x, channels, length, x_ld, window, frame_length, hop, fft_length, g, M, scaling,
                          sampling_rate, mel_bins, max_mel, mel_frequency_spacing, out, pick(ctx, stream));
 }
@@ -575,13 +459,14 @@ int nxs_stft_mel_f32_host(nxs_ctx* ctx, const float* x, int64_t channels, int64_
   rc = mel_check(channels, M, fft_length, fft_length, mel_bins, sampling_rate, mel_frequency_spacing);
   if (rc) return rc;
   DeviceGuard guard(ctx->device);
+  StreamOrder stream_order(ctx, ctx->stream);
   const size_t in_bytes = (size_t(channels - 1) * x_ld + length) * sizeof(float);
   const size_t w_bytes = size_t(frame_length) * sizeof(float);
   const size_t row_out = size_t(M) * mel_bins;  // floats per channel
   const size_t out_bytes = size_t(channels) * row_out * sizeof(float);
-  rc = grow(ctx, &ctx->d_stage_in, &ctx->d_stage_in_bytes, in_bytes + w_bytes + 512, false);
+  rc = grow_buf(ctx, &ctx->d_stage_in, &ctx->d_stage_in_bytes, in_bytes + w_bytes + 512, false);
   if (rc) return rc;
-  rc = grow(ctx, &ctx->d_stage_out, &ctx->d_stage_out_bytes, out_bytes + 256, false);
+  rc = grow_buf(ctx, &ctx->d_stage_out, &ctx->d_stage_out_bytes, out_bytes + 256, false);
   if (rc) return rc;
   float* dx = (float*)ctx->d_stage_in;
   float* dw = (float*)((char*)ctx->d_stage_in + (in_bytes + 255) / 256 * 256);
@@ -677,6 +562,7 @@ int nxs_median_f32_dev(nxs_ctx* ctx, const float* t, int rank, const int64_t* sh
   int rc = median_check(rank, shape, kernel_shape, s3, k3);
   if (rc) return rc;
   DeviceGuard guard(ctx->device);
+  StreamOrder stream_order(ctx, pick(ctx, stream));
   return launch_median(ctx, t, s3, k3, out, pick(ctx, stream));
 }
 
@@ -687,7 +573,19 @@ int nxs_median_f32_host(nxs_ctx* ctx, const float* t, int rank, const int64_t* s
   int rc = median_check(rank, shape, kernel_shape, s3, k3);
   if (rc) return rc;
   DeviceGuard guard(ctx->device);
+  StreamOrder stream_order(ctx, ctx->stream);
   const size_t bytes = size_t(s3[0] * s3[1] * s3[2]) * sizeof(float);
+  if (k3[0] == 1 && s3[0] > 1) {  // the window does not span the leading axis: its slices are independent rows
+    PipeSpec ps;
+    ps.in = t;
+    ps.out = out;
+    ps.in_row_bytes = ps.in_pitch = ps.out_row_bytes = ps.out_pitch = size_t(s3[1] * s3[2]) * sizeof(float);
+    ps.rows = s3[0];
+    return host_pipeline(ctx, ps, [&](int64_t, int64_t n, void* dt, void*, void* dout) {
+      const int64_t sn[3] = {n, s3[1], s3[2]};
+      return launch_median(ctx, (const float*)dt, sn, k3, (float*)dout, ctx->stream);
+    });
+  }
   return host_roundtrip(ctx, t, bytes, nullptr, 0, out, bytes, [&](void* dt, void*, void* dout) {
     return launch_median(ctx, (const float*)dt, s3, k3, (float*)dout, ctx->stream);
   });
@@ -700,6 +598,7 @@ int nxs_wiener_dev(nxs_ctx* ctx, const void* t, int is_f64, int rank, const int6
   int rc = pad3(rank, shape, kernel_size, s3, k3);
   if (rc) return rc;
   DeviceGuard guard(ctx->device);
+  StreamOrder stream_order(ctx, pick(ctx, stream));
   return launch_wiener(ctx, t, is_f64 != 0, s3, k3, has_noise != 0, noise, out, pick(ctx, stream));
 }
 
@@ -710,6 +609,7 @@ int nxs_wiener_host(nxs_ctx* ctx, const void* t, int is_f64, int rank, const int
   int rc = pad3(rank, shape, kernel_size, s3, k3);
   if (rc) return rc;
   DeviceGuard guard(ctx->device);
+  StreamOrder stream_order(ctx, ctx->stream);
   const size_t bytes = size_t(s3[0] * s3[1] * s3[2]) * (is_f64 ? sizeof(double) : sizeof(float));
   return host_roundtrip(ctx, t, bytes, nullptr, 0, out, bytes, [&](void* dt, void*, void* dout) {
     return launch_wiener(ctx, dt, is_f64 != 0, s3, k3, has_noise != 0, noise, dout, ctx->stream);
@@ -737,6 +637,7 @@ int nxs_argrelextrema_f32_dev(nxs_ctx* ctx, const float* data, int rank, const i
   int rc = argrel_check(rank, shape, axis, order, comparator, &total);
   if (rc) return rc;
   DeviceGuard guard(ctx->device);
+  StreamOrder stream_order(ctx, pick(ctx, stream));
   return launch_argrelextrema(ctx, data, rank, shape, axis, order, comparator, indices, valid_count, pick(ctx, stream));
 }
 
@@ -747,10 +648,11 @@ int nxs_argrelextrema_f32_host(nxs_ctx* ctx, const float* data, int rank, const 
   int rc = argrel_check(rank, shape, axis, order, comparator, &total);
   if (rc) return rc;
   DeviceGuard guard(ctx->device);
+  StreamOrder stream_order(ctx, ctx->stream);
   const size_t idx_bytes = size_t(total) * rank * sizeof(int32_t);
   const size_t idx_pad = (idx_bytes + 255) / 256 * 256;
   // staged result = indices followed by the count
-  rc = grow(ctx, &ctx->d_stage_out, &ctx->d_stage_out_bytes, idx_pad + 256, false);
+  rc = grow_buf(ctx, &ctx->d_stage_out, &ctx->d_stage_out_bytes, idx_pad + 256, false);
   if (rc) return rc;
   rc = host_roundtrip(ctx, data, size_t(total) * sizeof(float), nullptr, 0, indices, idx_bytes,
                       [&](void* dd, void*, void* dout) {
@@ -783,6 +685,7 @@ int nxs_as_windowed_dev(nxs_ctx* ctx, const void* x, int elem_size, int64_t chan
   int rc = aw_check(elem_size, channels, length, x_ld, window_length, stride, pad_mode, pad_lo, pad_hi, &g, &M);
   if (rc) return rc;
   DeviceGuard guard(ctx->device);
+  StreamOrder stream_order(ctx, pick(ctx, stream));
   return launch_as_windowed(ctx, x, elem_size, channels, length, x_ld, window_length, stride, g, M, out,
                             pick(ctx, stream));
 }
@@ -796,11 +699,17 @@ int nxs_as_windowed_host(nxs_ctx* ctx, const void* x, int elem_size, int64_t cha
   int rc = aw_check(elem_size, channels, length, x_ld, window_length, stride, pad_mode, pad_lo, pad_hi, &g, &M);
   if (rc) return rc;
   DeviceGuard guard(ctx->device);
-  const size_t in_bytes = size_t(channels > 0 ? (channels - 1) * x_ld + length : 0) * elem_size;
-  const size_t out_bytes = size_t(channels) * M * window_length * elem_size;
-  return host_roundtrip(ctx, x, in_bytes, nullptr, 0, out, out_bytes, [&](void* dx, void*, void* dout) {
-    return launch_as_windowed(ctx, dx, elem_size, channels, length, x_ld, window_length, stride, g, M, dout,
-                              ctx->stream);
+  if (channels == 0 || M == 0) return NXS_OK;
+  StreamOrder stream_order(ctx, ctx->stream);
+  PipeSpec ps;
+  ps.in = x;
+  ps.in_row_bytes = size_t(length) * elem_size;
+  ps.in_pitch = size_t(x_ld) * elem_size;
+  ps.out = out;
+  ps.out_row_bytes = ps.out_pitch = size_t(M) * window_length * elem_size;
+  ps.rows = channels;
+  return host_pipeline(ctx, ps, [&](int64_t, int64_t n, void* dx, void*, void* dout) {
+    return launch_as_windowed(ctx, dx, elem_size, n, length, x_ld, window_length, stride, g, M, dout, ctx->stream);
   });
 }
 
@@ -817,6 +726,7 @@ static int ola_dev(nxs_ctx* ctx, const float* t, int cplx, int64_t batch, int64_
   int rc = ola_check(batch, num_frames, frame_length, overlap);
   if (rc) return rc;
   DeviceGuard guard(ctx->device);
+  StreamOrder stream_order(ctx, pick(ctx, stream));
   return launch_overlap_and_add(ctx, t, cplx, batch, num_frames, frame_length, overlap, out, pick(ctx, stream));
 }
 
@@ -826,13 +736,18 @@ static int ola_host(nxs_ctx* ctx, const float* t, int cplx, int64_t batch, int64
   int rc = ola_check(batch, num_frames, frame_length, overlap);
   if (rc) return rc;
   DeviceGuard guard(ctx->device);
+  StreamOrder stream_order(ctx, ctx->stream);
   const size_t es = cplx ? 8 : 4;
-  const size_t out_len = size_t(num_frames) * (frame_length - overlap) + overlap;
-  return host_roundtrip(ctx, t, size_t(batch) * num_frames * frame_length * es, nullptr, 0, out,
-                        size_t(batch) * out_len * es, [&](void* dt, void*, void* dout) {
-                          return launch_overlap_and_add(ctx, (const float*)dt, cplx, batch, num_frames,
-                                                        frame_length, overlap, (float*)dout, ctx->stream);
-                        });
+  PipeSpec ps;
+  ps.in = t;
+  ps.in_row_bytes = ps.in_pitch = size_t(num_frames) * frame_length * es;
+  ps.out = out;
+  ps.out_row_bytes = ps.out_pitch = (size_t(num_frames) * (frame_length - overlap) + overlap) * es;
+  ps.rows = batch;
+  return host_pipeline(ctx, ps, [&](int64_t, int64_t n, void* dt, void*, void* dout) {
+    return launch_overlap_and_add(ctx, (const float*)dt, cplx, n, num_frames, frame_length, overlap, (float*)dout,
+                                  ctx->stream);
+  });
 }
 
 int nxs_overlap_and_add_f32_dev(nxs_ctx* ctx, const float* t, int64_t batch, int64_t num_frames,
@@ -869,6 +784,7 @@ int nxs_fir_f32_dev(nxs_ctx* ctx, const float* x, int64_t channels, int64_t leng
   int rc = fir_check(channels, length, x_ld, num_taps, mode, y_ld, &out_len);
   if (rc) return rc;
   DeviceGuard guard(ctx->device);
+  StreamOrder stream_order(ctx, pick(ctx, stream));
   return launch_fir(ctx, x, channels, length, x_ld, taps, num_taps, mode, y, y_ld, pick(ctx, stream));
 }
 
@@ -879,13 +795,23 @@ int nxs_fir_f32_host(nxs_ctx* ctx, const float* x, int64_t channels, int64_t len
   int rc = fir_check(channels, length, x_ld, num_taps, mode, y_ld, &out_len);
   if (rc) return rc;
   DeviceGuard guard(ctx->device);
-  const size_t in_bytes = size_t(channels > 0 ? (channels - 1) * x_ld + length : 0) * sizeof(float);
-  const size_t out_bytes = size_t(channels > 0 ? (channels - 1) * y_ld + out_len : 0) * sizeof(float);
-  return host_roundtrip(ctx, x, in_bytes, taps, size_t(num_taps) * sizeof(float), y, out_bytes,
-                        [&](void* dx, void* dt, void* dy) {
-                          return launch_fir(ctx, (const float*)dx, channels, length, x_ld, (const float*)dt,
-                                            num_taps, mode, (float*)dy, y_ld, ctx->stream);
-                        });
+  StreamOrder stream_order(ctx, ctx->stream);
+  // channels are independent: H2D | overlap-save kernels | D2H, chunk by chunk -- the call costs
+  // max(H2D, D2H) instead of their sum (PCIe is full duplex)
+  PipeSpec ps;
+  ps.in = x;
+  ps.in_row_bytes = size_t(length) * sizeof(float);
+  ps.in_pitch = size_t(x_ld) * sizeof(float);
+  ps.out = y;
+  ps.out_row_bytes = size_t(out_len) * sizeof(float);
+  ps.out_pitch = size_t(y_ld) * sizeof(float);
+  ps.rows = channels;
+  ps.aux = taps;
+  ps.aux_bytes = size_t(num_taps) * sizeof(float);
+  return host_pipeline(ctx, ps, [&](int64_t, int64_t n, void* dx, void* dt, void* dy) {
+    return launch_fir(ctx, (const float*)dx, n, length, x_ld, (const float*)dt, num_taps, mode, (float*)dy, y_ld,
+                      ctx->stream);
+  });
 }
 
 // ---- N-d convolution ----------------------------------------------------------------------------
@@ -915,6 +841,7 @@ int nxs_convolve_nd_dev(nxs_ctx* ctx, const float* a, const int64_t a_shape[3], 
   int rc = conv_check(a_shape, b_shape, mode, os);
   if (rc) return rc;
   DeviceGuard guard(ctx->device);
+  StreamOrder stream_order(ctx, pick(ctx, stream));
   return launch_convolve_nd(ctx, a, a_shape, b, b_shape, is_complex, mode, out, pick(ctx, stream));
 }
 
@@ -925,6 +852,7 @@ int nxs_convolve_nd_host(nxs_ctx* ctx, const float* a, const int64_t a_shape[3],
   int rc = conv_check(a_shape, b_shape, mode, os);
   if (rc) return rc;
   DeviceGuard guard(ctx->device);
+  StreamOrder stream_order(ctx, ctx->stream);
   const size_t es = is_complex ? 8 : 4;
   const size_t na = size_t(a_shape[0]) * a_shape[1] * a_shape[2], nb = size_t(b_shape[0]) * b_shape[1] * b_shape[2];
   const size_t no = size_t(os[0]) * os[1] * os[2];
@@ -953,6 +881,7 @@ int nxs_bcast_coeffs_dev(nxs_ctx* ctx, void* comm, float* buf, int64_t count, in
     return NXS_ENCCL;
   }
   DeviceGuard guard(ctx->device);
+  StreamOrder stream_order(ctx, pick(ctx, stream));
   const int rc = fn(buf, buf, (size_t)count, /*ncclFloat32*/ 7, root, comm, pick(ctx, stream));
   if (rc != 0) {
     ctx->last_error = "ncclBroadcast failed with code " + std::to_string(rc);

@@ -77,6 +77,16 @@ struct nxs_ctx {
   std::vector<cudaEvent_t> slab_events;
   nxs::HostPool* pool = nullptr;
   double host_t[4] = {0, 0, 0, 0};  // nxs_ctx_host_timeline
+  // nxs_stft_f32_host on pinned results: 0 = both spectrum halves over PCIe, 1 = lower half + host mirror;
+  // measured cost (seconds per result byte) of each, and the mode pinned by nxs_ctx_set_host_mode (-1: auto)
+  double host_cost[2] = {0, 0};
+  int host_mode_forced = -1, host_mode_last = 0;
+  uint64_t host_calls = 0;
+  // stream ordering of the context's shared device state (d_coef, d_scratch, tables under construction):
+  // the last stream that used them and an event recorded behind that use (StreamOrder)
+  cudaStream_t order_stream = nullptr;
+  cudaEvent_t order_event = nullptr;
+  bool order_valid = false;
   // optional per-kernel timing (nxs_ctx_profile)
   bool prof_enabled = false;
   std::vector<cudaEvent_t> prof_events;  // start/stop pairs
@@ -95,6 +105,47 @@ int set_cuda_error(nxs_ctx* ctx, cudaError_t e, const char* where);
     cudaError_t e__ = (call);                                          \
     if (e__ != cudaSuccess) return nxs::set_cuda_error(ctx, e__, #call); \
   } while (0)
+
+struct PadGeom;
+// RAII device switch of every entry point
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// The prepared window (d_coef) and the scratch block (d_scratch) are per context, and every compute
+// entry rewrites them on the stream it runs on.  A call arriving on a different stream than the
+// previous one first waits (on the device) for that call's work; the previous call's stream is
+// never blocked and the host never waits.  Same-stream sequences cost one event record per call.
+struct StreamOrder {
+  nxs_ctx* ctx;
+  cudaStream_t st;
+  StreamOrder(nxs_ctx* c, cudaStream_t s) : ctx(c), st(s) {
+    if (ctx->order_valid && ctx->order_stream != st) cudaStreamWaitEvent(st, ctx->order_event, 0);
+  }
+  ~StreamOrder() {
+    if (!ctx->order_event && cudaEventCreateWithFlags(&ctx->order_event, cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      return;
+    }
+    if (cudaEventRecord(ctx->order_event, st) == cudaSuccess) {
+      ctx->order_stream = st;
+      ctx->order_valid = true;
+    } else {
+      cudaGetLastError();
+    }
+  }
+};
+
+int stft_check(int64_t channels, int64_t length, int64_t x_ld, int64_t frame_length, int64_t hop, int64_t fft_length,
+               int pad_mode, int64_t pad_lo, int64_t pad_hi, int scaling, double sampling_rate, PadGeom* g, int64_t* M);
 
 void prof_begin(nxs_ctx* ctx, cudaStream_t st);
 void prof_end(nxs_ctx* ctx, cudaStream_t st);

@@ -55,7 +55,14 @@ __global__ void prep_window_kernel(const float* __restrict__ w, int n, int nfft,
 struct StftArgs {
   const float* x;
   int64_t x_ld, L;
-  const float* wprep;  // [nfft], scaled, zero-extended
+  const float* wprep;  // [nfft], scaled, zero-extended (prep_window_kernel) -- or, with winline, the caller's raw window
+  int winline = 0;     // 1: no :scaling, the staged kernel forms w[i] * wmul itself (one launch less per call)
+  float wmul = 1.f;
+  // what prep_window_kernel needs when a path does not take the window inline
+  const float* wraw = nullptr;
+  int wn = 0, scaling = 0;
+  float sr = 0.f;
+  float* wdst = nullptr;
   float2* z;           // [total_frames][z_ld]; nfft bins per frame, or nfft/2 + 1 when onesided
   int64_t z_ld;
   int onesided;        // 1: only bins 0 .. nfft/2 are stored (the rest is their conjugate mirror)
@@ -266,7 +273,11 @@ __global__ void __launch_bounds__(CF::THREADS, MINB) stft_r2c_staged_kernel(cons
   }
   int mel_c = -1;            // channel the running maximum belongs to
   float mel_max = -INFINITY;  // running maximum of this thread's log-mel values
-  for (int i = tid; i < NFFT; i += THREADS) wsm[i] = a.wprep[i];
+  if (a.winline) {
+    for (int i = tid; i < NFFT; i += THREADS) wsm[i] = i < a.nload ? a.wprep[i] * a.wmul : 0.f;
+  } else {
+    for (int i = tid; i < NFFT; i += THREADS) wsm[i] = a.wprep[i];
+  }
   if constexpr (!CF::TWREG) {
     cpx* twsm = reinterpret_cast<cpx*>(smem_raw + CF::TW_OFF);
     for (int i = tid; i < PL::TW_TOTAL; i += THREADS) twsm[i] = a.tw[i];
@@ -698,21 +709,53 @@ int get_dft_table(nxs_ctx* ctx, int64_t n, int sign, float2** out) {
   return NXS_OK;
 }
 
+int launch_prep_window(nxs_ctx* ctx, const float* window, int64_t n, int64_t nfft, int scaling,
+                       double sampling_rate, float prescale, int invert, float* out, cudaStream_t st);
+
+// scaled, zero-extended window into the context's coefficient block (paths that do not take it inline)
+static int prep_for(nxs_ctx* ctx, StftArgs& a, int nfft, cudaStream_t st) {
+  int rc = launch_prep_window(ctx, a.wraw, a.wn, nfft, a.scaling, a.sr, a.wmul, 0, a.wdst, st);
+  a.wprep = a.wdst;
+  a.winline = 0;
+  return rc;
+}
+
+// cudaFuncSetAttribute + occupancy query once per (kernel instantiation, device), not per call
+struct LaunchCache {
+  int occ[16] = {0};
+  size_t smem[16] = {0};
+  template <class K>
+  int get(nxs_ctx* ctx, K kern, int threads, size_t smem_bytes, int* out) {
+    const int d = ctx->device & 15;
+    if (occ[d] == 0 || smem[d] != smem_bytes) {
+      NXS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+      int o = 1;
+      NXS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, threads, smem_bytes));
+      smem[d] = smem_bytes;
+      occ[d] = o < 1 ? 1 : o;
+    }
+    *out = occ[d];
+    return NXS_OK;
+  }
+};
+
 template <class PL, class TW, int THREADS>
 static int run_r2c(nxs_ctx* ctx, StftArgs a, cudaStream_t st) {
   if (a.mel_out) return NXS_EUNSUPPORTED;  // the caller chains stft -> stft_to_mel instead
   PlanTables tabs;
   int rc = get_tables<PL>(ctx, &tabs);
   if (rc) return rc;
+  rc = prep_for(ctx, a, 2 * PL::N, st);
+  if (rc) return rc;
   a.tw = tabs.tw;
   a.post = tabs.post;
   constexpr int G = THREADS / PL::T;
   const size_t smem = size_t(G) * 2 * PL::BUF * sizeof(cpx);
   auto kern = stft_r2c_kernel<PL, TW, THREADS>;
-  NXS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static LaunchCache cache;
   int occ = 1;
-  NXS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
-  if (occ < 1) occ = 1;
+  rc = cache.get(ctx, kern, THREADS, smem, &occ);
+  if (rc) return rc;
   const int64_t tiles = (a.total_frames + G - 1) / G;
   int64_t grid = int64_t(ctx->sm_count) * occ;
   if (grid > tiles) grid = tiles;
@@ -751,10 +794,17 @@ static int run_r2c_staged(nxs_ctx* ctx, StftArgs a, int64_t channels, cudaStream
     smem = (CF::SMEM + 15) / 16 * 16 + size_t(PL::N) * sizeof(float2) + size_t(a.mel_bins + 3) * sizeof(int);
   }
   if (smem > 232448) return NXS_EUNSUPPORTED;
-  NXS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static LaunchCache cache[3];  // one per epilogue mode
   int occ = 1;
-  NXS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
-  if (occ < 1) occ = 1;
+  rc = cache[a.mel_out ? 2 : a.onesided ? 1 : 0].get(ctx, kern, THREADS, smem, &occ);
+  if (rc) return rc;
+  if (a.scaling == NXS_SCALE_NONE) {  // the kernel scales the raw window while it loads it
+    a.wprep = a.wraw;
+    a.winline = 1;
+  } else {
+    rc = prep_for(ctx, a, CF::NFFT, st);
+    if (rc) return rc;
+  }
   int64_t grid = int64_t(ctx->sm_count) * occ;
   if (grid > tiles) grid = tiles;
   prof_begin(ctx, st);
@@ -810,6 +860,11 @@ int launch_stft(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, 
   a.x_ld = x_ld;
   a.L = length;
   a.wprep = ctx->d_coef;
+  a.wdst = ctx->d_coef;
+  a.wraw = window;
+  a.wn = (int)frame_length;
+  a.scaling = scaling;
+  a.sr = (float)sampling_rate;
   a.z = z;
   a.z_ld = z_ld;
   a.onesided = onesided;
@@ -829,9 +884,7 @@ int launch_stft(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, 
   }
 
   const bool fast = stft_has_exact_mirror(nfft);
-  rc = launch_prep_window(ctx, window, frame_length, nfft, scaling, sampling_rate, fast ? 0.5f : 1.0f, 0,
-                          ctx->d_coef, st);
-  if (rc) return rc;
+  a.wmul = fast ? 0.5f : 1.0f;  // the split pass' 1/2 rides on the window
 
   if (fast) {
     // staged (TMA) configurations first; each falls back to the general kernel when the call
@@ -894,6 +947,9 @@ int launch_stft(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, 
     }
   }
   if (a.mel_out) return NXS_EUNSUPPORTED;
+  a.wmul = 1.0f;
+  rc = prep_for(ctx, a, (int)nfft, st);
+  if (rc) return rc;
   float2* tab = nullptr;
   rc = get_dft_table(ctx, nfft, -1, &tab);
   if (rc) return rc;

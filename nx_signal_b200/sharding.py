@@ -66,3 +66,81 @@ def broadcast_coeffs(tensor, src: int = 0):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.broadcast(tensor, src=src)
     return tensor
+
+
+# ---- the C ABI's own NCCL communicator ---------------------------------------------------------
+# nxs_bcast_coeffs_dev takes an ncclComm_t.  One process per GPU: rank 0 creates an ncclUniqueId,
+# the id travels over the already-initialised torch.distributed group (any backend), and every rank
+# joins with ncclCommInitRank on torch's bundled libnccl -- the library itself has no link-time
+# NCCL dependency.
+
+def _libnccl():
+    import ctypes as C
+    import glob
+    import os
+
+    import torch  # noqa: F401  (loads its bundled libnccl into the process)
+
+    for name in ("libnccl.so.2", "libnccl.so"):
+        try:
+            return C.CDLL(name, mode=C.RTLD_GLOBAL)
+        except OSError:
+            continue
+    import nvidia.nccl  # type: ignore
+
+    path = glob.glob(os.path.join(os.path.dirname(nvidia.nccl.__file__), "lib", "libnccl.so*"))[0]
+    return C.CDLL(path, mode=C.RTLD_GLOBAL)
+
+
+class NcclComm:
+    """ncclComm_t of this rank, created through ncclGetUniqueId / ncclCommInitRank."""
+
+    def __init__(self, rank: int, world: int, device: int):
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+
+        class UniqueId(C.Structure):
+            _fields_ = [("internal", C.c_byte * 128)]
+
+        self._nccl = _libnccl()
+        uid = UniqueId()
+        if rank == 0:
+            rc = self._nccl.ncclGetUniqueId(C.byref(uid))
+            if rc != 0:
+                raise RuntimeError(f"ncclGetUniqueId failed: {rc}")
+        box = [bytes(uid.internal) if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        C.memmove(C.byref(uid), box[0], 128)
+        self._nccl.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, UniqueId, C.c_int]
+        self.comm = C.c_void_p()
+        with torch.cuda.device(device):
+            rc = self._nccl.ncclCommInitRank(C.byref(self.comm), world, uid, rank)
+        if rc != 0:
+            raise RuntimeError(f"ncclCommInitRank failed: {rc}")
+        self.rank, self.world = rank, world
+
+    def destroy(self):
+        import ctypes as C
+
+        if self.comm:
+            self._nccl.ncclCommDestroy.argtypes = [C.c_void_p]
+            self._nccl.ncclCommDestroy(self.comm)
+            self.comm = None
+
+
+def broadcast_coeffs_c_abi(comm: "NcclComm", tensor, device: int, src: int = 0):
+    """The path's single collective through the C ABI (nxs_bcast_coeffs_dev): `tensor` is a CUDA f32
+    tensor on every rank; after the call all ranks hold rank `src`'s values."""
+    import ctypes as C
+
+    import torch
+
+    from . import _lib
+
+    ctx = _lib.context(device)
+    st = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    rc = _lib.lib().nxs_bcast_coeffs_dev(ctx, comm.comm, C.c_void_p(tensor.data_ptr()), tensor.numel(), src, st)
+    _lib.check(rc, ctx, "nxs_bcast_coeffs_dev")
+    return tensor
