@@ -35,6 +35,7 @@ struct FirArgs {
   FastDiv div_ppc;  // tile / pairs_per_channel without the emulated division (twice per block pair per thread)
   int total_tiles;
   const float2* H;  // [F], already divided by F
+  const float2* PQ = nullptr;  // fir_ols_r2c_kernel: P[N] then Q[N] (fir_pq_kernel), already divided by N
   const float2* tw;
   int accumulate = 0;  // 1: y += result (later partitions of a long filter)
 };
@@ -314,6 +315,237 @@ __global__ void __launch_bounds__(THREADS, MINB) fir_ols_pg_kernel(const FirArgs
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Real-packed overlap-save (the hot path for K > 513).  The two kernels above spend one complex
+// FFT of F points on two real blocks and keep F - K + 1 outputs of each: at F = 4096, K = 2049 half
+// of every inverse transform is thrown away.  Here ONE real block of 2N samples is packed as N
+// complex points z[i] = x[2i] + i x[2i+1] (the same N = 4096-point engine, the same registers), so a
+// block keeps 2N - K + 1 = 6144 outputs instead of 2 x 2048 for the same two transforms.  The
+// spectral multiply becomes "widely linear": with He / Ho the N-point DFTs of the even / odd taps,
+//     Z'[k] = P[k] Z[k] + Q[k] conj(Z[N - k]),
+//     P = He + (i/2)(1 - e^{-2 pi i k / N}) Ho,   Q = (i/2)(1 + e^{-2 pi i k / N}) Ho
+// (the polyphase form ye = he * xe + z^-1 ho * xo, yo = ho * xe + he * xo written on the packed
+// spectra), and the inverse transform of Z' is the circular convolution, packed the same way.  No
+// split passes: two complex multiply-adds per bin and one exchange for conj(Z[N - k]).
+// Per block 2 FFTs + 8 flops per bin for 6144 outputs: ~28 % fewer instructions per output sample
+// than the pair kernel (cfg4: 64 ch x 600 s, K = 2049).
+// The group's exchange buffer doubles as its TMA stage: the kernel is issue-bound with three groups
+// per SM, so a group waiting ~1 us for its own block costs nothing while the others compute.
+// ------------------------------------------------------------------------------------------
+// P / Q tables in double: one warp per bin k < N; tab[m] = exp(+2 pi i m / N) (get_dft_table_f64)
+__global__ void __launch_bounds__(256) fir_pq_kernel(const float* __restrict__ taps, int K, int N,
+                                                     const double2* __restrict__ tab, float2* __restrict__ PQ) {
+  const int lane = threadIdx.x & 31;
+  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (k >= N) return;
+  double er = 0.0, ei = 0.0, orr = 0.0, oi = 0.0;
+  // tap j = 2 m (+1) contributes h[j] e^{-2 pi i m k / N}
+  const int M2 = (K + 1) / 2;
+  int idx = (int)(((int64_t)lane * k) % N);
+  const int step = (int)(((int64_t)32 * k) % N);
+  for (int m = lane; m < M2; m += 32) {
+    const double2 e = tab[idx];
+    const double h0 = (double)taps[2 * m];
+    const double h1 = 2 * m + 1 < K ? (double)taps[2 * m + 1] : 0.0;
+    er += h0 * e.x;
+    ei -= h0 * e.y;
+    orr += h1 * e.x;
+    oi -= h1 * e.y;
+    idx += step;
+    if (idx >= N) idx -= N;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    er += __shfl_xor_sync(0xffffffffu, er, o);
+    ei += __shfl_xor_sync(0xffffffffu, ei, o);
+    orr += __shfl_xor_sync(0xffffffffu, orr, o);
+    oi += __shfl_xor_sync(0xffffffffu, oi, o);
+  }
+  if (lane == 0) {
+    const double2 w = tab[k];  // e^{+i theta}; e^{-i theta} = (w.x, -w.y)
+    // a = (i/2)(1 - e^{-i theta}) = (i/2)(1 - w.x + i w.y) = (-w.y/2, (1 - w.x)/2);  b = (i/2)(1 + e^{-i theta}) = (w.y/2, (1 + w.x)/2)
+    const double ar = -0.5 * w.y, ai = 0.5 * (1.0 - w.x), br = 0.5 * w.y, bi = 0.5 * (1.0 + w.x);
+    const double pr = er + ar * orr - ai * oi, pi = ei + ar * oi + ai * orr;
+    const double qr = br * orr - bi * oi, qi = br * oi + bi * orr;
+    PQ[k] = make_float2((float)(pr / N), (float)(pi / N));
+    PQ[N + k] = make_float2((float)(qr / N), (float)(qi / N));
+  }
+}
+
+template <class PL, int THREADS>
+struct FirR2cCfg {
+  static constexpr int N = PL::N, G = THREADS / PL::T;
+  static_assert(size_t(PL::BUF) * sizeof(cpx) >= size_t(2 * N + 8) * sizeof(float), "the exchange buffer must hold a staged block");
+  static constexpr size_t GROUP_BYTES = size_t(PL::BUF) * sizeof(cpx);
+  static constexpr size_t PQ_OFF = size_t(G) * GROUP_BYTES;
+  static constexpr size_t TW_OFF = PQ_OFF + size_t(2 * N) * sizeof(cpx);
+  static constexpr size_t BAR_OFF = TW_OFF + size_t(PL::TWC_TOTAL) * sizeof(cpx);
+  static constexpr size_t SMEM = BAR_OFF + 8 * size_t(G) + 8;
+};
+
+template <class PL, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) fir_ols_r2c_kernel(const FirArgs a, const int aligned_rows) {
+  using CF = FirR2cCfg<PL, THREADS>;
+  constexpr int N = PL::N, F2 = 2 * N, T = PL::T, P = PL::P, G = CF::G;
+  constexpr int R0 = PL::R(0), B0 = P / R0;
+  constexpr int RL = PL::R(PL::NP - 1);
+  static_assert(R0 == RL, "FIR plans must be palindromic (first radix == last radix)");
+  static_assert(T >= 32, "per-group barriers need whole warps");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tid = threadIdx.x, g = tid / T, t = tid % T;
+  cpx* const xbuf = reinterpret_cast<cpx*>(smem_raw + size_t(g) * CF::GROUP_BYTES);
+  float* const stage = reinterpret_cast<float*>(xbuf);  // the block's 2N samples land where the exchanges happen later
+  const cpx* const Ps = reinterpret_cast<const cpx*>(smem_raw + CF::PQ_OFF);
+  const cpx* const Qs = Ps + N;
+  cpx* const twsm = reinterpret_cast<cpx*>(smem_raw + CF::TW_OFF);
+  const uint32_t mybar = smem_u32(smem_raw + CF::BAR_OFF) + 8 * g;
+  {
+    cpx* pq = reinterpret_cast<cpx*>(smem_raw + CF::PQ_OFF);
+    for (int i = tid; i < 2 * N; i += THREADS) pq[i] = a.PQ[i];
+  }
+  for (int i = tid; i < PL::TWC_TOTAL; i += THREADS) twsm[i] = a.tw[i];
+  if (tid == 0) {
+    for (int i = 0; i < G; ++i) mbar_init(smem_u32(smem_raw + CF::BAR_OFF) + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  TwDeriveC<PL> tw;
+  tw.init(twsm, t);
+  const GroupSync<T> sync{1 + g};
+  const int K1 = a.K - 1;
+
+  // geometry of a block; returns whether its 2N-sample span can be staged by TMA (copied from the
+  // 16-byte boundary at or below it; the frame then sits at a 0..3 sample offset inside the stage)
+  auto geom = [&](int tile, int& c, int64_t& n0, int64_t& s0a, int& off, uint32_t& bytes) {
+    c = a.div_ppc.div(tile);
+    const int bi = tile - c * a.pairs_per_channel;
+    n0 = (a.b_lo + (int64_t)bi) * a.V;  // first full-convolution index the block produces
+    const int64_t s0 = n0 - K1;
+    s0a = s0 & ~(int64_t)3;
+    off = (int)(s0 - s0a);
+    const int len4 = (off + F2 + 3) & ~3;
+    bytes = (uint32_t)len4 * (uint32_t)sizeof(float);
+    return aligned_rows && s0a >= 0 && s0a + len4 <= a.L;
+  };
+  auto issue = [&](int tile) {
+    int c, off;
+    int64_t n0, s0a;
+    uint32_t bytes;
+    if (geom(tile, c, n0, s0a, off, bytes)) {
+      // the buffer was last written by this group's generic-proxy stores (the inverse transform's
+      // exchanges): order them before the bulk copy's async-proxy writes
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(mybar, bytes);
+      tma_load_1d(smem_u32(stage), a.x + (int64_t)c * a.x_ld + s0a, bytes, mybar);
+    }
+  };
+
+  const int gid = blockIdx.x * G + g, ngroups = gridDim.x * G;
+  uint32_t parity = 0;
+  int tile = gid;
+  if (tile < a.total_tiles && t == 0) issue(tile);
+  for (; tile < a.total_tiles; tile += ngroups) {
+    int c, off;
+    int64_t n0, s0a;
+    uint32_t bytes;
+    const bool staged = geom(tile, c, n0, s0a, off, bytes);
+    cpx v[P];
+    if (staged) {
+      mbar_wait(mybar, parity);
+      parity ^= 1;
+      if (!(off & 1)) {
+        const float2* __restrict__ p2 = reinterpret_cast<const float2*>(stage + off);
+#pragma unroll
+        for (int b = 0; b < B0; ++b)
+#pragma unroll
+          for (int q = 0; q < R0; ++q) v[b * R0 + q] = p2[fft_in_index<PL>(t, b, q)];
+      } else {  // odd sample offset: the (even, odd) pairs are not 8-byte aligned in the stage
+        const float* __restrict__ p1 = stage + off;
+#pragma unroll
+        for (int b = 0; b < B0; ++b)
+#pragma unroll
+          for (int q = 0; q < R0; ++q) {
+            const int i = fft_in_index<PL>(t, b, q);
+            v[b * R0 + q] = make_float2(p1[2 * i], p1[2 * i + 1]);
+          }
+      }
+    } else {
+      const float* __restrict__ xrow = a.x + (int64_t)c * a.x_ld;
+      const int64_t s0 = n0 - K1;
+#pragma unroll
+      for (int b = 0; b < B0; ++b)
+#pragma unroll
+        for (int q = 0; q < R0; ++q) {
+          const int64_t i0 = s0 + 2 * fft_in_index<PL>(t, b, q), i1 = i0 + 1;
+          float re = 0.f, im = 0.f;
+          if (i0 >= 0 && i0 < a.L) re = __ldg(xrow + i0);
+          if (i1 >= 0 && i1 < a.L) im = __ldg(xrow + i1);
+          v[b * R0 + q] = make_float2(re, im);
+        }
+    }
+    sync();  // the staged block is in registers
+    block_fft_single<PL>(v, t, xbuf, tw, sync);
+    sync();  // last pass's reads done before Z overwrites the buffer
+#pragma unroll
+    for (int b = 0; b < B0; ++b)
+#pragma unroll
+      for (int q = 0; q < R0; ++q) xbuf[fft_out_index<PL>(t, b, q)] = v[fft_out_reg<PL>(b, q)];
+    sync();
+    // Z'[k] = P[k] Z[k] + Q[k] conj(Z[N - k]); palindromic plan: output register (b, q) is input register (b, q)
+    cpx u[P];
+#pragma unroll
+    for (int b = 0; b < B0; ++b)
+#pragma unroll
+      for (int q = 0; q < R0; ++q) {
+        const int k = fft_out_index<PL>(t, b, q);
+        const cpx A = v[fft_out_reg<PL>(b, q)];
+        const cpx Bc = cconj(xbuf[(N - k) & (N - 1)]);
+        const cpx pk = Ps[k], qk = Qs[k];
+        const float yr = fmaf(pk.x, A.x, fmaf(-pk.y, A.y, fmaf(qk.x, Bc.x, -qk.y * Bc.y)));
+        const float yi = fmaf(pk.x, A.y, fmaf(pk.y, A.x, fmaf(qk.x, Bc.y, qk.y * Bc.x)));
+        u[b * R0 + q] = make_float2(yi, yr);  // swap for the inverse transform
+      }
+    sync();  // every partner read done before the inverse transform's exchanges
+    block_fft_single<PL>(u, t, xbuf, tw, sync);
+    sync();  // the buffer is free: stage the group's next block while this one is stored
+    if (t == 0 && tile + ngroups < a.total_tiles) issue(tile + ngroups);
+    // sample n of the block sits in u at pair i = n / 2: (swap identity) .y = even sample, .x = odd sample
+    float* __restrict__ yrow = a.y + (int64_t)c * a.y_ld;
+    const int64_t obase = n0 - K1 - a.start;  // output index of block sample n is obase + n
+    const bool interior = obase + K1 >= 0 && obase + F2 <= a.out_len;
+    if (interior && !(K1 & 1) && ((reinterpret_cast<uintptr_t>(yrow + obase) & 7) == 0)) {
+      float2* __restrict__ y2 = reinterpret_cast<float2*>(yrow + obase);
+#pragma unroll
+      for (int b = 0; b < B0; ++b)
+#pragma unroll
+        for (int q = 0; q < R0; ++q) {
+          const int i = fft_out_index<PL>(t, b, q);
+          if (2 * i >= K1) {
+            const cpx r = u[fft_out_reg<PL>(b, q)];
+            float2 o = make_float2(r.y, r.x);
+            if (a.accumulate) {
+              const float2 old = y2[i];
+              o.x += old.x;
+              o.y += old.y;
+            }
+            __stcs(y2 + i, o);
+          }
+        }
+    } else {
+#pragma unroll
+      for (int b = 0; b < B0; ++b)
+#pragma unroll
+        for (int q = 0; q < R0; ++q) {
+          const int i = fft_out_index<PL>(t, b, q);
+          const cpx r = u[fft_out_reg<PL>(b, q)];
+          const int64_t o0 = obase + 2 * i, o1 = o0 + 1;
+          if (2 * i >= K1 && o0 >= 0 && o0 < a.out_len) __stcs(yrow + o0, a.accumulate ? r.y + yrow[o0] : r.y);
+          if (2 * i + 1 >= K1 && o1 >= 0 && o1 < a.out_len) __stcs(yrow + o1, a.accumulate ? r.x + yrow[o1] : r.x);
+        }
+    }
+  }
+}
+
 template <class PL>
 static int fir_tw_table(nxs_ctx* ctx, float2** out) {
   const uint64_t key = (uint64_t(PL::N) << 32) | (uint64_t(PL::T) << 8) | uint64_t(PL::NP) | (uint64_t(2) << 62) |
@@ -443,6 +675,53 @@ static int run_fir_pg(nxs_ctx* ctx, FirArgs a, int64_t channels, const float* ta
   return NXS_OK;
 }
 
+template <class PL, int THREADS, int MINB>
+static int run_fir_r2c(nxs_ctx* ctx, FirArgs a, int64_t channels, const float* taps, cudaStream_t st) {
+  using CF = FirR2cCfg<PL, THREADS>;
+  constexpr int N = PL::N;
+  float2* tw = nullptr;
+  int rc = fir_twc_table<PL>(ctx, &tw);
+  if (rc) return rc;
+  a.tw = tw;
+  rc = ensure_scratch(ctx, size_t(2 * N) * sizeof(float2));
+  if (rc) return rc;
+  double2* tab = nullptr;
+  rc = get_dft_table_f64(ctx, N, &tab);
+  if (rc) return rc;
+  fir_pq_kernel<<<(N + 7) / 8, 256, 0, st>>>(taps, a.K, N, tab, (float2*)ctx->d_scratch);
+  ctx->launches++;
+  NXS_CUDA(ctx, cudaGetLastError());
+  a.PQ = (const float2*)ctx->d_scratch;
+  a.V = 2 * N - a.K + 1;
+  if (a.start + a.out_len <= 0) return NXS_OK;
+  a.b_lo = (a.start > 0 ? a.start : 0) / a.V;
+  const int64_t b_hi = (a.start + a.out_len - 1) / a.V;
+  const int64_t blocks = b_hi - a.b_lo + 1;
+  const int64_t tiles = blocks * channels;
+  if (tiles >= (int64_t(1) << 31)) return NXS_EUNSUPPORTED;
+  a.pairs_per_channel = (int)blocks;  // one block per tile here
+  a.div_ppc = FastDiv((int)blocks);
+  a.total_tiles = (int)tiles;
+  auto kern = fir_ols_r2c_kernel<PL, THREADS, MINB>;
+  const size_t smem = CF::SMEM;
+  static_assert(CF::SMEM <= 232448, "fir_ols_r2c_kernel: shared memory");
+  static int attr_done[16] = {0};
+  if (!attr_done[ctx->device & 15]) {
+    NXS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done[ctx->device & 15] = 1;
+  }
+  int64_t grid = int64_t(ctx->sm_count) * MINB;
+  const int64_t need = (tiles + CF::G - 1) / CF::G;
+  if (grid > need) grid = need;
+  const int aligned_rows = (reinterpret_cast<uintptr_t>(a.x) & 15) == 0 && a.x_ld % 4 == 0;
+  prof_begin(ctx, st);
+  kern<<<(unsigned)grid, THREADS, smem, st>>>(a, aligned_rows);
+  prof_end(ctx, st);
+  ctx->launches++;
+  NXS_CUDA(ctx, cudaGetLastError());
+  return NXS_OK;
+}
+
 // short filters / very long filters: direct summation, one thread per output (fp32 FMA chain in
 // ascending tap order)
 __global__ void __launch_bounds__(256) fir_direct_kernel(const float* __restrict__ x, int64_t channels, int64_t L,
@@ -498,6 +777,35 @@ int launch_fir(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, i
     if (pg) return run_fir_pg<Plan<1024, 64, 8, 16, 8>, 384, 2>(ctx, a, channels, taps, st);
     return run_fir<Plan<1024, 64, 8, 16, 8>, 256, 2>(ctx, a, channels, taps, st);
   }
+  if (K > 513 && pg && variant != 1 && variant != 3) {
+    // real-packed overlap-save: one 8192-sample real block per 4096-point transform pair, V = 8193 - KP
+    // outputs kept; long filters are cut into n equal runs of KP taps whose partial convolutions are
+    // accumulated, y[n] += (x * h_p)[n - p KP] (work per output ~ n / (8193 - K / n); later passes
+    // read-modify-write y)
+    using PL = Plan<4096, 256, 16, 16, 16>;
+    int64_t n_best = 1;
+    double c_best = 1e300;
+    for (int64_t n = 1; n <= (K + 1023) / 1024; ++n) {
+      const int64_t kp = (K + n - 1) / n;
+      if (kp > 7169) continue;
+      const double c = (double(n) + 0.15 * double(n - 1)) / double(8193 - kp);
+      if (c < c_best) {
+        c_best = c;
+        n_best = n;
+      }
+    }
+    const int64_t KP = (K + n_best - 1) / n_best;
+    for (int64_t p = 0; p * KP < K; ++p) {
+      FirArgs ap = a;
+      ap.K = (int)(K - p * KP < KP ? K - p * KP : KP);
+      ap.start = a.start - p * KP;
+      ap.accumulate = p > 0;
+      rc = variant == 4 ? run_fir_r2c<PL, 512, 1>(ctx, ap, channels, taps + p * KP, st)
+                        : run_fir_r2c<PL, 768, 1>(ctx, ap, channels, taps + p * KP, st);
+      if (rc) return rc;
+    }
+    return NXS_OK;
+  }
   if (K > 513 && (K <= 3585 || pg)) {
     using PL = Plan<4096, 256, 16, 16, 16>;
     if (!pg) return run_fir<PL, 256, 2>(ctx, a, channels, taps, st);
@@ -523,7 +831,7 @@ int launch_fir(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, i
       ap.start = a.start - p * KP;
       ap.accumulate = p > 0;
       // three groups per SM when the stage (V + F samples) is small enough, else two
-      const bool three = variant != 1 && FirPgCfg<PL, 768>::smem(int(4096 - ap.K + 1)) <= 232448;
+      const bool three = variant != 1 && FirPgCfg<PL, 768>::smem(int(4096 - ap.K + 1)) <= 232448;  // variant 3: the pair kernel, three groups
       rc = three ? run_fir_pg<PL, 768, 1>(ctx, ap, channels, taps + p * KP, st)
                  : run_fir_pg<PL, 512, 1>(ctx, ap, channels, taps + p * KP, st);
       if (rc) return rc;
