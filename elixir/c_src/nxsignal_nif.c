@@ -131,7 +131,7 @@ static ERL_NIF_TERM ctx_create(ErlNifEnv* env, int argc, const ERL_NIF_TERM argv
 
 /* ---- stft(ctx, x_bin, channels, length, window_bin, hop, fft_length, pad_mode, pad_lo, pad_hi, scaling, sr)
  * NxSignal.stft/3, lib/nx_signal.ex:68-130 -> {:ok, z, times, frequencies, num_frames} */
-static ERL_NIF_TERM stft(ErlNifEnv* env, int argc, const ERL_NIF_TERM argv[]) {
+static ERL_NIF_TERM stft_common(ErlNifEnv* env, int argc, const ERL_NIF_TERM argv[], int cplx) {
   ctx_res* r;
   ErlNifBinary x, w;
   int64_t ch, len, hop, nfft, lo, hi, frames = 0, xb, zb;
@@ -145,7 +145,7 @@ static ERL_NIF_TERM stft(ErlNifEnv* env, int argc, const ERL_NIF_TERM argv[]) {
     return enif_make_badarg(env);
   const int64_t n = (int64_t)(w.size / sizeof(float));
   if (n < 1 || w.size != (size_t)n * sizeof(float) || hop < 1 || nfft < 1) return mk_error(env, NXS_ESHAPE);
-  if (!bytes3(ch, len, 1, sizeof(float), &xb) || (int64_t)x.size != xb) return mk_error(env, NXS_ESHAPE);
+  if (!bytes3(ch, len, 1, (cplx ? 2 : 1) * sizeof(float), &xb) || (int64_t)x.size != xb) return mk_error(env, NXS_ESHAPE);
   int rc = nxs_num_frames(len, n, hop, pad, lo, hi, &frames);
   if (rc) return mk_error(env, rc);
   if (!bytes3(ch, frames, nfft, 2 * sizeof(float), &zb)) return mk_error(env, NXS_ESHAPE); /* no frame fits, or too large */
@@ -154,13 +154,23 @@ static ERL_NIF_TERM stft(ErlNifEnv* env, int argc, const ERL_NIF_TERM argv[]) {
   float* times = (float*)enif_make_new_binary(env, (size_t)frames * sizeof(float), &tt);
   float* freqs = (float*)enif_make_new_binary(env, (size_t)nfft * sizeof(float), &ft);
   LOCK(r);
-  rc = nxs_stft_f32_host(r->ctx, (const float*)x.data, ch, len, len, (const float*)w.data, n, hop, nfft, pad, lo,
-                         hi, scal, sr, z);
+  rc = cplx ? nxs_stft_c64_host(r->ctx, (const float*)x.data, ch, len, len, (const float*)w.data, n, hop, nfft, pad,
+                                lo, hi, scal, sr, z)
+            : nxs_stft_f32_host(r->ctx, (const float*)x.data, ch, len, len, (const float*)w.data, n, hop, nfft, pad,
+                                lo, hi, scal, sr, z);
   UNLOCK(r);
   if (!rc) rc = nxs_stft_times_f32(n, sr, frames, times);
   if (!rc) rc = nxs_fft_frequencies_f32(sr, nfft, freqs);
   if (rc) return mk_error(env, rc);
   return enif_make_tuple5(env, enif_make_atom(env, "ok"), zt, tt, ft, enif_make_int64(env, frames));
+}
+
+static ERL_NIF_TERM stft(ErlNifEnv* env, int argc, const ERL_NIF_TERM argv[]) {
+  return stft_common(env, argc, argv, 0);
+}
+/* the same head on complex data (x_bin holds c64): Nx.multiply(window) -> Nx.fft, lib/nx_signal.ex:101-102 */
+static ERL_NIF_TERM stft_c64(ErlNifEnv* env, int argc, const ERL_NIF_TERM argv[]) {
+  return stft_common(env, argc, argv, 1);
 }
 
 /* shared argument block of istft / istft_c2r:
@@ -545,6 +555,7 @@ static int load(ErlNifEnv* env, void** priv, ERL_NIF_TERM info) {
 static ErlNifFunc funcs[] = {
     {"ctx_create", 1, ctx_create, 0},
     {"stft", 12, stft, ERL_NIF_DIRTY_JOB_IO_BOUND},
+    {"stft_c64", 12, stft_c64, ERL_NIF_DIRTY_JOB_IO_BOUND},
     {"istft", 10, istft, ERL_NIF_DIRTY_JOB_IO_BOUND},
     {"istft_c2r", 10, istft_c2r, ERL_NIF_DIRTY_JOB_IO_BOUND},
     {"fir", 6, fir, ERL_NIF_DIRTY_JOB_IO_BOUND},

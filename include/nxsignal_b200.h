@@ -114,6 +114,9 @@ int nxs_ctx_host_mode(const nxs_ctx* ctx, int* mode);
  * = :is_periodic (ignored by rectangular/bartlett/triangular), beta/eps = kaiser
  * options.  Bit-compatible with Nx.BinaryBackend's per-op f32 rounding. */
 int nxs_window_f32(int kind, int64_t n, int periodic, double beta, double eps, float* out);
+/* the same windows with `type: :f64`: the reference's graph evaluated in double (windows.ex:58,161,
+ * 226,279,342); kaiser keeps the reference's f32 scalars (I0(beta), Nx.Constants.pi()) */
+int nxs_window_f64(int kind, int64_t n, int periodic, double beta, double eps, double* out);
 
 /* NxSignal.Filters.firwin(num_taps, cutoff, opts)  lib/nx_signal/filters.ex:147-252
  * cutoffs in the units of sampling_rate; window_kind one of NXS_WIN_{HAMMING,HANN,
@@ -121,9 +124,15 @@ int nxs_window_f32(int kind, int64_t n, int periodic, double beta, double eps, f
  * three ArgumentError conditions (filters.ex:170-178, 189-193, 274-277). */
 int nxs_firwin_f32(int64_t num_taps, const double* cutoffs, int ncut, int window_kind, double beta,
                    int pass_zero, int scale, double sampling_rate, float* out);
+/* `type: :f64` (filters.ex:153): the same graph in double */
+int nxs_firwin_f64(int64_t num_taps, const double* cutoffs, int ncut, int window_kind, double beta,
+                   int pass_zero, int scale, double sampling_rate, double* out);
 
 /* NxSignal.fft_frequencies(sampling_rate, fft_length: n)  lib/nx_signal.ex:154-166 */
 int nxs_fft_frequencies_f32(double sampling_rate, int64_t fft_length, float* out);
+/* with the head's other options: `endpoint:` (Nx.linspace divides by n - 1 instead of n) and
+ * `type: :f64` (out is double* when is_f64) */
+int nxs_fft_frequencies_ex(double sampling_rate, int64_t fft_length, int endpoint, int is_f64, void* out);
 
 /* NxSignal.mel_filters(fft_length, mel_bins, sampling_rate, max_mel:, mel_frequency_spacing:)
  * lib/nx_signal.ex:397-445 -- out [mel_bins][fft_length] f32, bit-compatible with the
@@ -153,6 +162,17 @@ int nxs_stft_f32_dev(nxs_ctx* ctx, const float* x, int64_t channels, int64_t len
                      int pad_mode, int64_t pad_lo, int64_t pad_hi, int scaling, double sampling_rate,
                      float* z, void* stream);
 int nxs_stft_f32_host(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, int64_t x_ld,
+                      const float* window, int64_t frame_length, int64_t hop, int64_t fft_length,
+                      int pad_mode, int64_t pad_lo, int64_t pad_hi, int scaling, double sampling_rate,
+                      float* z);
+
+/* The same head on COMPLEX data (the reference's graph takes any numeric tensor: Nx.multiply(window) ->
+ * Nx.fft, lib/nx_signal.ex:101-102): x [channels][x_ld] c64 (interleaved), z as above. */
+int nxs_stft_c64_dev(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, int64_t x_ld,
+                     const float* window, int64_t frame_length, int64_t hop, int64_t fft_length,
+                     int pad_mode, int64_t pad_lo, int64_t pad_hi, int scaling, double sampling_rate,
+                     float* z, void* stream);
+int nxs_stft_c64_host(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, int64_t x_ld,
                       const float* window, int64_t frame_length, int64_t hop, int64_t fft_length,
                       int pad_mode, int64_t pad_lo, int64_t pad_hi, int scaling, double sampling_rate,
                       float* z);

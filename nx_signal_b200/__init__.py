@@ -78,10 +78,14 @@ def _num_frames(length, window_length, stride, mode, lo, hi):
 
 
 def fft_frequencies(sampling_rate, fft_length, type="f32", name="frequencies", endpoint=False):
-    """NxSignal.fft_frequencies/2 (lib/nx_signal.ex:154-166): f32 [fft_length]."""
-    out = np.empty(int(fft_length), dtype=np.float32)
-    _lib.check(_lib.lib().nxs_fft_frequencies_f32(float(sampling_rate), int(fft_length), out.ctypes.data),
-               what="fft_frequencies")
+    """NxSignal.fft_frequencies/2 (lib/nx_signal.ex:154-166): [fft_length] of `type` ("f32" | "f64");
+    `endpoint` is forwarded to the reference's Nx.linspace (divide by n - 1 instead of n)."""
+    f64 = type in ("f64", np.float64)
+    if not f64 and type not in ("f32", np.float32):
+        raise NotImplementedError(f"fft_frequencies: type {type!r} is not supported by this backend (f32, f64)")
+    out = np.empty(int(fft_length), dtype=np.float64 if f64 else np.float32)
+    _lib.check(_lib.lib().nxs_fft_frequencies_ex(float(sampling_rate), int(fft_length), int(bool(endpoint)), int(f64),
+                                                 out.ctypes.data), what="fft_frequencies")
     return out
 
 
@@ -111,7 +115,9 @@ def stft(data, window, overlap_length=None, fft_length="power_of_two", window_pa
     if sampling_rate is None:
         raise NxSignalArgumentError("missing sampling_rate option")
     scale = _scaling_code(scaling)
-    x = A.to_real_f32(data, "data")
+    # complex `data` is a complex transform in the reference's graph (Nx.multiply -> Nx.fft, :101-102)
+    cplx = (data.is_complex() if A.is_torch(data) else np.iscomplexobj(np.asarray(data)))
+    x = A.to_c64(data) if cplx else A.to_real_f32(data, "data")
     w = A.like_device(x, A.to_real_f32(window, "window"))
     if w.ndim != 1:
         raise NxSignalArgumentError("window must be a rank-1 tensor")
@@ -127,6 +133,19 @@ def stft(data, window, overlap_length=None, fft_length="power_of_two", window_pa
     batch_shape = tuple(x.shape[:-1])
     Cn = int(np.prod(batch_shape, dtype=np.int64)) if batch_shape else 1
     M = _num_frames(L, N, hop, mode, lo, hi)
+    if cplx:
+        if onesided:
+            raise NxSignalArgumentError("onesided=True needs real data (a complex signal's spectrum has no mirror symmetry)")
+        z = A.empty_like_kind(x, batch_shape + (M, nfft), "c64")
+        if M > 0 and Cn > 0:
+            ctx = _lib.context(A.device_index(x))
+            args = (Cn, L, L, A.ptr(w), N, hop, nfft, mode, lo, hi, scale, float(sampling_rate), A.ptr(z))
+            if A.is_cuda(x):
+                rc = _lib.lib().nxs_stft_c64_dev(ctx, A.ptr(x), *args, A.stream_of(x))
+            else:
+                rc = _lib.lib().nxs_stft_c64_host(ctx, A.ptr(x), *args)
+            _lib.check(rc, ctx, "stft")
+        return z, A.from_host(x, stft_times(N, sampling_rate, M)), A.from_host(x, fft_frequencies(sampling_rate, nfft))
     if onesided and not A.is_cuda(x):
         raise NotImplementedError("onesided=True takes CUDA tensors (the host entry already moves the one-sided "
                                   "form over PCIe and returns the reference's two-sided result)")

@@ -59,6 +59,19 @@ def like_device(x, arr):
     return np.ascontiguousarray(arr, dtype=np.float32)
 
 
+def move_like(x, arr):
+    """arr (numpy or torch, any dtype) moved next to x, dtype unchanged."""
+    if is_cuda(x):
+        import torch
+
+        if is_torch(arr):
+            return arr.to(x.device).contiguous()
+        return torch.from_numpy(np.ascontiguousarray(arr)).to(x.device)
+    if is_torch(arr):
+        return np.ascontiguousarray(arr.detach().cpu().numpy())
+    return np.ascontiguousarray(arr)
+
+
 def empty_like_kind(x, shape, dtype):
     """dtype in {'f32','c64', np dtype}; allocates where x lives."""
     if is_cuda(x):

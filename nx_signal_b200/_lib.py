@@ -42,6 +42,9 @@ SIGNATURES = {
     "nxs_ctx_set_host_mode": (i32, [vp, i32]),
     "nxs_ctx_host_mode": (i32, [vp, C.POINTER(i32)]),
     "nxs_window_f32": (i32, [i32, i64, i32, f64, f64, vp]),
+    "nxs_window_f64": (i32, [i32, i64, i32, f64, f64, vp]),
+    "nxs_firwin_f64": (i32, [i64, C.POINTER(f64), i32, i32, f64, i32, i32, f64, vp]),
+    "nxs_fft_frequencies_ex": (i32, [f64, i64, i32, i32, vp]),
     "nxs_firwin_f32": (i32, [i64, C.POINTER(f64), i32, i32, f64, i32, i32, f64, vp]),
     "nxs_fft_frequencies_f32": (i32, [f64, i64, vp]),
     "nxs_mel_filters_f32": (i32, [i64, i64, f64, f64, f64, vp]),
@@ -52,6 +55,8 @@ SIGNATURES = {
     "nxs_stft_times_f32": (i32, [i64, f64, i64, vp]),
     "nxs_num_frames": (i32, [i64, i64, i64, i32, i64, i64, C.POINTER(i64)]),
     "nxs_stft_f32_dev": (i32, [vp, vp, i64, i64, i64, vp, i64, i64, i64, i32, i64, i64, i32, f64, vp, vp]),
+    "nxs_stft_c64_dev": (i32, [vp, vp, i64, i64, i64, vp, i64, i64, i64, i32, i64, i64, i32, f64, vp, vp]),
+    "nxs_stft_c64_host": (i32, [vp, vp, i64, i64, i64, vp, i64, i64, i64, i32, i64, i64, i32, f64, vp]),
     "nxs_stft_onesided_f32_dev": (i32, [vp, vp, i64, i64, i64, vp, i64, i64, i64, i32, i64, i64, i32, f64, vp, i64, vp]),
     "nxs_stft_f32_host": (i32, [vp, vp, i64, i64, i64, vp, i64, i64, i64, i32, i64, i64, i32, f64, vp]),
     "nxs_istft_c64_dev": (i32, [vp, vp, i64, i64, i64, vp, i64, i64, i64, i32, f64, vp, vp]),

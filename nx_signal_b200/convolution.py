@@ -54,7 +54,7 @@ def convolve(in1, in2, mode="full", method="direct"):
     b = in2 if A.is_torch(in2) else np.asarray(in2)
     rank = _ranks(a, b, method == "fft")
     if rank > 3:
-        raise NotImplementedError("convolve: rank > 3 is not supported by this backend")
+        return _batched_high_rank(a, b, mode, method, rank)
     sa = (1,) * (3 - a.ndim) + tuple(int(s) for s in a.shape)
     sb = (1,) * (3 - b.ndim) + tuple(int(s) for s in b.shape)
     if mode == "valid":
@@ -69,6 +69,26 @@ def convolve(in1, in2, mode="full", method="direct"):
             and A.is_cuda(a) == A.is_cuda(b)):
         return _fir(a, b, sa, sb, mode, rank)
     return _direct(a, b, sa, sb, cplx, mode, rank)
+
+
+def _batched_high_rank(a, b, mode, method, rank):
+    """rank > 3 (the reference's direct_convolve is rank-generic, convolution.ex:95-211): served when every
+    axis of in2 before its last three has size 1 -- those axes are batch axes of in1 (a size-1 kernel axis
+    leaves the axis unchanged in all three modes), so the leading axes fold and each slice is a 3-d problem."""
+    lead_a, lead_b = tuple(a.shape[:-3]), tuple(b.shape[:-3])
+    if any(d != 1 for d in lead_b):
+        raise NotImplementedError("convolve: rank > 3 needs size-1 leading axes on in2 (true > 3-d kernels are not "
+                                  "supported by this backend)")
+    b3 = b.reshape(tuple(b.shape[-3:]))
+    a4 = a.reshape((-1,) + tuple(a.shape[-3:]))
+    outs = [convolve(a4[i], b3, mode=mode, method=method) for i in range(a4.shape[0])]
+    if A.is_torch(outs[0]):
+        import torch
+
+        y = torch.stack(outs, dim=0)
+    else:
+        y = np.stack(outs, axis=0)
+    return y.reshape(lead_a + tuple(y.shape[1:]))
 
 
 def correlate(in1, in2, mode="full", method="direct"):
@@ -122,8 +142,8 @@ def _direct(a, b, sa, sb, cplx, mode, rank):
         xa, xb = A.to_c64(a), A.to_c64(b)
     else:
         xa, xb = A.to_real_f32(a), A.to_real_f32(b)
-    if A.is_cuda(xa) != A.is_cuda(xb):
-        xb = A.like_device(xa, xb) if not cplx else (xb.to(xa.device) if A.is_torch(xb) else xb)
+    if A.is_cuda(xa) != A.is_cuda(xb) or A.is_torch(xa) != A.is_torch(xb):
+        xb = A.move_like(xa, xb)  # operands of either family (numpy / torch, host / device) end up next to in1
     os_ = _out_shape(sa, sb, mode)
     out = A.empty_like_kind(xa, os_, "c64" if cplx else "f32")
     ctx = _lib.context(A.device_index(xa))

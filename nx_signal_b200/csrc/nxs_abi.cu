@@ -205,6 +205,7 @@ int nxs_ctx_destroy(nxs_ctx* ctx) {
   }
   cudaFree(ctx->d_coef);
   cudaFree(ctx->d_scratch);
+  cudaFree(ctx->d_work);
   cudaFree(ctx->d_stage_in);
   cudaFree(ctx->d_stage_out);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);

@@ -63,6 +63,9 @@ struct nxs_ctx {
   // generic device scratch (FIR spectra, etc.)
   void* d_scratch = nullptr;
   size_t d_scratch_bytes = 0;
+  // work buffer of composite device entries (complex-input STFT: real planes + their spectra)
+  void* d_work = nullptr;
+  size_t d_work_bytes = 0;
   // staging for the _host entry points
   void* h_pinned = nullptr;
   size_t h_pinned_bytes = 0;
@@ -171,6 +174,10 @@ int launch_stft(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, 
 // true when launch_stft serves fft_length with a kernel whose upper half-spectrum is the exact
 // conjugate mirror of the lower half (the r2c kernels; not the generic DFT)
 bool stft_has_exact_mirror(int64_t fft_length);
+// complex `data` (nxs_cplx.cu): two real-plane transforms and a combine pass
+int launch_stft_c64(nxs_ctx* ctx, const float2* x, int64_t channels, int64_t length, int64_t x_ld,
+                    const float* window, int64_t frame_length, int64_t hop, int64_t fft_length, const PadGeom& g,
+                    int64_t num_frames, int scaling, double sampling_rate, float2* z, cudaStream_t st);
 int launch_istft(nxs_ctx* ctx, const float2* z, int64_t channels, int64_t num_frames, int64_t z_len,
                  const float* window, int64_t frame_length, int64_t hop, int64_t fft_length, int scaling,
                  double sampling_rate, float2* y, cudaStream_t st);

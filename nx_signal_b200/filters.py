@@ -71,7 +71,11 @@ def wiener(t, kernel_size=3, noise=None):
     else:
         rc = _lib.lib().nxs_wiener_host(ctx, A.ptr(x), int(f64), x.ndim, _i64(shape), _i64(ks), has_noise, nz, A.ptr(out))
     _lib.check(rc, ctx, "Filters.wiener")
-    return out
+    # the reference casts the f64 result back to the INPUT's type (filters.ex:108-110): integers truncate
+    if is_t:
+        return out if t.dtype.is_floating_point and out.dtype == t.dtype or t.dtype == torch.float64 else out.to(t.dtype)
+    src = np.asarray(t).dtype
+    return out if src == out.dtype else out.astype(src)
 
 
 def firwin(num_taps, cutoff, window="hamming", pass_zero=True, scale=True, sampling_rate=2.0, type="f32"):
@@ -102,9 +106,11 @@ def firwin(num_taps, cutoff, window="hamming", pass_zero=True, scale=True, sampl
             f"unknown window {window!r}, supported: "
             ":hamming, :hann, :blackman, :bartlett, :rectangular, {:kaiser, beta}")
     cuts = (C.c_double * len(cutoff))(*[float(c) for c in cutoff])
-    out = np.empty(int(num_taps), dtype=np.float32)
-    _lib.check(
-        _lib.lib().nxs_firwin_f32(int(num_taps), cuts, len(cutoff), _lib.WIN[kind], beta, int(bool(pass_zero)),
-                                  int(bool(scale)), float(sampling_rate), out.ctypes.data),
-        what="Filters.firwin")
-    return out if type in ("f32", np.float32) else out.astype(np.float64)
+    f64 = type in ("f64", np.float64)
+    if not f64 and type not in ("f32", np.float32):
+        raise NotImplementedError(f"firwin: type {type!r} is not supported by this backend (f32, f64)")
+    out = np.empty(int(num_taps), dtype=np.float64 if f64 else np.float32)
+    fn = _lib.lib().nxs_firwin_f64 if f64 else _lib.lib().nxs_firwin_f32  # computed in the requested type (filters.ex:153)
+    _lib.check(fn(int(num_taps), cuts, len(cutoff), _lib.WIN[kind], beta, int(bool(pass_zero)), int(bool(scale)),
+                  float(sampling_rate), out.ctypes.data), what="Filters.firwin")
+    return out

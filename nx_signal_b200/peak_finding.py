@@ -28,10 +28,20 @@ def argrelextrema(data, comparator, axis=0, order=1):
     if not -rank <= int(axis) < rank:
         raise _lib.NxSignalArgumentError(f"given axis ({axis}) invalid for shape with rank {rank}")
     axis = int(axis) % rank
-    if int(order) < 1:
-        raise _lib.NxSignalArgumentError(f"order must be a positive integer, got: {order!r}")
+    if int(order) < 0:
+        raise _lib.NxSignalArgumentError(f"order must be a non-negative integer, got: {order!r}")
     shape = tuple(int(s) for s in x.shape)
     total = int(np.prod(shape, dtype=np.int64))
+    if int(order) == 0:
+        # the reference's while loop (peak_finding.ex:354-363) runs no comparison when order = 0: every element
+        # stays marked, so `nonzero` lists all multi-indices in row-major order
+        idx = np.stack(np.unravel_index(np.arange(total), shape), axis=-1).astype(np.int32).reshape(total, rank)
+        if A.is_cuda(x):
+            import torch
+
+            return {"indices": torch.from_numpy(idx).to(x.device),
+                    "valid_indices": torch.tensor(total, dtype=torch.int64, device=x.device)}
+        return {"indices": idx, "valid_indices": np.int64(total)}
     shp = (C.c_int64 * rank)(*shape)
     ctx = _lib.context(A.device_index(x))
     if A.is_cuda(x):
@@ -48,7 +58,7 @@ def argrelextrema(data, comparator, axis=0, order=1):
     rc = _lib.lib().nxs_argrelextrema_f32_host(ctx, A.ptr(x), rank, shp, axis, int(order), _lib.CMP[comparator],
                                                A.ptr(idx), C.byref(cnt))
     _lib.check(rc, ctx, "PeakFinding.argrelextrema")
-    return {"indices": idx, "valid_indices": np.uint32(cnt.value)}
+    return {"indices": idx, "valid_indices": np.int64(cnt.value)}  # one dtype on both paths (int64, like the device entry)
 
 
 def argrelmin(data, axis=0, order=1):

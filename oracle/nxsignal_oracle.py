@@ -44,6 +44,7 @@ Each function cites the reference file:line it follows.
 """
 from __future__ import annotations
 
+import contextlib
 import math
 from typing import Optional, Sequence, Tuple, Union
 
@@ -60,8 +61,29 @@ PI = math.pi
 # ---------------------------------------------------------------------------
 # Nx.BinaryBackend element-wise semantics: compute in double, round once.
 # ---------------------------------------------------------------------------
+# The float type the windows / firwin / fft_frequencies graphs run in: f32 by default; `float_type(F64)`
+# restates the same graphs for `type: :f64` (windows.ex:58,161,226,279,342; filters.ex:153), where every op is
+# plain double arithmetic.  UNPINNED: the reference holds no f64 vector for these functions.
+_FT = F32
+
+
+@contextlib.contextmanager
+def float_type(t):
+    global _FT
+    old, _FT = _FT, t
+    try:
+        yield
+    finally:
+        _FT = old
+
+
 def _f(x):
-    """Round to f32 (the single rounding every f32-typed Nx op performs)."""
+    """Round to the graph's float type (the single rounding every Nx op performs; f32 unless float_type(F64))."""
+    return np.asarray(x, dtype=F64).astype(_FT)
+
+
+def _f32(x):
+    """Round to f32 whatever the graph's type (numbers entering a defn are f32 scalars)."""
     return np.asarray(x, dtype=F64).astype(F32)
 
 
@@ -99,12 +121,12 @@ def _sin(a):
 
 
 def _lit(x):
-    """A float literal in a defn becomes an f32 scalar tensor."""
-    return F32(x)
+    """A float literal in a defn becomes a scalar of the tensor it meets (f32 by default)."""
+    return _FT(x)
 
 
 def _iota(n):
-    return np.arange(n, dtype=F32)
+    return np.arange(n, dtype=_FT)
 
 
 def nx_linspace(start, stop, n, endpoint=True):
@@ -117,9 +139,9 @@ def nx_linspace(start, stop, n, endpoint=True):
     start = _tensor_scalar(start)
     stop = _tensor_scalar(stop)
     div = (n - 1) if endpoint else n
-    diff = _sub(stop, start)
+    diff = _f32(_d(stop) - _d(start))  # start / stop are f32 scalars whatever `type:` is, so the step is an f32 value
     with np.errstate(divide="ignore", invalid="ignore"):
-        step = _div(diff, div)
+        step = _f32(_d(diff) / div)
         return _add(_mul(_iota(n), step), start)
 
 
@@ -147,7 +169,7 @@ def bartlett(n: int):
     right_idx = _add(_iota(n_on_2), left_size)
     left = _div(_mul(left_idx, 2), n)
     right = _sub(2, _div(_mul(right_idx, 2), n))
-    return np.concatenate([left, right]).astype(F32)
+    return np.concatenate([left, right]).astype(_FT)
 
 
 def triangular(n: int):
@@ -156,9 +178,9 @@ def triangular(n: int):
     idx = _add(_iota(n_on_2), 1)
     if n % 2 == 1:
         left = _div(_mul(idx, 2), n + 1)
-        return np.concatenate([left, left[::-1][1:]]).astype(F32)
+        return np.concatenate([left, left[::-1][1:]]).astype(_FT)
     left = _div(_sub(_mul(2, idx), 1), n)
-    return np.concatenate([left, left[::-1]]).astype(F32)
+    return np.concatenate([left, left[::-1]]).astype(_FT)
 
 
 def blackman(n: int, is_periodic: bool = True):
@@ -177,7 +199,7 @@ def blackman(n: int, is_periodic: bool = True):
         w = np.concatenate([left, left[::-1][1:]])
     if is_periodic:
         w = w[:-1]
-    return w.astype(F32)
+    return w.astype(_FT)
 
 
 def hamming(n: int, is_periodic: bool = True):
@@ -186,7 +208,7 @@ def hamming(n: int, is_periodic: bool = True):
     k = _iota(l)
     a = _div(_mul(_lit(2 * PI), k), l - 1)
     w = _sub(_lit(0.54), _mul(_lit(0.46), _cos(a)))
-    return (w[: l - 1] if is_periodic else w).astype(F32)
+    return (w[: l - 1] if is_periodic else w).astype(_FT)
 
 
 def hann(n: int, is_periodic: bool = True):
@@ -195,7 +217,7 @@ def hann(n: int, is_periodic: bool = True):
     k = _iota(l)
     a = _div(_mul(_lit(2 * PI), k), l - 1)
     w = _mul(_lit(0.5), _sub(1, _cos(a)))
-    return (w[: l - 1] if is_periodic else w).astype(F32)
+    return (w[: l - 1] if is_periodic else w).astype(_FT)
 
 
 def _kaiser_i0(x):
@@ -211,20 +233,22 @@ def _kaiser_i0(x):
     )
     with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
         ex = _f(np.exp(_d(ax)))
-        den = _f(np.sqrt(_d(_mul(_lit(2 * PI), ax))))
+        den = _f(np.sqrt(_d(_mul(F32(2 * PI), ax))))  # 2 * Nx.Constants.pi(): pi is an f32 tensor by default
         poly = _add(1, _add(_div(1, _mul(8, ax)), _div(9, _mul(128, p(2)))))
         large = _mul(_div(ex, den), poly)
-    return np.where(ax < F32(3.75), small, large).astype(F32)
+    return np.where(ax < _FT(3.75), small, large).astype(_FT)
 
 
 def kaiser(n: int, beta: float = 12.0, eps: float = 1.0e-7, is_periodic: bool = True):
     """windows.ex:341-369."""
     l = n + 1 if is_periodic else n
     ratio = nx_linspace(-1, 1, l, endpoint=True)
-    sqrt_arg = np.maximum(_sub(1, _f(_d(ratio) ** 2)), _lit(eps)).astype(F32)
+    sqrt_arg = np.maximum(_sub(1, _f(_d(ratio) ** 2)), _lit(eps)).astype(_FT)
     r = _mul(_lit(beta), _f(np.sqrt(_d(sqrt_arg))))
-    w = _div(_kaiser_i0(r), _kaiser_i0(np.array([_lit(beta)], dtype=F32)))
-    return (w[:n] if is_periodic else w).astype(F32)
+    with float_type(F32):  # beta is a number: Nx.abs(beta) is an f32 scalar, so I0(beta) is f32 for any `type`
+        i0b = _kaiser_i0(np.array([F32(beta)], dtype=F32))
+    w = _div(_kaiser_i0(r), i0b)
+    return (w[:n] if is_periodic else w).astype(_FT)
 
 
 # ---------------------------------------------------------------------------
@@ -375,12 +399,12 @@ def as_windowed(x, window_length: int, stride: int = 1, padding: PaddingT = "val
     return xp[..., idx]
 
 
-def fft_frequencies(sampling_rate, fft_length: int):
-    """lib/nx_signal.ex:154-166: step = sr / nfft; linspace(0, step * nfft, n: nfft,
-    endpoint: false), every op an f32 tensor op."""
+def fft_frequencies(sampling_rate, fft_length: int, endpoint: bool = False):
+    """lib/nx_signal.ex:154-166: step = sr / nfft (f32 scalars); linspace(0, step * nfft, n: nfft,
+    endpoint:, type:) -- the iota * step + start part runs in the graph's float type."""
     sr = _tensor_scalar(sampling_rate)
-    step = _div(sr, fft_length)
-    return nx_linspace(0, _mul(step, fft_length), fft_length, endpoint=False)
+    step = _f32(_d(sr) / fft_length)
+    return nx_linspace(0, _f32(_d(step) * fft_length), fft_length, endpoint=endpoint)
 
 
 def stft_times(frame_length: int, sampling_rate, num_frames: int):
@@ -529,7 +553,7 @@ def sinc(t):
     t = _mul(_f(t), _lit(PI))
     with np.errstate(divide="ignore", invalid="ignore"):
         s = _div(_sin(t), t)
-    return np.where(t == 0, F32(1.0), s).astype(F32)
+    return np.where(t == 0, _FT(1.0), s).astype(_FT)
 
 
 def firwin(
@@ -563,7 +587,7 @@ def firwin(
     m = (num_taps - 1) / 2.0
     alpha = _sub(_iota(num_taps), _lit(m))
     freqs = [0.0] + cl + [1.0]
-    h = np.zeros(num_taps, dtype=F32)
+    h = np.zeros(num_taps, dtype=_FT)
     for i in range(len(freqs) - 1):
         take = (i % 2 == 0) if pass_zero else (i % 2 == 1)
         if not take:
@@ -598,7 +622,7 @@ def _firwin_window(num_taps, window):
     if window == "bartlett":
         return bartlett(num_taps)
     if window == "rectangular":
-        return rectangular(num_taps, dtype=F32)
+        return rectangular(num_taps, dtype=_FT)
     if isinstance(window, tuple) and len(window) == 2 and window[0] == "kaiser":
         return kaiser(num_taps, beta=window[1], is_periodic=False)
     raise ValueError(

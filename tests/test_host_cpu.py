@@ -178,7 +178,11 @@ def test_postop_and_onesided_argument_errors_need_no_device():
     with pytest.raises(nx.NxSignalArgumentError, match="axis"):
         nx.PeakFinding.argrelmin(np.arange(4), axis=2)
     with pytest.raises(nx.NxSignalArgumentError, match="order"):
-        nx.PeakFinding.argrelmax(np.arange(4), order=0)
+        nx.PeakFinding.argrelmax(np.arange(4), order=-1)
+    # order = 0 is valid in the reference (the comparison loop runs zero times, peak_finding.ex:354-363):
+    # every element stays marked
+    r = nx.PeakFinding.argrelmax(np.arange(6).reshape(2, 3), order=0)
+    assert int(r["valid_indices"]) == 6 and r["indices"].tolist() == [[0, 0], [0, 1], [0, 2], [1, 0], [1, 1], [1, 2]]
     with pytest.raises(nx.NxSignalArgumentError, match="onesided istft"):
         nx.istft(np.zeros((1, 4, 512), np.complex64), nx.windows.hann(1024), onesided=True, overlap_length=768,
                  fft_length=1024)
