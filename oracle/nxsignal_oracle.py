@@ -904,7 +904,7 @@ def _local_sum_same(a, kernel_size):
 def wiener(t, kernel_size=3, noise=None):
     """filters.ex:80-110, 281-303: computed in f64 (Nx.as_type(:f64)), cast back to t's type."""
     t = np.asarray(t)
-    out_t = t.dtype if t.dtype in (np.dtype(F32), np.dtype(F64)) else np.dtype(F32)
+    out_t = t.dtype  # |> Nx.as_type(Nx.type(t)), filters.ex:108-110: integer inputs get the truncated result back
     if isinstance(kernel_size, (int, np.integer)):
         kernel_size = (int(kernel_size),) * t.ndim
     elif not isinstance(kernel_size, tuple):

@@ -174,3 +174,92 @@ def test_cfg5_full_size_round_trip(onesided):
     lo, hi = N, (m1 - m0) * H - N
     got = yr[C - 1, m0 * H + lo: m0 * H + hi].cpu().numpy()
     assert np.abs(got - yo.real[lo:hi]).max() / np.abs(yo).max() <= TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# Whole-channel oracle parity at the BASELINE sizes: every frame / sample of at least one full channel
+# of each config against the oracle (chunked, so the f64 temporaries stay bounded), in the plain
+# per-frame / per-channel max-norm bound of 1e-5 -- not a handful of spot frames.
+# ---------------------------------------------------------------------------------------------
+def _whole_channel_stft_err(x_c, z_c, w_np, N, H, chunk=8192):
+    """max over ALL frames of one channel of max|gpu - oracle| / max|oracle| (oracle = stft_fast, chunked)."""
+    M = z_c.shape[0]
+    worst = 0.0
+    for m0 in range(0, M, chunk):
+        m1 = min(M, m0 + chunk)
+        seg = x_c[m0 * H: (m1 - 1) * H + N].cpu().numpy()
+        zo, _, _ = o.stft_fast(seg, w_np, overlap_length=N - H, fft_length=N, sampling_rate=FS)
+        got = z_c[m0:m1].cpu().numpy()
+        assert zo.shape == got.shape
+        err = np.abs(got - zo).max(axis=-1) / np.abs(zo).max(axis=-1)
+        worst = max(worst, float(err.max()))
+    return worst
+
+
+def test_cfg2_whole_channels_against_the_oracle():
+    """cfg2: all 112 497 frames of the first and the last channel vs the oracle."""
+    import torch
+
+    _need(40)
+    C, L, N, H = 8, FS * 600, 1024, 256
+    w_np = nx.windows.hann(N)
+    x = _signal(C, L, 1002)
+    z, _, _ = nx.stft(x, torch.from_numpy(w_np).cuda(), overlap_length=N - H, fft_length=N, sampling_rate=FS)
+    for c in (0, C - 1):
+        assert _whole_channel_stft_err(x[c], z[c], w_np, N, H) <= TOL, c
+
+
+def test_cfg3_whole_channels_against_the_oracle():
+    """cfg3 shard: all 2 809 frames of three channels (first, middle, last of the 128) vs the oracle."""
+    import torch
+
+    _need(30)
+    C, L, N, H = 128, FS * 60, 4096, 1024
+    w_np = nx.windows.hann(N)
+    x = _signal(C, L, 1003)
+    z, _, _ = nx.stft(x, torch.from_numpy(w_np).cuda(), overlap_length=N - H, fft_length=N, sampling_rate=FS)
+    for c in (0, 64, 127):
+        assert _whole_channel_stft_err(x[c], z[c], w_np, N, H, chunk=1024) <= TOL, c
+
+
+def test_cfg4_whole_channel_against_f64_convolution():
+    """cfg4: all 28.8 M output samples of two channels vs scipy's oaconvolve in f64 (mode :same)."""
+    import torch
+    from scipy.signal import oaconvolve
+
+    _need(60)
+    C, L, K = 64, FS * 600, 2049
+    taps_np = nx.filters.firwin(K, [6000], sampling_rate=FS)
+    a = _signal(C, L, 1004)
+    y = conv.convolve(a, torch.from_numpy(taps_np).cuda()[None, :], mode="same", method="fft")
+    s = (K - 1) // 2
+    for c in (0, C - 1):
+        full = oaconvolve(a[c].cpu().numpy().astype(np.float64), taps_np.astype(np.float64), mode="full")
+        want = full[s: s + L]
+        got = y[c].cpu().numpy()
+        assert np.abs(got - want).max() / np.abs(want).max() <= TOL, c
+
+
+def test_cfg5_whole_channel_istft_including_edges():
+    """cfg5: istft of a whole channel (11 247 frames) vs the oracle on EVERY output sample -- the first / last
+    window included, where the reference divides by an overlap-added window energy that tends to zero and the
+    f64 edge kernel does the work (plain 1e-5 bound, per channel max-norm)."""
+    import torch
+
+    _need(20)
+    C, L, N, H = 32, FS * 60, 1024, 256
+    w_np = nx.windows.hann(N)
+    w = torch.from_numpy(w_np).cuda()
+    kw = dict(overlap_length=N - H, fft_length=N, sampling_rate=FS)
+    x = _signal(C, L, 1005)
+    z, _, _ = nx.stft(x, w, **kw)
+    y = nx.istft(z, w, **kw)
+    for c in (0, C - 1):
+        yo = o.istft_fast(z[c].cpu().numpy(), w_np, **kw)
+        got = y[c].cpu().numpy()
+        assert got.shape == yo.shape
+        scale = np.abs(yo).max()
+        assert np.abs(got - yo).max() / scale <= TOL, c
+        # and separately on the edge samples alone, against their own scale
+        for sl in (slice(0, N), slice(-N, None)):
+            assert np.abs(got[sl] - yo[sl]).max() / np.abs(yo[sl]).max() <= TOL, (c, sl)
