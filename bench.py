@@ -426,7 +426,26 @@ def pcie_probe(env, nbytes=1 << 30):
         dt = env.max_over_ranks((time.perf_counter() - t) / 3)
         res[name + "_gbs_per_gpu"] = nbytes / dt / 1e9
         res[name + "_gbs_aggregate"] = env.world * nbytes / dt / 1e9
-    del h, d
+    # both directions at once (what a pipelined host call does): two streams, two buffer pairs
+    h2 = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    d2 = torch.empty(nbytes, dtype=torch.uint8, device=env.dev)
+    s1, s2 = torch.cuda.Stream(env.dev), torch.cuda.Stream(env.dev)
+
+    def duplex():
+        with torch.cuda.stream(s1):
+            d.copy_(h, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h2.copy_(d2, non_blocking=True)
+
+    duplex()
+    env.barrier()
+    t = time.perf_counter()
+    for _ in range(3):
+        duplex()
+    env.barrier()
+    dt = env.max_over_ranks((time.perf_counter() - t) / 3)
+    res["duplex_gbs_per_direction_per_gpu"] = nbytes / dt / 1e9
+    del h, d, h2, d2
     return res
 
 
@@ -600,6 +619,7 @@ def other_host_entries(env, nx):
                                  ctx, "fir(host)"))
     h2d = d2h = xh.numel() * 4
     floor = max(h2d / probe["h2d_gbs_per_gpu"], d2h / probe["d2h_gbs_per_gpu"]) / 1e9
+    floor_duplex = max(h2d, d2h) / probe["duplex_gbs_per_direction_per_gpu"] / 1e9
     xd = xh[:1].to(env.dev)
     yd = torch.empty((1, L), dtype=torch.float32, device=env.dev)
     _lib.check(lib.nxs_fir_f32_dev(ctx, A.ptr(xd), 1, L, L, A.ptr(torch.from_numpy(taps).to(env.dev)), 2049, 1, A.ptr(yd), L,
@@ -607,6 +627,8 @@ def other_host_entries(env, nx):
     torch.cuda.synchronize(env.dev)
     out["fir_cfg4_host_call"] = {"ms_per_step": 1e3 * s, "samples_per_s": C4 * L / s, "h2d_bytes_per_step": int(h2d),
                                  "d2h_bytes_per_step": int(d2h), "pcie_floor_ms": 1e3 * floor, "over_pcie_floor": s / floor,
+                                 "pcie_floor_both_directions_busy_ms": 1e3 * floor_duplex,
+                                 "over_pcie_floor_both_directions_busy": s / floor_duplex,
                                  "host_equals_device_bitwise": bool(torch.equal(yd.cpu().view(torch.int32),
                                                                                 yh[:1].view(torch.int32)))}
     out["pcie_probe"] = probe
@@ -724,7 +746,14 @@ def other_kernels(env, nx, peak):
     ms = timed(lambda: _lib.check(lib.nxs_fir_f32_dev(ctx, A.ptr(x4), C4, L, L, A.ptr(taps), 2049, 1, A.ptr(y4), L, s), ctx),
                iters=3)
     out["fir_cfg4"] = entry(ms, 8 * C4 * L, C4 * L, "samples_per_s")
-    out["fir_cfg4"]["note"] = "instruction-issue-bound at K = 2049 (FFT -> x H -> IFFT per block pair), not HBM-bound"
+    # fp32 roofline (SURVEY 8d asks for both): 80.9 flop per output sample from the executed instruction mix of
+    # fir_ols_r2c_kernel (ncu, profiles/r02_fir_r2c_4096.txt: FADD 37.7 %, FMUL 15.9 %, FFMA 20.8 % of 489 M warp
+    # instructions for 64 ch x 60 s)
+    tfl = 80.9 * C4 * L / (ms * 1e-3) / 1e12
+    fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12  # SMs x lanes x FMA x max SM clock
+    out["fir_cfg4"].update({"fp32_tflops": tfl, "fp32_peak_tflops": fp32_peak, "frac_of_fp32_peak": tfl / fp32_peak,
+                            "note": "real-packed overlap-save (one 8192-sample block per 4096-point transform pair): "
+                                    "instruction-issue-bound at K = 2049 (ncu: 68 % of issue slots, DRAM 12 %), not HBM-bound"})
     del x4, y4
     torch.cuda.empty_cache()
     return out
@@ -854,6 +883,15 @@ def main():
     torch.cuda.empty_cache()
 
     peak, peak_src = peaks()
+    # single-GPU extras first (each kernel timed alone, before the long cfg3 leg heats the part into its power cap)
+    other = None
+    if world == 1 and not args.no_extras:
+        time.sleep(1.0)
+        try:
+            other = other_kernels(env, nx, peak)
+            other.update(other_host_entries(env, nx))
+        except Exception as ex:  # report, never fake
+            other = {"error": repr(ex)[:300]}
     multi = None
     if not args.no_multi:
         try:
@@ -879,13 +917,6 @@ def main():
             traffic = json.load(open(tp)).get("stft_r2c_1024_bytes_per_launch")
         except Exception:
             traffic = None
-    other = None
-    if world == 1 and not args.no_extras:
-        try:
-            other = other_kernels(env, nx, peak)
-            other.update(other_host_entries(env, nx))
-        except Exception as ex:  # report, never fake
-            other = {"error": repr(ex)[:300]}
     cpu = None
     cfg1 = None
     if world == 1 and not args.no_cpu:

@@ -24,7 +24,7 @@ def _bits(a):
     if A.is_torch(a):
         a = (torch.view_as_real(a) if a.is_complex() else a).cpu().numpy()
     a = np.ascontiguousarray(a)
-    return a.view(np.int32) if a.dtype.itemsize % 4 == 0 else a
+    return a.view(np.int32).ravel() if a.dtype.itemsize % 4 == 0 else a.ravel()
 
 
 def _pinned(arr):
