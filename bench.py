@@ -948,6 +948,7 @@ def main():
                      "kernel_ms": kern_avg_ms, "kernel_launches_timed": kern_n, "algorithmic_bytes": ALGO_BYTES},
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "multi_gpu": multi, "cfg1": cfg1, "other_kernels": other,
+        "build": _lib.build_info(),  # which binary ran: the stamp compiled into the .so vs the sources in the tree
     }
     emit(line)
     if comm is not None:

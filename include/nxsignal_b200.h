@@ -72,6 +72,10 @@ typedef struct nxs_ctx nxs_ctx;
 
 /* ---- library / context -------------------------------------------------- */
 int nxs_abi_version(void);
+/* "src_sha256=<16 hex digits> built=<UTC time> nvcc=<version> arch=sm_100a": the hash is over the library's
+ * source files in sorted order (csrc Makefile, STAMP_SRC), so a caller can tell whether the binary it loaded
+ * was built from the sources beside it (bench.py prints both) */
+const char* nxs_build_info(void);
 const char* nxs_strerror(int code);
 /* number of visible CUDA devices (0 when there is none; never an error) */
 int nxs_device_count(void);

@@ -29,6 +29,7 @@ vp = C.c_void_p
 # name -> (restype, argtypes); every symbol include/nxsignal_b200.h declares
 SIGNATURES = {
     "nxs_abi_version": (i32, []),
+    "nxs_build_info": (C.c_char_p, []),
     "nxs_strerror": (C.c_char_p, [i32]),
     "nxs_device_count": (i32, []),
     "nxs_ctx_create": (i32, [i32, C.POINTER(vp)]),
@@ -183,3 +184,28 @@ def host_mode(device=0):
 def set_host_mode(mode, device=0):
     """-1: the context picks the cheaper mode from its own measurements (default); 0 / 1: pin it."""
     check(lib().nxs_ctx_set_host_mode(context(device), int(mode)))
+
+
+def build_info():
+    """The stamp compiled into the loaded library and the same hash computed now from the sources in the tree
+    (None when they are not there): {"lib": ..., "src_sha256_of_tree": ..., "lib_matches_tree": bool}."""
+    import glob
+    import hashlib
+
+    stamp = lib().nxs_build_info().decode()
+    csrc = os.path.join(_HERE, "csrc")
+    files = sorted(os.path.basename(p) for pat in ("*.cu", "*.cuh", "*.h") for p in glob.glob(os.path.join(csrc, pat)))
+    files += [f for f in ("nxs_host.cpp", "nxs_hostpool.cpp")]
+    files = sorted(set(files))
+    tree = None
+    try:
+        h = hashlib.sha256()
+        for f in files:
+            h.update(open(os.path.join(csrc, f), "rb").read())
+        h.update(open(os.path.join(_HERE, "..", "include", "nxsignal_b200.h"), "rb").read())
+        tree = h.hexdigest()[:16]
+    except OSError:
+        pass
+    lib_hash = stamp.split("src_sha256=")[1].split()[0] if "src_sha256=" in stamp else None
+    return {"lib": stamp, "src_sha256_of_tree": tree, "lib_matches_tree": (tree == lib_hash) if tree else None,
+            "path": os.path.relpath(LIB_PATH, os.path.join(_HERE, ".."))}

@@ -35,5 +35,6 @@ def test_gpu_path_reproduces_reference_vector(rec):
         np.testing.assert_array_equal(np.asarray(got, dtype=np.float32).view(np.uint32), want.view(np.uint32))
         return
     scale = max(float(np.abs(want).max()), 1e-30)
-    assert np.abs(got.astype(want.dtype) - want).max() <= 1.5e-6 * scale if key == ("lib/nx_signal.ex", 385) else True
+    if key == ("lib/nx_signal.ex", 385):  # the mel_filters row: tighter than the general bound below
+        assert np.abs(got.astype(want.dtype) - want).max() <= 1.5e-6 * scale
     assert np.abs(got.astype(np.complex128) - want.astype(np.complex128)).max() <= TOL * scale
