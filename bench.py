@@ -505,6 +505,16 @@ def e2e_legs(env, x, w, zo, zo_frames, args):
         zd_h = torch.view_as_real(zd).cpu()
         e2e["host_equals_device_bitwise"] = bool(torch.equal(zd_h, torch.view_as_real(zh[CHANNELS - 1, M - 4096:])))
     e2e["pcie_probe"] = pcie_probe(env)
+    # what the box allows: every rank's 7.37 GB result must be written to host memory through the ranks' shared
+    # host memory system; the aggregate D2H rate of plain pinned copies on all ranks at once bounds the call
+    agg = e2e["pcie_probe"]["d2h_gbs_aggregate"] * 1e9
+    full_floor = world * CHANNELS * M * NFFT * 8 / agg
+    e2e["box_ceiling"] = {"aggregate_d2h_gbs": agg / 1e9, "floor_ms_both_halves_over_pcie": 1e3 * full_floor,
+                          "floor_ms_lower_half_only": 1e3 * world * CHANNELS * M * (NFFT // 2 + 1) * 8 / agg,
+                          "ms_per_step_over_full_result_floor": s / full_floor,
+                          "note": "floors = result bytes of all ranks / aggregate D2H rate measured in this run; the lower-half "
+                                  "floor ignores the host-memory traffic of the mirror pass and is not reachable when the "
+                                  "host memory system, not PCIe, is the shared bottleneck (N >= 2 on this box)"}
 
     # the same call on memory the DMA engines cannot address: what a BEAM binary (enif_make_new_binary) is
     try:

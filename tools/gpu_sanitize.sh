@@ -73,6 +73,29 @@ kwm = dict(overlap_length=768, fft_length=1024, sampling_rate=16000)
 mh = nx.stft_mel(xm, wm, mel_bins=80, **kwm)
 zo, _, _ = o.stft_fast(xm, wm, **kwm)
 chk("stft_mel host entry (11 channels -> 8 chunks)", mh, np.stack([o.stft_to_mel(zo[c], 16000, 1024, 80) for c in range(11)]))
+# round 2: real-packed FIR kernel with an even tap count (odd K - 1: scalar stores), an unaligned row, a partitioned filter
+for K, L in [(2048, 30001), (1000, 25000), (9001, 40000)]:
+    x = rng.standard_normal((3, L)).astype(np.float32); taps = (rng.standard_normal(K) / np.sqrt(K)).astype(np.float32)
+    for mode in ("full", "valid"):
+        y = nx.convolution.convolve(torch.from_numpy(x).cuda(), torch.from_numpy(taps).cuda()[None, :], mode=mode, method="fft")
+        full = oaconvolve(x.astype(np.float64), taps.astype(np.float64)[None, :], mode=mode, axes=-1)
+        chk(f"fir r2c K={K} {mode}", y, full.astype(np.float32))
+# complex-data STFT (plane split + combine), host pipelines on pageable numpy buffers (pinned rings, unstage + mirror)
+xc = (rng.standard_normal((3, 9000)) + 1j * rng.standard_normal((3, 9000))).astype(np.complex64); wc = o.hann(512)
+kwc = dict(overlap_length=384, fft_length=512, sampling_rate=48000)
+zc, _, _ = nx.stft(torch.from_numpy(xc).cuda(), torch.from_numpy(wc).cuda(), **kwc)
+zco, _, _ = o.stft_fast(xc, wc, **kwc); chk("stft complex data", torch.view_as_real(zc), np.stack([zco.real, zco.imag], -1))
+xh = rng.standard_normal((5, 300_000)).astype(np.float32); wh = o.hann(1024)
+kwh = dict(overlap_length=768, fft_length=1024, sampling_rate=48000)
+zh, _, _ = nx.stft(xh, wh, **kwh)
+zd, _, _ = nx.stft(torch.from_numpy(xh).cuda(), torch.from_numpy(wh).cuda(), **kwh)
+assert np.array_equal(zh.view(np.float32), torch.view_as_real(zd).cpu().numpy().reshape(zh.shape[0], zh.shape[1], -1)); print("stft host (pageable) == device OK")
+yh = nx.istft(zh, wh, **kwh); yd = nx.istft(zd, torch.from_numpy(wh).cuda(), **kwh)
+assert np.array_equal(yh.view(np.float32), torch.view_as_real(yd).cpu().numpy().reshape(yh.shape[0], -1)); print("istft host (pageable) == device OK")
+th = (rng.standard_normal(2049) / 45).astype(np.float32)
+fh = nx.convolution.convolve(xh, th[None, :], mode="same", method="fft")
+fd = nx.convolution.convolve(torch.from_numpy(xh).cuda(), torch.from_numpy(th).cuda()[None, :], mode="same", method="fft")
+assert np.array_equal(fh, fd.cpu().numpy()); print("fir host (pageable) == device OK")
 torch.cuda.synchronize(); print("all cases done")
 PY
 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 1 python /tmp/san_cases.py > $OUT/memcheck.log 2>&1; echo "memcheck rc=$?" | tee -a $OUT/memcheck.log; grep -c "OK" $OUT/memcheck.log; grep -E "ERROR SUMMARY|Invalid|FAIL" $OUT/memcheck.log | head -5
