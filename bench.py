@@ -350,6 +350,7 @@ def multi_gpu_legs(env, nx, w1024, comm, peak, steps):
     torch.cuda.empty_cache()
 
     if world > 1:
+        time.sleep(0.5)  # every leg starts from the same power state (the cfg3 leg runs the part at its power cap)
         # ---- cfg2, strong scaling by channel: the 8 channels split over the ranks ----
         shc = sharding.shard_channels(CHANNELS, world, rank)
         xs = gen_cfg2_channels(torch, dev, shc.start, shc.count)
@@ -377,6 +378,7 @@ def multi_gpu_legs(env, nx, w1024, comm, peak, steps):
         del xs, zs
         torch.cuda.empty_cache()
 
+        time.sleep(0.5)
         # ---- cfg2, strong scaling by frame range (read-only halo of N - hop samples, no exchange) ----
         fs = sharding.shard_frames(M, NFFT, HOP, world, rank)
         xfull = gen_cfg2_channels(torch, dev, 0, CHANNELS)

@@ -221,16 +221,21 @@ __global__ void __launch_bounds__(THREADS) stft_r2c_kernel(const StftArgs a) {
 // PAIRED: conjugate-paired last pass (nxs_fft.cuh): thread t ends up holding Z[k] and Z[N - k] for each
 // of its bins, so the split pass runs out of registers -- no exchange, and no misaligned descending
 // shared-memory reads (ncu: they were 10 % excess wavefronts on the nfft = 4096 plan).
+// XD (LEAN + PAIRED only): two exchange buffers per group and the compact twiddle table (power-of-two rows only),
+// so no barrier separates a middle pass's reads from its writes: three group barriers per frame instead of
+// four, paid for with shared memory (one 512-thread CTA per SM instead of two of 256).
 template <class PL_, int THREADS_, int HOPDIV_, bool TWREG_, bool PERGROUP_ = false, bool LEAN_ = false,
-          bool WINREG_ = false, bool PAIRED_ = false>
+          bool WINREG_ = false, bool PAIRED_ = false, bool XD_ = false>
 struct StagedCfg {
   using PL = PL_;
   static constexpr int THREADS = THREADS_, HOPDIV = HOPDIV_;
-  static constexpr bool TWREG = TWREG_, PERGROUP = PERGROUP_, LEAN = LEAN_, WINREG = WINREG_, PAIRED = PAIRED_;
+  static constexpr bool TWREG = TWREG_, PERGROUP = PERGROUP_, LEAN = LEAN_, WINREG = WINREG_, PAIRED = PAIRED_, XD = XD_;
   static_assert(!LEAN || PERGROUP, "LEAN needs per-group staging");
   static_assert(!PAIRED || !TWREG, "the paired last pass reads its twiddles from the table");
+  static_assert(!XD || (LEAN && PAIRED && !TWREG), "XD is the LEAN + PAIRED layout with a second exchange buffer");
   static constexpr int G = THREADS / PL::T, NFFT = 2 * PL::N;
-  static constexpr int NSTAGE = LEAN ? 1 : 2, NXBUF = LEAN ? 1 : 2;
+  static constexpr int NSTAGE = LEAN ? 1 : 2, NXBUF = (LEAN && !XD) ? 1 : 2;
+  static constexpr int TW_ENTRIES = TWREG ? 0 : (XD ? PL::TWC_TOTAL : PL::TW_TOTAL);
   // floats per stage: one tile span, or G private frames
   // (per-group frames carry 4 floats of slack: the copy starts at the 16-byte boundary below the frame)
   static constexpr int FRAME_STAGE = NFFT + 4;
@@ -239,7 +244,7 @@ struct StagedCfg {
   static constexpr size_t WIN_OFF = BUF_BYTES;
   static constexpr size_t STAGE_OFF = WIN_OFF + size_t(NFFT) * sizeof(float);
   static constexpr size_t TW_OFF = STAGE_OFF + NSTAGE * size_t(STAGE) * sizeof(float);
-  static constexpr size_t BAR_OFF = TW_OFF + (TWREG ? 0 : size_t(PL::TW_TOTAL) * sizeof(cpx));
+  static constexpr size_t BAR_OFF = TW_OFF + size_t(TW_ENTRIES) * sizeof(cpx);
   static constexpr size_t SMEM = BAR_OFF + 16 * (PERGROUP ? G : 1);
 };
 
@@ -247,7 +252,8 @@ template <class CF, int MINB, int MODE>
 __global__ void __launch_bounds__(CF::THREADS, MINB) stft_r2c_staged_kernel(const StftArgs a, const int tpc,
                                                                             const int total_tiles) {
   using PL = typename CF::PL;
-  using TW = typename std::conditional<CF::TWREG, TwRegs<PL>, TwDerive<PL>>::type;
+  using TW = typename std::conditional<CF::TWREG, TwRegs<PL>,
+                                       typename std::conditional<CF::XD, TwDeriveC<PL>, TwDerive<PL>>::type>::type;
   constexpr int THREADS = CF::THREADS;
   constexpr int N = PL::N, T = PL::T, P = PL::P, G = CF::G, NFFT = 2 * N;
   constexpr int R0 = PL::R(0), B0 = P / R0;
@@ -256,7 +262,7 @@ __global__ void __launch_bounds__(CF::THREADS, MINB) stft_r2c_staged_kernel(cons
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, g = tid / T, t = tid % T;
   cpx* bufA = reinterpret_cast<cpx*>(smem_raw) + (size_t)(CF::NXBUF * g) * PL::BUF;
-  cpx* bufB = CF::LEAN ? bufA : bufA + PL::BUF;
+  cpx* bufB = CF::NXBUF == 1 ? bufA : bufA + PL::BUF;
   float* wsm = reinterpret_cast<float*>(smem_raw + CF::WIN_OFF);
   float* stage0 = reinterpret_cast<float*>(smem_raw + CF::STAGE_OFF);
   const uint32_t bar0 = smem_u32(smem_raw + CF::BAR_OFF);
@@ -280,7 +286,7 @@ __global__ void __launch_bounds__(CF::THREADS, MINB) stft_r2c_staged_kernel(cons
   }
   if constexpr (!CF::TWREG) {
     cpx* twsm = reinterpret_cast<cpx*>(smem_raw + CF::TW_OFF);
-    for (int i = tid; i < PL::TW_TOTAL; i += THREADS) twsm[i] = a.tw[i];
+    for (int i = tid; i < CF::TW_ENTRIES; i += THREADS) twsm[i] = a.tw[i];
   }
   if (tid == 0) {
     for (int i = 0; i < 2 * (CF::PERGROUP ? G : 1); ++i) mbar_init(bar0 + 8 * i, 1);
@@ -470,7 +476,8 @@ __global__ void __launch_bounds__(CF::THREADS, MINB) stft_r2c_staged_kernel(cons
       // exchange buffer): refill the stage with the next frame while this one is transformed
       sync();
       if (issuer && tile + (int)gridDim.x < total_tiles) issue(cn, rn, 0);
-      block_fft_single<PL, TW, GroupSync<T>, CF::PAIRED>(v, t, bufA, tw, sync);
+      if constexpr (CF::XD) block_fft_paired<PL>(v, t, bufA, bufB, tw, sync);
+      else block_fft_single<PL, TW, GroupSync<T>, CF::PAIRED>(v, t, bufA, tw, sync);
       if constexpr (!CF::PAIRED) sync();  // last pass's reads done before the post-pass reuses the buffer
     } else if constexpr (CF::PAIRED) {
       block_fft_paired<PL>(v, t, bufA, bufB, tw, sync);
@@ -768,6 +775,25 @@ static int run_r2c(nxs_ctx* ctx, StftArgs a, cudaStream_t st) {
   return NXS_OK;
 }
 
+// compact twiddle table (TwDeriveC: only the power-of-two rows of every pass), cached per context
+template <class PL>
+static int get_compact_tw(nxs_ctx* ctx, float2** out) {
+  const uint64_t key = (uint64_t(PL::N) << 32) | (uint64_t(PL::T) << 8) | uint64_t(PL::NP) | (uint64_t(1) << 61);
+  auto it = ctx->tables.find(key);
+  if (it != ctx->tables.end()) {
+    *out = it->second.tw;
+    return NXS_OK;
+  }
+  std::vector<float2> tw(PL::TWC_TOTAL > 0 ? PL::TWC_TOTAL : 1);
+  build_compact_twiddles<PL>(tw.data());
+  PlanTables t;
+  NXS_CUDA(ctx, cudaMalloc(&t.tw, tw.size() * sizeof(float2)));
+  NXS_CUDA(ctx, cudaMemcpy(t.tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+  ctx->tables[key] = t;
+  *out = t.tw;
+  return NXS_OK;
+}
+
 template <class CF, int MINB>
 static int run_r2c_staged(nxs_ctx* ctx, StftArgs a, int64_t channels, cudaStream_t st) {
   using PL = typename CF::PL;
@@ -777,6 +803,13 @@ static int run_r2c_staged(nxs_ctx* ctx, StftArgs a, int64_t channels, cudaStream
   if (rc) return rc;
   a.tw = tabs.tw;
   a.post = tabs.post;
+  if constexpr (CF::XD) {
+    float2* twc = nullptr;
+    rc = get_compact_tw<PL>(ctx, &twc);
+    if (rc) return rc;
+    a.tw = twc;
+    if (a.mel_out) return NXS_EUNSUPPORTED;  // the fused log-mel epilogue keeps the single-buffer layout
+  }
   const int64_t tpc = (a.M + CF::G - 1) / CF::G;
   const int64_t tiles = tpc * channels;
   auto kern = a.mel_out ? stft_r2c_staged_kernel<CF, MINB, kMel>
@@ -935,6 +968,7 @@ int launch_stft(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, 
         if (variant_env() == 2) { using CF = StagedCfg<PL, 256, 4, false, true>; NXS_TRY_STAGED(CF, 1); }
         if (variant_env() == 3) { using CF = StagedCfg<PL, 512, 4, false, true, true>; NXS_TRY_STAGED(CF, 1); }
         if (variant_env() == 4) { using CF = StagedCfg<PL, 256, 4, false, true, true>; NXS_TRY_STAGED(CF, 2); }
+        if (variant_env() == 5 && !a.mel_out) { using CF = StagedCfg<PL, 512, 4, false, true, true, false, true, true>; NXS_TRY_STAGED(CF, 1); }
         { using CF = StagedCfg<PL, 256, 4, false, true, true, false, true>; NXS_TRY_STAGED(CF, 2); }
         return run_r2c<PL, TwTable<PL>, 512>(ctx, a, st);
       }

@@ -455,6 +455,9 @@ def stft(
     # Nx.multiply: int x int stays int (then Nx.fft casts); else f32
     if np.issubdtype(frames.dtype, np.integer) and np.issubdtype(window.dtype, np.integer):
         windowed = frames.astype(np.int64) * window.astype(np.int64)
+    elif np.iscomplexobj(frames) or np.iscomplexobj(window):
+        # complex data: Nx.multiply(c64, f32) is a complex product in double, rounded once to c64 (:101)
+        windowed = _c(np.asarray(frames, dtype=C128) * np.asarray(window, dtype=C128))
     else:
         windowed = _mul(frames, window)
     if fft_length == "power_of_two":

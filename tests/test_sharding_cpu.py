@@ -100,3 +100,34 @@ def test_gloo_world2_broadcast_and_channel_sharding():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(a and b for a, b in res), res
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_bench_shards_tile_the_baseline_configs(world):
+    """bench.py's multi-GPU legs: cfg3's 1024 channels split into whole 64-channel generation blocks, cfg2's 8
+    channels by channel, and cfg2's 112 497 frames by frame range -- every unit owned exactly once, and a frame
+    shard's sample span is exactly what its frames read."""
+    from nx_signal_b200 import sharding
+
+    covered = []
+    for r in range(world):
+        sh = sharding.shard_channels(1024, world, r)
+        assert sh.start % 64 == 0 and sh.count % 64 == 0 and sh.count == 1024 // world
+        covered += list(range(sh.start, sh.start + sh.count))
+    assert covered == list(range(1024))
+    covered = []
+    for r in range(world):
+        sh = sharding.shard_channels(8, world, r)
+        covered += list(range(sh.start, sh.start + sh.count))
+    assert covered == list(range(8))
+    L, N, hop = 48000 * 600, 1024, 256
+    M = (L - N) // hop + 1
+    nxt = 0
+    for r in range(world):
+        fs = sharding.shard_frames(M, N, hop, world, r)
+        assert fs.frame_start == nxt and fs.frame_count > 0
+        assert fs.sample_start == fs.frame_start * hop
+        assert fs.sample_count == (fs.frame_count - 1) * hop + N and fs.sample_start + fs.sample_count <= L
+        assert (fs.sample_count - N) // hop + 1 == fs.frame_count  # stft of the span yields exactly the shard's frames
+        nxt += fs.frame_count
+    assert nxt == M
