@@ -225,17 +225,18 @@ __global__ void __launch_bounds__(THREADS) stft_r2c_kernel(const StftArgs a) {
 // so no barrier separates a middle pass's reads from its writes: three group barriers per frame instead of
 // four, paid for with shared memory (one 512-thread CTA per SM instead of two of 256).
 template <class PL_, int THREADS_, int HOPDIV_, bool TWREG_, bool PERGROUP_ = false, bool LEAN_ = false,
-          bool WINREG_ = false, bool PAIRED_ = false, bool XD_ = false>
+          bool WINREG_ = false, bool PAIRED_ = false, bool XD_ = false, bool TWC_ = XD_>
 struct StagedCfg {
   using PL = PL_;
   static constexpr int THREADS = THREADS_, HOPDIV = HOPDIV_;
   static constexpr bool TWREG = TWREG_, PERGROUP = PERGROUP_, LEAN = LEAN_, WINREG = WINREG_, PAIRED = PAIRED_, XD = XD_;
+  static constexpr bool TWC = TWC_ || XD_;  // compact twiddle table (power-of-two rows; TwDeriveC)
   static_assert(!LEAN || PERGROUP, "LEAN needs per-group staging");
   static_assert(!PAIRED || !TWREG, "the paired last pass reads its twiddles from the table");
   static_assert(!XD || (LEAN && PAIRED && !TWREG), "XD is the LEAN + PAIRED layout with a second exchange buffer");
   static constexpr int G = THREADS / PL::T, NFFT = 2 * PL::N;
   static constexpr int NSTAGE = LEAN ? 1 : 2, NXBUF = (LEAN && !XD) ? 1 : 2;
-  static constexpr int TW_ENTRIES = TWREG ? 0 : (XD ? PL::TWC_TOTAL : PL::TW_TOTAL);
+  static constexpr int TW_ENTRIES = TWREG ? 0 : (TWC ? PL::TWC_TOTAL : PL::TW_TOTAL);
   // floats per stage: one tile span, or G private frames
   // (per-group frames carry 4 floats of slack: the copy starts at the 16-byte boundary below the frame)
   static constexpr int FRAME_STAGE = NFFT + 4;
@@ -253,7 +254,7 @@ __global__ void __launch_bounds__(CF::THREADS, MINB) stft_r2c_staged_kernel(cons
                                                                             const int total_tiles) {
   using PL = typename CF::PL;
   using TW = typename std::conditional<CF::TWREG, TwRegs<PL>,
-                                       typename std::conditional<CF::XD, TwDeriveC<PL>, TwDerive<PL>>::type>::type;
+                                       typename std::conditional<CF::TWC, TwDeriveC<PL>, TwDerive<PL>>::type>::type;
   constexpr int THREADS = CF::THREADS;
   constexpr int N = PL::N, T = PL::T, P = PL::P, G = CF::G, NFFT = 2 * N;
   constexpr int R0 = PL::R(0), B0 = P / R0;
@@ -302,34 +303,47 @@ __global__ void __launch_bounds__(CF::THREADS, MINB) stft_r2c_staged_kernel(cons
   cpx wpost[P / 2];
 #pragma unroll
   for (int i = 0; i < P / 2; ++i) {
-    if constexpr (CF::PAIRED) wpost[i] = __ldg(a.post + t + (i / RL) * T + (i % RL) * JL);
-    else wpost[i] = __ldg(a.post + t + i * T);
+    if constexpr (CF::PAIRED) {
+      int kk = t + (i / RL) * T + (i % RL) * JL;
+      if (t == 0 && i >= RL / 2 && i < RL) kk = JL / 2 + (i - RL / 2) * JL;  // thread 0's self-paired butterfly JL / 2
+      wpost[i] = __ldg(a.post + kk);
+    } else {
+      wpost[i] = __ldg(a.post + t + i * T);
+    }
   }
-  // the pair (Z[kk], conj Z[N - kk]) number i of this thread, its twiddle and (kk == 0 only) Z[N / 2]
+  // the pair (Z[kk], conj Z[N - kk]) number i of this thread, its twiddle and (kk == 0 only) Z[N / 2].
+  // PAIRED: slot b < B/2 holds butterfly j = t + b T (bins j + q JL in v[b RL + bitrev q]) and slot b + B/2 its
+  // conjugate partner butterfly JL - j, so pair q is (slot b, q) with (slot b + B/2, RL - 1 - q).  Thread 0's first
+  // slot pair is special -- butterflies 0 and JL / 2 pair with THEMSELVES (q with RL - q, resp. q with RL - 1 - q) --
+  // and is brought into the general form by a register permutation done with selects (no divergent branch: a
+  // divergent special case here sits on the critical path of the whole group's next barrier):
+  //   A' = [A_0 .. A_{R/2-1}, B_0 .. B_{R/2-1}],  B' = [B_{R/2} .. B_{R-1}, A_{R/2+1} .. A_{R-1}, A_0],  Zh = A_{R/2}
+  // with bins kk_i = i JL (i < R/2), JL / 2 + (i - R/2) JL (i >= R/2); wpost[] holds the matching twiddles.
+  const bool z0 = CF::PAIRED && t == 0;
   auto load_pair = [&](const cpx (&v)[P], const cpx* pb, int i, int& kk, cpx& A, cpx& Bc, cpx& w, cpx& Zh) {
     if constexpr (CF::PAIRED) {
       constexpr int LB = ilog2(RL);
       const int b = i / RL, q = i % RL;
-      if (b == 0 && t == 0) {
-        // thread 0, slot 0: butterflies 0 (bins q JL, partner R - q) and JL / 2 (partner R - 1 - q) pair with themselves
+      w = wpost[i];
+      if (b == 0) {
+        const cpx a_q = v[bitrev(q, LB)];
+        const cpx b_p = v[(BL / 2) * RL + bitrev(RL - 1 - q, LB)];  // general partner
+        cpx a0, b0;  // what thread 0 uses instead
         if (q < RL / 2) {
-          kk = q * JL;
-          A = v[bitrev(q, LB)];
-          Bc = cconj(v[bitrev((RL - q) % RL, LB)]);
-          w = wpost[i];
-          Zh = v[bitrev(RL / 2, LB)];
+          a0 = a_q;
+          b0 = v[bitrev((RL - q) % RL, LB)];  // A_{R-q}; q = 0: A_0 itself (DC)
         } else {
-          const int q2 = q - RL / 2;
-          kk = JL / 2 + q2 * JL;
-          A = v[(BL / 2) * RL + bitrev(q2, LB)];
-          Bc = cconj(v[(BL / 2) * RL + bitrev(RL - 1 - q2, LB)]);
-          w = __ldg(a.post + kk);
+          a0 = v[(BL / 2) * RL + bitrev(q - RL / 2, LB)];               // B_{q - R/2}
+          b0 = v[(BL / 2) * RL + bitrev(RL - 1 - (q - RL / 2), LB)];    // B_{R-1-(q-R/2)}
         }
+        A = make_float2(z0 ? a0.x : a_q.x, z0 ? a0.y : a_q.y);
+        Bc = make_float2(z0 ? b0.x : b_p.x, z0 ? -b0.y : -b_p.y);
+        kk = (z0 && q >= RL / 2) ? JL / 2 + (q - RL / 2) * JL : t + q * JL;
+        if (q == 0) Zh = v[bitrev(RL / 2, LB)];  // only read when kk == 0 (thread 0)
       } else {
         kk = t + b * T + q * JL;
         A = v[b * RL + bitrev(q, LB)];
         Bc = cconj(v[(b + BL / 2) * RL + bitrev(RL - 1 - q, LB)]);
-        w = wpost[i];
       }
     } else {
       kk = t + i * T;
@@ -803,11 +817,13 @@ static int run_r2c_staged(nxs_ctx* ctx, StftArgs a, int64_t channels, cudaStream
   if (rc) return rc;
   a.tw = tabs.tw;
   a.post = tabs.post;
-  if constexpr (CF::XD) {
+  if constexpr (CF::TWC) {
     float2* twc = nullptr;
     rc = get_compact_tw<PL>(ctx, &twc);
     if (rc) return rc;
     a.tw = twc;
+  }
+  if constexpr (CF::XD) {
     if (a.mel_out) return NXS_EUNSUPPORTED;  // the fused log-mel epilogue keeps the single-buffer layout
   }
   const int64_t tpc = (a.M + CF::G - 1) / CF::G;
@@ -969,6 +985,9 @@ int launch_stft(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, 
         if (variant_env() == 3) { using CF = StagedCfg<PL, 512, 4, false, true, true>; NXS_TRY_STAGED(CF, 1); }
         if (variant_env() == 4) { using CF = StagedCfg<PL, 256, 4, false, true, true>; NXS_TRY_STAGED(CF, 2); }
         if (variant_env() == 5 && !a.mel_out) { using CF = StagedCfg<PL, 512, 4, false, true, true, false, true, true>; NXS_TRY_STAGED(CF, 1); }
+        // two warps per frame, 32 points per thread (more independent butterflies per thread, barriers between two warps only)
+        if (variant_env() == 6 && !a.mel_out) { using CF = StagedCfg<Plan<2048, 64, 16, 16, 8>, 384, 4, false, true, true, false, true, false, true>; NXS_TRY_STAGED(CF, 1); }
+        if (variant_env() == 7 && !a.mel_out) { using CF = StagedCfg<Plan<2048, 64, 16, 16, 8>, 256, 4, false, true, true, false, true, false, true>; NXS_TRY_STAGED(CF, 1); }
         { using CF = StagedCfg<PL, 256, 4, false, true, true, false, true>; NXS_TRY_STAGED(CF, 2); }
         return run_r2c<PL, TwTable<PL>, 512>(ctx, a, st);
       }
