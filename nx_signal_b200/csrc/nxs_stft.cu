@@ -984,10 +984,13 @@ int launch_stft(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, 
         if (variant_env() == 2) { using CF = StagedCfg<PL, 256, 4, false, true>; NXS_TRY_STAGED(CF, 1); }
         if (variant_env() == 3) { using CF = StagedCfg<PL, 512, 4, false, true, true>; NXS_TRY_STAGED(CF, 1); }
         if (variant_env() == 4) { using CF = StagedCfg<PL, 256, 4, false, true, true>; NXS_TRY_STAGED(CF, 2); }
-        if (variant_env() == 5 && !a.mel_out) { using CF = StagedCfg<PL, 512, 4, false, true, true, false, true, true>; NXS_TRY_STAGED(CF, 1); }
         // two warps per frame, 32 points per thread (more independent butterflies per thread, barriers between two warps only)
         if (variant_env() == 6 && !a.mel_out) { using CF = StagedCfg<Plan<2048, 64, 16, 16, 8>, 384, 4, false, true, true, false, true, false, true>; NXS_TRY_STAGED(CF, 1); }
         if (variant_env() == 7 && !a.mel_out) { using CF = StagedCfg<Plan<2048, 64, 16, 16, 8>, 256, 4, false, true, true, false, true, false, true>; NXS_TRY_STAGED(CF, 1); }
+        // default for the spectrum outputs: paired split pass, two exchange buffers, one 512-thread CTA per SM
+        // (cfg3 shard: 2.48 ms; paired 256 x 2 (variant 8): 2.52 - 2.64 ms; unpaired (4): 2.53 ms; P = 32 (6 / 7): 2.61 / 2.91 ms);
+        // the fused log-mel epilogue keeps the single-buffer paired layout
+        if (variant_env() != 8 && !a.mel_out) { using CF = StagedCfg<PL, 512, 4, false, true, true, false, true, true>; NXS_TRY_STAGED(CF, 1); }
         { using CF = StagedCfg<PL, 256, 4, false, true, true, false, true>; NXS_TRY_STAGED(CF, 2); }
         return run_r2c<PL, TwTable<PL>, 512>(ctx, a, st);
       }
