@@ -257,17 +257,29 @@ int nxs_stft_f32_host(nxs_ctx* ctx, const float* x, int64_t channels, int64_t le
   // from here on every exit must join the workers
   size_t next_land = 0, enq_slabs = 0;
   int64_t next_h2d = 0, enq_chunks = 0;
+  cudaError_t async_err = cudaSuccess;  // a failed copy / kernel surfaces in the event queries: stop waiting for it
   auto pump = [&]() {  // publish completed copies to the workers
-    while (next_land < enq_slabs && cudaEventQuery(ev_slab[next_land]) == cudaSuccess) {
+    while (next_land < enq_slabs) {
+      const cudaError_t q = cudaEventQuery(ev_slab[next_land]);
+      if (q != cudaSuccess) {
+        if (q != cudaErrorNotReady) async_err = q;
+        break;
+      }
       if (next_land == 0) ctx->host_t[1] = wall_seconds() - t_start;
       job.landed.store((int64_t)++next_land, std::memory_order_release);
     }
-    while (next_h2d < enq_chunks && cudaEventQuery(ev_h2d[next_h2d]) == cudaSuccess)
+    while (next_h2d < enq_chunks) {
+      const cudaError_t q = cudaEventQuery(ev_h2d[next_h2d]);
+      if (q != cudaSuccess) {
+        if (q != cudaErrorNotReady) async_err = q;
+        break;
+      }
       job.h2d_done.store(++next_h2d, std::memory_order_release);
+    }
   };
   auto spin_until = [&](const std::atomic<int>& left) {
     int spins = 0;
-    while (left.load(std::memory_order_acquire) > 0) {
+    while (left.load(std::memory_order_acquire) > 0 && async_err == cudaSuccess) {
       pump();
       cpu_relax();
       if (++spins == 256) {
@@ -275,6 +287,7 @@ int nxs_stft_f32_host(nxs_ctx* ctx, const float* x, int64_t channels, int64_t le
         sched_yield();
       }
     }
+    return async_err == cudaSuccess;
   };
   auto enqueue = [&]() -> int {
     NXS_CUDA(ctx, cudaMemcpyAsync(d_w, window, size_t(frame_length) * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_stream));
@@ -283,7 +296,7 @@ int nxs_stft_f32_host(nxs_ctx* ctx, const float* x, int64_t channels, int64_t le
       const size_t xb = size_t((n - 1) * x_ld + length) * sizeof(float);
       const float* src = x + c0 * x_ld;
       if (stage_in) {
-        spin_until(job.in_left[(size_t)i]);
+        if (!spin_until(job.in_left[(size_t)i])) return set_cuda_error(ctx, async_err, "nxs_stft_f32_host (input staging)");
         src = (const float*)(h_in + (i & 1) * in_slot);
       }
       NXS_CUDA(ctx, cudaMemcpyAsync(d_x + c0 * x_ld, src, xb, cudaMemcpyHostToDevice, ctx->copy_stream));
@@ -298,7 +311,8 @@ int nxs_stft_f32_host(nxs_ctx* ctx, const float* x, int64_t channels, int64_t le
       for (int s = chunk_first_slab[(size_t)i]; s < chunk_first_slab[(size_t)i + 1]; ++s) {
         const int64_t r0 = slab_r0[(size_t)s], r1 = slab_r1[(size_t)s];
         if (unstage) {
-          if (s >= nslots) spin_until(job.slab_left[(size_t)(s - nslots)]);  // the ring slot has been copied out
+          if (s >= nslots && !spin_until(job.slab_left[(size_t)(s - nslots)]))  // the ring slot has been copied out
+            return set_cuda_error(ctx, async_err, "nxs_stft_f32_host (result ring)");
           NXS_CUDA(ctx, cudaMemcpyAsync(h_ring + size_t(s % nslots) * ring_slot, d_z + size_t(r0) * z_ld,
                                         size_t(r1 - r0) * z_ld * sizeof(float2), cudaMemcpyDeviceToHost, ctx->out_stream));
         } else if (mirror) {
@@ -321,6 +335,7 @@ int nxs_stft_f32_host(nxs_ctx* ctx, const float* x, int64_t channels, int64_t le
       for (; next_land < nslabs;) {
         NXS_CUDA(ctx, cudaEventSynchronize(ev_slab[next_land]));
         pump();
+        if (async_err != cudaSuccess) return set_cuda_error(ctx, async_err, "nxs_stft_f32_host (device to host)");
       }
     }
     return NXS_OK;

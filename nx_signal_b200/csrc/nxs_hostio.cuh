@@ -42,7 +42,8 @@ inline int ensure_events(nxs_ctx* ctx, size_t n) {
 }
 
 inline HostPool* ensure_pool(nxs_ctx* ctx) {
-  if (!ctx->pool) ctx->pool = new HostPool(HostPool::default_threads());
+  // at least one worker besides the calling thread: the staged host calls wait for items only workers run
+  if (!ctx->pool) ctx->pool = new HostPool(HostPool::default_threads() < 2 ? 2 : HostPool::default_threads());
   return ctx->pool;
 }
 
