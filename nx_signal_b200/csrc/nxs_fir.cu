@@ -772,6 +772,10 @@ int launch_fir(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, i
   // per-group F = 1024 kernel (V = 1025 - K, 88 - 98 % kept) is the better trade
   const bool short_on_long_rows = K >= 16 && K <= 129 && pg && variant != 2 && a.out_len >= 8192;
   if (K >= 16 && K <= 129 && !short_on_long_rows) return run_fir<Plan<256, 16, 16, 16>, 256, 2>(ctx, a, channels, taps, st);
+  // mid-size filters: the real-packed kernel at N = 1024 (one 2048-sample real block per transform pair keeps
+  // 2049 - K outputs; the pair kernel keeps 2 x (1025 - K): 1794 vs 1540 at K = 255, 1536 vs 1024 at K = 513)
+  if (K > 129 && K <= 513 && pg && variant != 1 && variant != 3 && a.out_len >= 8192)
+    return run_fir_r2c<Plan<1024, 64, 8, 16, 8>, 384, 2>(ctx, a, channels, taps, st);
   if (short_on_long_rows || (K > 129 && K <= 513)) {
     if (pg && variant == 1) return run_fir_pg<Plan<1024, 64, 8, 16, 8>, 256, 2>(ctx, a, channels, taps, st);
     if (pg) return run_fir_pg<Plan<1024, 64, 8, 16, 8>, 384, 2>(ctx, a, channels, taps, st);
