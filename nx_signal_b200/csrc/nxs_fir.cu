@@ -772,16 +772,17 @@ int launch_fir(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, i
   // per-group F = 1024 kernel (V = 1025 - K, 88 - 98 % kept) is the better trade
   const bool short_on_long_rows = K >= 16 && K <= 129 && pg && variant != 2 && a.out_len >= 8192;
   if (K >= 16 && K <= 129 && !short_on_long_rows) return run_fir<Plan<256, 16, 16, 16>, 256, 2>(ctx, a, channels, taps, st);
-  // mid-size filters: the real-packed kernel at N = 1024 (one 2048-sample real block per transform pair keeps
-  // 2049 - K outputs; the pair kernel keeps 2 x (1025 - K): 1794 vs 1540 at K = 255, 1536 vs 1024 at K = 513)
-  if (K > 129 && K <= 513 && pg && variant != 1 && variant != 3 && a.out_len >= 8192)
-    return run_fir_r2c<Plan<1024, 64, 8, 16, 8>, 384, 2>(ctx, a, channels, taps, st);
+  // mid-size filters on long rows take the real-packed N = 4096 kernel below from K = 192 on (94 - 98 % of every
+  // 8192-sample block kept); measured on 64 ch x 600 s: K = 255 pair kernel 4.95 ms, real-packed N = 1024 5.77 ms
+  // (variant 6: small transforms, little work per barrier); K = 513 7.23 / 5.56 ms
+  const bool mid_r2c = K >= 192 && K <= 513 && a.out_len >= 32768;
+  if (mid_r2c && pg && variant == 6) return run_fir_r2c<Plan<1024, 64, 8, 16, 8>, 384, 2>(ctx, a, channels, taps, st);
   if (short_on_long_rows || (K > 129 && K <= 513)) {
     if (pg && variant == 1) return run_fir_pg<Plan<1024, 64, 8, 16, 8>, 256, 2>(ctx, a, channels, taps, st);
     if (pg) return run_fir_pg<Plan<1024, 64, 8, 16, 8>, 384, 2>(ctx, a, channels, taps, st);
     return run_fir<Plan<1024, 64, 8, 16, 8>, 256, 2>(ctx, a, channels, taps, st);
   }
-  if (K > 513 && pg && variant != 1 && variant != 3) {
+  if ((K > 513 || mid_r2c) && pg && variant != 1 && variant != 3) {
     // real-packed overlap-save: one 8192-sample real block per 4096-point transform pair, V = 8193 - KP
     // outputs kept; long filters are cut into n equal runs of KP taps whose partial convolutions are
     // accumulated, y[n] += (x * h_p)[n - p KP] (work per output ~ n / (8193 - K / n); later passes

@@ -31,9 +31,13 @@ struct MelArgs {
   const int* offs;   // [mel_bins] offset of the run in wts
   float* out;        // [C][M][mel_bins]
   int* chmax;        // [C] ordered-int maximum of log_spec per channel
-  FastDiv div_m;     // f / M when total_frames < 2^31 (use_fastdiv)
+  // a warp walks tiles of kMelTile consecutive frames of one channel (one atomicMax per tile: with frames dealt
+  // round-robin a warp changed channel on almost every frame when M is small, 360 k contended atomics on cfg5's shape)
+  int64_t tiles_per_channel, total_tiles;
+  FastDiv div_tpc;   // tile / tiles_per_channel when total_tiles < 2^31 (use_fastdiv)
   int use_fastdiv;
 };
+constexpr int kMelTile = 8;
 
 __device__ __forceinline__ int float_key(float v) {
   const int b = __float_as_int(v);
@@ -45,55 +49,53 @@ __global__ void __launch_bounds__(256) mel_logspec_kernel(const MelArgs a) {
   extern __shared__ float pw_all[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   float* pw = pw_all + (size_t)warp * a.half;
-  int64_t cur_c = -1;
-  float cur_max = -INFINITY;
-  for (int64_t f = (int64_t)blockIdx.x * wpb + warp; f < a.total_frames; f += (int64_t)gridDim.x * wpb) {
-    const int64_t c = a.use_fastdiv ? (int64_t)a.div_m.div((int)f) : f / a.M;
-    if (c != cur_c) {
-      if (cur_c >= 0 && lane == 0) atomicMax(a.chmax + cur_c, float_key(cur_max));
-      cur_c = c;
-      cur_max = -INFINITY;
-    }
-    const float2* __restrict__ zf = a.z + f * a.z_ld;
-    int k = lane;
-    for (; k + 96 < a.half; k += 128) {  // four independent loads in flight per lane
-      const float2 v0 = __ldcs(zf + k), v1 = __ldcs(zf + k + 32), v2 = __ldcs(zf + k + 64), v3 = __ldcs(zf + k + 96);
-      pw[k] = v0.x * v0.x + v0.y * v0.y;  // Nx.abs(z) ** 2
-      pw[k + 32] = v1.x * v1.x + v1.y * v1.y;
-      pw[k + 64] = v2.x * v2.x + v2.y * v2.y;
-      pw[k + 96] = v3.x * v3.x + v3.y * v3.y;
-    }
-    for (; k < a.half; k += 32) {
-      const float2 v = __ldcs(zf + k);
-      pw[k] = v.x * v.x + v.y * v.y;
-    }
-    __syncwarp();
-    float m = -INFINITY;
-    for (int j = lane; j < a.mel_bins; j += 32) {
-      const int s = a.start[j], n = a.count[j];
-      const float* __restrict__ w = a.wts + a.offs[j];
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;  // independent partial sums (same order as the fused epilogue)
-      const float* __restrict__ pp = pw + s;
-      int i = 0;
-      for (; i + 4 <= n; i += 4) {
-        a0 = fmaf(pp[i], __ldg(w + i), a0);
-        a1 = fmaf(pp[i + 1], __ldg(w + i + 1), a1);
-        a2 = fmaf(pp[i + 2], __ldg(w + i + 2), a2);
-        a3 = fmaf(pp[i + 3], __ldg(w + i + 3), a3);
+  for (int64_t tile = (int64_t)blockIdx.x * wpb + warp; tile < a.total_tiles; tile += (int64_t)gridDim.x * wpb) {
+    const int64_t c = a.use_fastdiv ? (int64_t)a.div_tpc.div((int)tile) : tile / a.tiles_per_channel;
+    const int64_t m0 = (tile - c * a.tiles_per_channel) * kMelTile;
+    const int64_t m1 = m0 + kMelTile < a.M ? m0 + kMelTile : a.M;
+    float cur_max = -INFINITY;
+    for (int64_t f = c * a.M + m0; f < c * a.M + m1; ++f) {
+      const float2* __restrict__ zf = a.z + f * a.z_ld;
+      int k = lane;
+      for (; k + 96 < a.half; k += 128) {  // four independent loads in flight per lane
+        const float2 v0 = __ldcs(zf + k), v1 = __ldcs(zf + k + 32), v2 = __ldcs(zf + k + 64), v3 = __ldcs(zf + k + 96);
+        pw[k] = v0.x * v0.x + v0.y * v0.y;  // Nx.abs(z) ** 2
+        pw[k + 32] = v1.x * v1.x + v1.y * v1.y;
+        pw[k + 64] = v2.x * v2.x + v2.y * v2.y;
+        pw[k + 96] = v3.x * v3.x + v3.y * v3.y;
       }
-      for (; i < n; ++i) a0 = fmaf(pp[i], __ldg(w + i), a0);
-      const float acc = (a0 + a1) + (a2 + a3);
-      // Nx.log(Nx.clip(mel, 1e-10, inf)) / Nx.log(10)
-      const float v = __log2f(fmaxf(acc, 1.0e-10f)) * 0.30102999566f;
-      a.out[f * a.mel_bins + j] = v;
-      m = fmaxf(m, v);
+      for (; k < a.half; k += 32) {
+        const float2 v = __ldcs(zf + k);
+        pw[k] = v.x * v.x + v.y * v.y;
+      }
+      __syncwarp();
+      float m = -INFINITY;
+      for (int j = lane; j < a.mel_bins; j += 32) {
+        const int s = a.start[j], n = a.count[j];
+        const float* __restrict__ w = a.wts + a.offs[j];
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;  // independent partial sums (same order as the fused epilogue)
+        const float* __restrict__ pp = pw + s;
+        int i = 0;
+        for (; i + 4 <= n; i += 4) {
+          a0 = fmaf(pp[i], __ldg(w + i), a0);
+          a1 = fmaf(pp[i + 1], __ldg(w + i + 1), a1);
+          a2 = fmaf(pp[i + 2], __ldg(w + i + 2), a2);
+          a3 = fmaf(pp[i + 3], __ldg(w + i + 3), a3);
+        }
+        for (; i < n; ++i) a0 = fmaf(pp[i], __ldg(w + i), a0);
+        const float acc = (a0 + a1) + (a2 + a3);
+        // Nx.log(Nx.clip(mel, 1e-10, inf)) / Nx.log(10)
+        const float v = __log2f(fmaxf(acc, 1.0e-10f)) * 0.30102999566f;
+        a.out[f * a.mel_bins + j] = v;
+        m = fmaxf(m, v);
+      }
+  #pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      cur_max = fmaxf(cur_max, m);
+      __syncwarp();
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    cur_max = fmaxf(cur_max, m);
-    __syncwarp();
+    if (lane == 0) atomicMax(a.chmax + c, float_key(cur_max));
   }
-  if (cur_c >= 0 && lane == 0) atomicMax(a.chmax + cur_c, float_key(cur_max));
 }
 
 // log_spec = max(log_spec, reduce_max(log_spec) - 8); (log_spec + 4) / 4   (lib/nx_signal.ex:512-513)
@@ -298,8 +300,10 @@ int launch_stft_to_mel(nxs_ctx* ctx, const float2* z, int64_t channels, int64_t 
   a.M = num_frames;
   a.z_ld = z_ld;
   a.total_frames = channels * num_frames;
-  a.use_fastdiv = a.total_frames < (int64_t(1) << 31) && num_frames < (int64_t(1) << 31);
-  a.div_m = FastDiv(a.use_fastdiv ? (int)num_frames : 1);
+  a.tiles_per_channel = (num_frames + kMelTile - 1) / kMelTile;
+  a.total_tiles = a.tiles_per_channel * channels;
+  a.use_fastdiv = a.total_tiles < (int64_t(1) << 31);
+  a.div_tpc = FastDiv(a.use_fastdiv ? (int)a.tiles_per_channel : 1);
   a.half = (int)half;
   a.mel_bins = (int)mel_bins;
   a.wts = bank->d_wts;
@@ -312,7 +316,7 @@ int launch_stft_to_mel(nxs_ctx* ctx, const float2* z, int64_t channels, int64_t 
   while (wpb > 1 && size_t(wpb) * half * sizeof(float) > 96 * 1024) wpb >>= 1;
   const size_t smem = size_t(wpb) * (half > 0 ? half : 1) * sizeof(float);
   NXS_CUDA(ctx, cudaFuncSetAttribute(mel_logspec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
-  int64_t grid = (a.total_frames + wpb - 1) / wpb;
+  int64_t grid = (a.total_tiles + wpb - 1) / wpb;
   if (grid > int64_t(ctx->sm_count) * 8) grid = int64_t(ctx->sm_count) * 8;
   prof_begin(ctx, st);
   mel_logspec_kernel<<<(unsigned)grid, wpb * 32, smem, st>>>(a);
