@@ -777,7 +777,8 @@ int launch_fir(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, i
   // (variant 6: small transforms, little work per barrier); K = 513 7.23 / 5.56 ms
   const bool mid_r2c = K >= 192 && K <= 513 && a.out_len >= 32768;
   if (mid_r2c && pg && variant == 6) return run_fir_r2c<Plan<1024, 64, 8, 16, 8>, 384, 2>(ctx, a, channels, taps, st);
-  if (short_on_long_rows || (K > 129 && K <= 513)) {
+  const bool r2c_mid = mid_r2c && pg && variant != 1 && variant != 3;  // served by the real-packed block below
+  if (!r2c_mid && (short_on_long_rows || (K > 129 && K <= 513))) {
     if (pg && variant == 1) return run_fir_pg<Plan<1024, 64, 8, 16, 8>, 256, 2>(ctx, a, channels, taps, st);
     if (pg) return run_fir_pg<Plan<1024, 64, 8, 16, 8>, 384, 2>(ctx, a, channels, taps, st);
     return run_fir<Plan<1024, 64, 8, 16, 8>, 256, 2>(ctx, a, channels, taps, st);
