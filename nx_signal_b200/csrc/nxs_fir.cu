@@ -531,6 +531,17 @@ __global__ void __launch_bounds__(THREADS, MINB) fir_ols_r2c_kernel(const FirArg
             __stcs(y2 + i, o);
           }
         }
+    } else if (interior) {  // odd output offset (or odd K - 1): element stores, no bounds to check
+      float* __restrict__ y0 = yrow + obase;
+#pragma unroll
+      for (int b = 0; b < B0; ++b)
+#pragma unroll
+        for (int q = 0; q < R0; ++q) {
+          const int i = fft_out_index<PL>(t, b, q);
+          const cpx r = u[fft_out_reg<PL>(b, q)];
+          if (2 * i >= K1) __stcs(y0 + 2 * i, a.accumulate ? r.y + y0[2 * i] : r.y);
+          if (2 * i + 1 >= K1) __stcs(y0 + 2 * i + 1, a.accumulate ? r.x + y0[2 * i + 1] : r.x);
+        }
     } else {
 #pragma unroll
       for (int b = 0; b < B0; ++b)
@@ -772,10 +783,11 @@ int launch_fir(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, i
   // per-group F = 1024 kernel (V = 1025 - K, 88 - 98 % kept) is the better trade
   const bool short_on_long_rows = K >= 16 && K <= 129 && pg && variant != 2 && a.out_len >= 8192;
   if (K >= 16 && K <= 129 && !short_on_long_rows) return run_fir<Plan<256, 16, 16, 16>, 256, 2>(ctx, a, channels, taps, st);
-  // mid-size filters on long rows take the real-packed N = 4096 kernel below from K = 192 on (94 - 98 % of every
-  // 8192-sample block kept); measured on 64 ch x 600 s: K = 255 pair kernel 4.95 ms, real-packed N = 1024 5.77 ms
-  // (variant 6: small transforms, little work per barrier); K = 513 7.23 / 5.56 ms
-  const bool mid_r2c = K >= 192 && K <= 513 && a.out_len >= 32768;
+  // mid-size filters on long rows take the real-packed N = 4096 kernel below from K = 320 on (94 - 96 % of every
+  // 8192-sample block kept).  Measured on 64 ch x 600 s, pair kernel (F = 1024) / real-packed N = 4096 / real-packed
+  // N = 1024 (variant 6: small transforms, little work per barrier): K = 193 4.56 / 4.83 / - ms, K = 255 4.95 / 5.47 /
+  // 5.77, K = 385 5.84 / 4.93 / 5.14, K = 513 7.23 / 5.01 / 5.56 (profiles/r02_fir_timings.txt)
+  const bool mid_r2c = K >= 320 && K <= 513 && a.out_len >= 32768;
   if (mid_r2c && pg && variant == 6) return run_fir_r2c<Plan<1024, 64, 8, 16, 8>, 384, 2>(ctx, a, channels, taps, st);
   const bool r2c_mid = mid_r2c && pg && variant != 1 && variant != 3;  // served by the real-packed block below
   if (!r2c_mid && (short_on_long_rows || (K > 129 && K <= 513))) {
