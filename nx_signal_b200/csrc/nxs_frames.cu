@@ -53,25 +53,32 @@ __global__ void __launch_bounds__(256) as_windowed_kernel_v4(const float* __rest
                                                              int stride, int lo, int reflect, int M,
                                                              const FastDiv div_n4, const FastDiv div_m, int total4,
                                                              float4* __restrict__ out) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += gridDim.x * blockDim.x) {
+  // four independent 128-bit loads in flight per thread, then four streaming stores (the frames are written once
+  // and never re-read here; the 4x re-read of the input stays in L2)
+  auto fetch = [&](int i) -> float4 {
     const int fm = div_n4.div(i), n = (i - fm * N4) * 4;
     const int c = div_m.div(fm), m = fm - c * M;
     const int64_t src = (int64_t)m * stride + n - lo;
     const float* __restrict__ row = x + c * x_ld;
-    float4 v;
-    if (src >= 0 && src + 3 < L) {
-      v = *reinterpret_cast<const float4*>(row + src);
-    } else {
-      float e[4];
+    if (src >= 0 && src + 3 < L) return *reinterpret_cast<const float4*>(row + src);
+    float e[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int64_t sk = src + k;
-        e[k] = (sk >= 0 && sk < L) ? row[sk] : (reflect ? row[reflect_index(sk, L)] : 0.f);
-      }
-      v = make_float4(e[0], e[1], e[2], e[3]);
+    for (int k = 0; k < 4; ++k) {
+      const int64_t sk = src + k;
+      e[k] = (sk >= 0 && sk < L) ? row[sk] : (reflect ? row[reflect_index(sk, L)] : 0.f);
     }
-    out[i] = v;
+    return make_float4(e[0], e[1], e[2], e[3]);
+  };
+  const int step = gridDim.x * blockDim.x;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i < total4 - 3 * (int64_t)step; i += 4 * step) {
+    const float4 v0 = fetch(i), v1 = fetch(i + step), v2 = fetch(i + 2 * step), v3 = fetch(i + 3 * step);
+    __stcs(out + i, v0);
+    __stcs(out + i + step, v1);
+    __stcs(out + i + 2 * step, v2);
+    __stcs(out + i + 3 * step, v3);
   }
+  for (; i < total4; i += step) __stcs(out + i, fetch(i));
 }
 
 int launch_as_windowed(nxs_ctx* ctx, const void* x, int elem_size, int64_t channels, int64_t length,
