@@ -537,19 +537,23 @@ def e2e_legs(env, x, w, zo, zo_frames, args):
         # ... and with cudaHostRegister / cudaHostUnregister of both buffers inside the timed call
         rt = torch.cuda.cudart()
 
+        reg_modes = []
+
         def registered():
-            rt.cudaHostRegister(xp.ctypes.data, xp.nbytes, 0)
-            rt.cudaHostRegister(zp.ctypes.data, zp.nbytes, 0)
+            ok = int(rt.cudaHostRegister(xp.ctypes.data, xp.nbytes, 0)) == 0 and \
+                int(rt.cudaHostRegister(zp.ctypes.data, zp.nbytes, 0)) == 0
             try:
                 call(xp.ctypes.data, zp.ctypes.data)
+                reg_modes.append((ok, _lib.host_mode(env.local_rank)))
             finally:
                 rt.cudaHostUnregister(zp.ctypes.data)
                 rt.cudaHostUnregister(xp.ctypes.data)
 
-        s = timed(registered, 1, warm=0)
-        e2e["pageable_host_register_in_call"] = {"ms_per_step": 1e3 * s, "value": world * FRAMES_PER_GPU / s,
-                                                "unit": "frames/s",
-                                                "path": "cudaHostRegister(x), cudaHostRegister(z), the pinned path, unregister"}
+        s_reg = timed(registered, 1, warm=0)
+        e2e["pageable_host_register_in_call"] = {
+            "ms_per_step": 1e3 * s_reg, "value": world * FRAMES_PER_GPU / s_reg, "unit": "frames/s",
+            "registered_ok": bool(reg_modes and reg_modes[-1][0]), "transfer_mode": reg_modes[-1][1] if reg_modes else None,
+            "path": "cudaHostRegister(x), cudaHostRegister(z), the pinned path, unregister"}
         del xp, zp
     except Exception as ex:  # report, never fake
         e2e["pageable"] = {"error": repr(ex)[:300]}
