@@ -476,14 +476,15 @@ def e2e_legs(env, x, w, zo, zo_frames, args):
         return env.max_over_ranks((time.perf_counter() - t) / n)
 
     step = lambda: call(A.ptr(xh), A.ptr(zh))  # noqa: E731
-    # two warm-up calls let the context measure both transfer modes (full / one-sided + host mirror) under
-    # the load of all ranks; the timed calls then use the cheaper one
+    # the warm-up calls let the context measure its transfer modes (full / one-sided + host mirror / mixed) under
+    # the load of all ranks; the timed calls then use the cheapest
     _lib.set_host_mode(-1, env.local_rank)
-    s = timed(step, args.e2e_steps, warm=3)
+    s = timed(step, args.e2e_steps, warm=4)
     mode = _lib.host_mode(env.local_rank)
     e2e = {"value": world * FRAMES_PER_GPU / s, "unit": "frames/s",
            "h2d_bytes_per_step": int(xh.numel() * 4 + NFFT * 4),
-           "d2h_bytes_per_step": int(CHANNELS * M * ((NFFT // 2 + 1) if "onesided" in mode["result"] else NFFT) * 8),
+           "d2h_bytes_per_step": int(CHANNELS * M * 8 * ((NFFT // 2 + 1) if mode["result"].startswith("onesided") else
+                                                         (3 * (NFFT // 2 + 1) + NFFT) // 4 if mode["result"].startswith("mixed") else NFFT)),
            "host_result_bytes_per_step": int(zh.numel() * 8), "steps": args.e2e_steps, "ms_per_step": 1e3 * s,
            "transfer_mode_chosen": mode["result"],
            "path": "nxs_stft_f32_host on pinned host buffers (wall clock, max over ranks): H2D | kernel | D2H in slabs; "
@@ -491,7 +492,8 @@ def e2e_legs(env, x, w, zo, zo_frames, args):
                    "and moving bins 0..nfft/2 while host threads write the conjugate-mirror bins; result = the "
                    "reference's two-sided c64 tensor, bit-identical to the device entry"}
     e2e["host_timeline_ms"] = [round(1e3 * t, 2) for t in _lib.host_timeline(env.local_rank)]
-    for forced, key in ((1, "ms_per_step_onesided_d2h_host_mirror"), (0, "ms_per_step_full_d2h_no_host_mirror")):
+    for forced, key in ((1, "ms_per_step_onesided_d2h_host_mirror"), (0, "ms_per_step_full_d2h_no_host_mirror"),
+                        (3, "ms_per_step_mixed_3_of_4_chunks_mirrored")):
         _lib.set_host_mode(forced, env.local_rank)
         e2e[key] = 1e3 * timed(step, 2, warm=1)
     _lib.set_host_mode(-1, env.local_rank)

@@ -100,15 +100,16 @@ int nxs_ctx_profile_read(nxs_ctx* ctx, double* total_ms, int64_t* launches);
  * memory, [3] host mirror threads done (= result complete).  bench.py reports them. */
 int nxs_ctx_host_timeline(const nxs_ctx* ctx, double out_seconds[4]);
 
-/* nxs_stft_f32_host moves the result in one of three ways, reported by nxs_ctx_host_mode for the
+/* nxs_stft_f32_host moves the result in one of four ways, reported by nxs_ctx_host_mode for the
  * last call: 0 = both spectrum halves over PCIe; 1 = bins 0 .. fft_length/2 over PCIe straight into
- * the caller's rows, host threads write the conjugate-mirror bins; 2 = the result buffer is pageable
- * (not cudaHostRegister'ed -- e.g. a BEAM binary): the lower half lands in the context's pinned ring
- * and host threads copy it out and write the mirror half in one pass.  +16: the input was pageable
- * and went through the pinned input ring.  For pinned results the context measures the cost of
- * modes 0 and 1 on its own calls and uses the cheaper one (which one depends on whether the box is
- * short of PCIe or of host memory bandwidth); nxs_ctx_set_host_mode pins it: -1 auto (default),
- * 0 or 1.  All modes give bit-identical results. */
+ * the caller's rows, host threads write the conjugate-mirror bins; 3 = mixed: three channel chunks of
+ * four as in 1, the fourth as in 0 (balances PCIe against host memory bandwidth); 2 = the result
+ * buffer is pageable (not cudaHostRegister'ed -- e.g. a BEAM binary): the lower half lands in the
+ * context's pinned ring and host threads copy it out and write the mirror half in one pass.
+ * +16: the input was pageable and went through the pinned input ring.  For pinned results the
+ * context measures the cost of modes 0, 1 and 3 on its own calls and uses the cheapest (which one
+ * depends on whether the box is short of PCIe or of host memory bandwidth); nxs_ctx_set_host_mode
+ * pins it: -1 auto (default), 0, 1 or 3.  All modes give bit-identical results. */
 int nxs_ctx_set_host_mode(nxs_ctx* ctx, int mode);
 int nxs_ctx_host_mode(const nxs_ctx* ctx, int* mode);
 

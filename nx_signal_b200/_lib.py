@@ -170,7 +170,8 @@ def host_timeline(device=0):
     return [float(v) for v in t]
 
 
-HOST_MODES = {0: "full_d2h", 1: "onesided_d2h+host_mirror", 2: "onesided_d2h+pinned_ring_unstage"}
+HOST_MODES = {0: "full_d2h", 1: "onesided_d2h+host_mirror", 2: "onesided_d2h+pinned_ring_unstage",
+              3: "mixed: 3 of 4 chunks onesided_d2h+host_mirror, 1 of 4 full_d2h"}
 
 
 def host_mode(device=0):
@@ -182,7 +183,7 @@ def host_mode(device=0):
 
 
 def set_host_mode(mode, device=0):
-    """-1: the context picks the cheaper mode from its own measurements (default); 0 / 1: pin it."""
+    """-1: the context picks the cheapest mode from its own measurements (default); 0 / 1 / 3: pin it."""
     check(lib().nxs_ctx_set_host_mode(context(device), int(mode)))
 
 

@@ -80,9 +80,10 @@ struct nxs_ctx {
   std::vector<cudaEvent_t> slab_events;
   nxs::HostPool* pool = nullptr;
   double host_t[4] = {0, 0, 0, 0};  // nxs_ctx_host_timeline
-  // nxs_stft_f32_host on pinned results: 0 = both spectrum halves over PCIe, 1 = lower half + host mirror;
+  // nxs_stft_f32_host on pinned results: 0 = both spectrum halves over PCIe, 1 = lower half + host mirror,
+  // 3 = mixed (three chunks of four as 1, one as 0);
   // measured cost (seconds per result byte) of each, and the mode pinned by nxs_ctx_set_host_mode (-1: auto)
-  double host_cost[2] = {0, 0};
+  double host_cost[4] = {0, 0, 0, 0};
   int host_mode_forced = -1, host_mode_last = 0;
   uint64_t host_calls = 0;
   // stream ordering of the context's shared device state (d_coef, d_scratch, tables under construction):

@@ -88,19 +88,31 @@ struct StftHostJob {
   }
 };
 
-// cost model of the pinned-result modes (seconds per result byte, exponentially averaged)
-int choose_mode(nxs_ctx* ctx, bool can_mirror, size_t result_bytes) {
+// Transfer modes of a pinned result: 0 = both spectrum halves over PCIe, 1 = lower half + host mirror,
+// 3 = mixed (three chunks of four as in 1, the fourth as in 0).  PCIe and the host memory system are separate
+// bottlenecks: mode 1 halves the PCIe bytes but adds a read and a write of host memory per mirrored row, mode 0
+// the reverse; when a box is short of both, the mix balances them.  Cost model: seconds per result byte of each
+// mode, exponentially averaged over the context's own calls.
+constexpr int kModes[3] = {1, 0, 3};
+int choose_mode(nxs_ctx* ctx, bool can_mirror, size_t result_bytes, int64_t nchunks) {
   if (!can_mirror) return 0;
   if (const char* e = getenv("NXS_HOST_NO_MIRROR")) {
     if (e[0] && e[0] != '0') return 0;
   }
-  if (ctx->host_mode_forced >= 0) return ctx->host_mode_forced ? 1 : 0;
+  const bool mix_ok = nchunks >= 4;
+  if (ctx->host_mode_forced >= 0) return ctx->host_mode_forced == 3 && !mix_ok ? 1 : ctx->host_mode_forced;
   if (result_bytes < (size_t(32) << 20)) return 1;  // too small to measure: one-sided transfer
-  if (ctx->host_cost[1] <= 0.0) return 1;           // unknown costs first
-  if (ctx->host_cost[0] <= 0.0) return 0;
-  const int best = ctx->host_cost[1] <= ctx->host_cost[0] ? 1 : 0;
-  // re-probe the other mode every 16th call: what the box is short of changes with its load
-  return (++ctx->host_calls % 16 == 0) ? 1 - best : best;
+  for (int m : kModes)                              // unknown costs first
+    if (ctx->host_cost[m] <= 0.0 && (m != 3 || mix_ok)) return m;
+  int best = 1;
+  for (int m : kModes)
+    if ((m != 3 || mix_ok) && ctx->host_cost[m] < ctx->host_cost[best]) best = m;
+  // re-probe another mode every 16th call: what the box is short of changes with its load
+  if (++ctx->host_calls % 16 == 0) {
+    const int other = kModes[(ctx->host_calls / 16) % 3];
+    if (other != best && (other != 3 || mix_ok)) return other;
+  }
+  return best;
 }
 
 }  // namespace
@@ -111,7 +123,7 @@ using namespace nxs;
 extern "C" {
 
 int nxs_ctx_set_host_mode(nxs_ctx* ctx, int mode) {
-  if (!ctx || mode < -1 || mode > 1) return NXS_EINVAL;
+  if (!ctx || mode < -1 || mode > 3 || mode == 2) return NXS_EINVAL;
   ctx->host_mode_forced = mode;
   return NXS_OK;
 }
@@ -142,20 +154,35 @@ int nxs_stft_f32_host(nxs_ctx* ctx, const float* x, int64_t channels, int64_t le
   const size_t result_bytes = size_t(rows) * size_t(fft_length) * sizeof(float2);
   const bool z_pinned = host_is_pinned(z), x_pinned = host_is_pinned(x);
   const bool can_mirror = stft_has_exact_mirror(fft_length);
-  // pageable result: always the one-sided transfer -- the pass that copies a slab out of the ring
-  // writes the mirror half too, so it costs no extra read
-  const bool mirror = z_pinned ? choose_mode(ctx, can_mirror, result_bytes) == 1 : can_mirror;
   const bool unstage = !z_pinned;
   const bool stage_in = !x_pinned;
-  ctx->host_mode_last = (unstage ? 2 : mirror ? 1 : 0) | (stage_in ? 16 : 0);
-
-  const int64_t nout = mirror ? fft_length / 2 + 1 : fft_length;
-  const int64_t z_ld = mirror ? (nout + 3) / 4 * 4 : fft_length;  // device row stride (32-byte multiple)
+  // geometry of the two row forms on the device: bins 0 .. nfft/2 (pitch a multiple of 32 bytes) or all bins
+  const int64_t nout_m = fft_length / 2 + 1, zld_m = (nout_m + 3) / 4 * 4;
+  // channel chunks (~128 MiB of one-sided device result each)
+  const size_t chunk_unit = size_t(M) * size_t(can_mirror ? zld_m : fft_length) * sizeof(float2);
+  int64_t cc = int64_t((size_t(128) << 20) / (chunk_unit ? chunk_unit : 1));
+  if (cc < 1) cc = 1;
+  if (cc > channels) cc = channels;
+  const int64_t nchunks = (channels + cc - 1) / cc;
+  // pageable result: always the one-sided transfer -- the pass that copies a slab out of the ring
+  // writes the mirror half too, so it costs no extra read
+  const int level = z_pinned ? choose_mode(ctx, can_mirror, result_bytes, nchunks) : (can_mirror ? 1 : 0);
+  ctx->host_mode_last = (unstage ? 2 : level) | (stage_in ? 16 : 0);
+  std::vector<char> cm((size_t)nchunks);           // chunk i moves the lower half only (and is mirrored on the host)
+  std::vector<size_t> dz_off((size_t)nchunks + 1);  // its first row in the device result, in complex elements
+  bool mirror = false;                              // any chunk mirrored
+  dz_off[0] = 0;
+  for (int64_t i = 0; i < nchunks; ++i) {
+    cm[(size_t)i] = level == 1 || (level == 3 && (i & 3) != 3);
+    mirror = mirror || cm[(size_t)i];
+    const int64_t n = channels - i * cc < cc ? channels - i * cc : cc;
+    dz_off[(size_t)i + 1] = dz_off[(size_t)i] + size_t(n) * size_t(M) * size_t(cm[(size_t)i] ? zld_m : fft_length);
+  }
+  const int64_t nout = can_mirror && (unstage || mirror) ? nout_m : fft_length;  // bins per staged row (host items)
   const size_t in_bytes = size_t((channels - 1) * x_ld + length) * sizeof(float);
-  const size_t dev_per_ch = size_t(M) * size_t(z_ld) * sizeof(float2);
   rc = grow_buf(ctx, &ctx->d_stage_in, &ctx->d_stage_in_bytes, in_bytes + size_t(frame_length) * sizeof(float) + 512, false);
   if (rc) return rc;
-  rc = grow_buf(ctx, &ctx->d_stage_out, &ctx->d_stage_out_bytes, dev_per_ch * size_t(channels) + 256, false);
+  rc = grow_buf(ctx, &ctx->d_stage_out, &ctx->d_stage_out_bytes, dz_off[(size_t)nchunks] * sizeof(float2) + 256, false);
   if (rc) return rc;
   if (!ctx->out_stream) NXS_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->out_stream, cudaStreamNonBlocking));
   float* d_x = (float*)ctx->d_stage_in;
@@ -163,26 +190,25 @@ int nxs_stft_f32_host(nxs_ctx* ctx, const float* x, int64_t channels, int64_t le
   float2* d_z = (float2*)ctx->d_stage_out;
   float2* hz = reinterpret_cast<float2*>(z);
 
-  // channel chunks (~128 MiB of device result each) and D2H slabs (whole 64-frame work items, a few
-  // MiB on the wire: small enough that the host threads read a slab while it is still cache-
-  // resident, large enough to keep the copy engine busy)
-  int64_t cc = int64_t((size_t(128) << 20) / (dev_per_ch ? dev_per_ch : 1));
-  if (cc < 1) cc = 1;
-  if (cc > channels) cc = channels;
-  const int64_t nchunks = (channels + cc - 1) / cc;
+  // D2H slabs (whole 64-frame work items, a few MiB on the wire: small enough that the host threads read a
+  // slab while it is still cache-resident, large enough to keep the copy engine busy)
   size_t slab_bytes = size_t(8) << 20;
   if (const char* e = getenv("NXS_HOST_SLAB_KB")) {
     if (atol(e) > 0) slab_bytes = size_t(atol(e)) << 10;
   }
-  int64_t slab_rows = int64_t(slab_bytes / (size_t(z_ld) * sizeof(float2)));
-  slab_rows = slab_rows < 64 ? 64 : slab_rows / 64 * 64;
+  auto rows_per_slab = [&](int64_t pitch) {
+    const int64_t r = int64_t(slab_bytes / (size_t(pitch) * sizeof(float2)));
+    return r < 64 ? int64_t(64) : r / 64 * 64;
+  };
+  const int64_t slab_rows = rows_per_slab(zld_m);  // the larger of the two: sizes the pinned ring
   std::vector<int64_t> slab_r0, slab_r1;
   std::vector<int> chunk_first_slab((size_t)nchunks + 1, 0);
   for (int64_t i = 0; i < nchunks; ++i) {
     const int64_t c0 = i * cc, n = channels - c0 < cc ? channels - c0 : cc;
+    const int64_t per = rows_per_slab(cm[(size_t)i] ? zld_m : fft_length);
     chunk_first_slab[(size_t)i] = (int)slab_r0.size();
     for (int64_t r0 = c0 * M, r_end = (c0 + n) * M; r0 < r_end;) {
-      int64_t r1 = (r0 / 64 + slab_rows / 64) * 64;  // slabs end on work-item boundaries except at the chunk's end
+      int64_t r1 = (r0 / 64 + per / 64) * 64;  // slabs end on work-item boundaries except at the chunk's end
       if (r1 > r_end) r1 = r_end;
       slab_r0.push_back(r0);
       slab_r1.push_back(r1);
@@ -196,6 +222,7 @@ int nxs_stft_f32_host(nxs_ctx* ctx, const float* x, int64_t channels, int64_t le
   cudaEvent_t* ev_slab = ctx->slab_events.data();
   cudaEvent_t* ev_h2d = ev_slab + nslabs;
   cudaEvent_t* ev_krn = ev_h2d + nchunks;
+  const int64_t z_ld = unstage && can_mirror ? zld_m : fft_length;  // pitch of the pinned result ring's rows
 
   // pinned rings for pageable caller memory
   const int nslots = 6;
@@ -217,7 +244,7 @@ int nxs_stft_f32_host(nxs_ctx* ctx, const float* x, int64_t channels, int64_t le
     job.z = z;
     job.nfft = fft_length;
     job.nout = nout;
-    job.mirror = mirror;
+    job.mirror = can_mirror;  // staged rows hold the lower half (unstage), or the item mirrors in place
     job.unstage = unstage;
     job.ring = (const float*)h_ring;
     job.ring_pitch = z_ld;
@@ -248,7 +275,7 @@ int nxs_stft_f32_host(nxs_ctx* ctx, const float* x, int64_t channels, int64_t le
     for (int64_t i = 0; i < nchunks; ++i) job.chunk_off[(size_t)i] = size_t(i * cc * x_ld) * sizeof(float);
     for (int64_t i = 0; i < nchunks + 2; ++i) {
       if (stage_in && i < nchunks) add_in(i);
-      if ((mirror || unstage) && i >= 2) add_out(i - 2);
+      if (i >= 2 && (unstage || cm[(size_t)(i - 2)])) add_out(i - 2);
     }
     if (!(mirror || unstage)) job.items.shrink_to_fit();
     ctx->pool->begin((int64_t)job.items.size(), &StftHostJob::run, &job, nullptr);
@@ -303,8 +330,11 @@ int nxs_stft_f32_host(nxs_ctx* ctx, const float* x, int64_t channels, int64_t le
       NXS_CUDA(ctx, cudaEventRecord(ev_h2d[i], ctx->copy_stream));
       enq_chunks = i + 1;
       NXS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_h2d[i], 0));
+      const bool one = cm[(size_t)i];
+      const int64_t pitch = one ? zld_m : fft_length;
+      float2* const dz = d_z + dz_off[(size_t)i];
       int rcl = launch_stft(ctx, d_x + c0 * x_ld, n, length, x_ld, d_w, frame_length, hop, fft_length, g, M, scaling,
-                            sampling_rate, d_z + size_t(c0) * M * z_ld, z_ld, mirror ? 1 : 0, ctx->stream);
+                            sampling_rate, dz, pitch, one ? 1 : 0, ctx->stream);
       if (rcl) return rcl;
       NXS_CUDA(ctx, cudaEventRecord(ev_krn[i], ctx->stream));
       NXS_CUDA(ctx, cudaStreamWaitEvent(ctx->out_stream, ev_krn[i], 0));
@@ -313,15 +343,15 @@ int nxs_stft_f32_host(nxs_ctx* ctx, const float* x, int64_t channels, int64_t le
         if (unstage) {
           if (s >= nslots && !spin_until(job.slab_left[(size_t)(s - nslots)]))  // the ring slot has been copied out
             return set_cuda_error(ctx, async_err, "nxs_stft_f32_host (result ring)");
-          NXS_CUDA(ctx, cudaMemcpyAsync(h_ring + size_t(s % nslots) * ring_slot, d_z + size_t(r0) * z_ld,
-                                        size_t(r1 - r0) * z_ld * sizeof(float2), cudaMemcpyDeviceToHost, ctx->out_stream));
-        } else if (mirror) {
+          NXS_CUDA(ctx, cudaMemcpyAsync(h_ring + size_t(s % nslots) * ring_slot, dz + size_t(r0 - c0 * M) * pitch,
+                                        size_t(r1 - r0) * pitch * sizeof(float2), cudaMemcpyDeviceToHost, ctx->out_stream));
+        } else if (one) {
           NXS_CUDA(ctx, cudaMemcpy2DAsync(hz + size_t(r0) * fft_length, size_t(fft_length) * sizeof(float2),
-                                          d_z + size_t(r0) * z_ld, size_t(z_ld) * sizeof(float2),
-                                          size_t(nout) * sizeof(float2), size_t(r1 - r0), cudaMemcpyDeviceToHost,
+                                          dz + size_t(r0 - c0 * M) * pitch, size_t(pitch) * sizeof(float2),
+                                          size_t(nout_m) * sizeof(float2), size_t(r1 - r0), cudaMemcpyDeviceToHost,
                                           ctx->out_stream));
         } else {
-          NXS_CUDA(ctx, cudaMemcpyAsync(hz + size_t(r0) * fft_length, d_z + size_t(r0) * fft_length,
+          NXS_CUDA(ctx, cudaMemcpyAsync(hz + size_t(r0) * fft_length, dz + size_t(r0 - c0 * M) * fft_length,
                                         size_t(r1 - r0) * fft_length * sizeof(float2), cudaMemcpyDeviceToHost,
                                         ctx->out_stream));
         }
@@ -356,7 +386,7 @@ int nxs_stft_f32_host(nxs_ctx* ctx, const float* x, int64_t channels, int64_t le
   // feed the mode's cost estimate (pinned results only; large calls only)
   if (z_pinned && can_mirror && result_bytes >= (size_t(32) << 20)) {
     const double cost = (wall_seconds() - t_start) / double(result_bytes);
-    double& c = ctx->host_cost[mirror ? 1 : 0];
+    double& c = ctx->host_cost[level];
     c = c <= 0.0 ? cost : 0.5 * c + 0.5 * cost;
   }
   return NXS_OK;

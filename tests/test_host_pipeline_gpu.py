@@ -34,13 +34,13 @@ def _pinned(arr):
     return t
 
 
-@pytest.mark.parametrize("mode", [-1, 0, 1])
+@pytest.mark.parametrize("mode", [-1, 0, 1, 3])
 @pytest.mark.parametrize("pinned_in,pinned_out", [(True, True), (False, False), (True, False), (False, True)])
 def test_stft_host_entry_equals_device_entry_for_every_memory_kind_and_mode(mode, pinned_in, pinned_out):
     """several chunks (12 channels), several slabs per chunk, frames not a multiple of the 64-frame work items"""
     import torch
 
-    Cn, L, N, H = 12, 1_200_003, 1024, 256
+    Cn, L, N, H = 12, 2_400_003, 1024, 256  # 4 channel chunks of 3: the mixed mode applies
     x = synth((Cn, L), 311)
     w = o.hann(N)
     M = (L - N) // H + 1
@@ -50,7 +50,7 @@ def test_stft_host_entry_equals_device_entry_for_every_memory_kind_and_mode(mode
     ctx = _lib.context(0)
     _lib.set_host_mode(mode)
     try:
-        for _ in range(3 if mode == -1 else 1):  # auto: both modes get explored
+        for _ in range(4 if mode == -1 else 1):  # auto: every mode gets explored
             if A.is_torch(zout):
                 zout.zero_()
             else:

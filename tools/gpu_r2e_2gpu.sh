@@ -1,6 +1,6 @@
 #!/bin/bash
-# r02e (gpurun --gpus 2): the 2-GPU tests and the N = 2 bench line (cfg3 sharded, strong scaling, in-run bitwise shard checks)
-OUT=gpurun_out/r02e; mkdir -p $OUT
+# r02q (gpurun --gpus 2): the 2-GPU tests and the N = 2 bench line on the round-2 final code
+OUT=gpurun_out/r02q; mkdir -p $OUT
 nvidia-smi topo -m > $OUT/topo.txt 2>&1; nproc >> $OUT/topo.txt
 timeout 600 python -m pytest tests/test_multigpu_gpu.py -m gpu -x -q > $OUT/pytest_multigpu.log 2>&1; tail -5 $OUT/pytest_multigpu.log
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5 > $OUT/bench_n2.json 2> $OUT/bench_n2.err
