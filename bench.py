@@ -476,10 +476,10 @@ def e2e_legs(env, x, w, zo, zo_frames, args):
         return env.max_over_ranks((time.perf_counter() - t) / n)
 
     step = lambda: call(A.ptr(xh), A.ptr(zh))  # noqa: E731
-    # the warm-up calls let the context measure its transfer modes (full / one-sided + host mirror / mixed) under
-    # the load of all ranks; the timed calls then use the cheapest
+    # the warm-up calls let the context measure its two automatic transfer modes (full / one-sided + host mirror)
+    # under the load of all ranks; the timed calls then use the cheaper (the mixed mode is timed below, pinned)
     _lib.set_host_mode(-1, env.local_rank)
-    s = timed(step, args.e2e_steps, warm=4)
+    s = timed(step, args.e2e_steps, warm=3)
     mode = _lib.host_mode(env.local_rank)
     e2e = {"value": world * FRAMES_PER_GPU / s, "unit": "frames/s",
            "h2d_bytes_per_step": int(xh.numel() * 4 + NFFT * 4),

@@ -107,9 +107,10 @@ int nxs_ctx_host_timeline(const nxs_ctx* ctx, double out_seconds[4]);
  * buffer is pageable (not cudaHostRegister'ed -- e.g. a BEAM binary): the lower half lands in the
  * context's pinned ring and host threads copy it out and write the mirror half in one pass.
  * +16: the input was pageable and went through the pinned input ring.  For pinned results the
- * context measures the cost of modes 0, 1 and 3 on its own calls and uses the cheapest (which one
- * depends on whether the box is short of PCIe or of host memory bandwidth); nxs_ctx_set_host_mode
- * pins it: -1 auto (default), 0, 1 or 3.  All modes give bit-identical results. */
+ * context measures the cost of modes 0 and 1 on its own calls and uses the cheaper (which one
+ * depends on whether the box is short of PCIe or of host memory bandwidth; mode 3 never won where it
+ * was measured and can only be pinned); nxs_ctx_set_host_mode pins a mode: -1 auto (default), 0, 1
+ * or 3.  All modes give bit-identical results. */
 int nxs_ctx_set_host_mode(nxs_ctx* ctx, int mode);
 int nxs_ctx_host_mode(const nxs_ctx* ctx, int* mode);
 

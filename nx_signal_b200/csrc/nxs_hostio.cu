@@ -89,30 +89,24 @@ struct StftHostJob {
 };
 
 // Transfer modes of a pinned result: 0 = both spectrum halves over PCIe, 1 = lower half + host mirror,
-// 3 = mixed (three chunks of four as in 1, the fourth as in 0).  PCIe and the host memory system are separate
-// bottlenecks: mode 1 halves the PCIe bytes but adds a read and a write of host memory per mirrored row, mode 0
-// the reverse; when a box is short of both, the mix balances them.  Cost model: seconds per result byte of each
-// mode, exponentially averaged over the context's own calls.
-constexpr int kModes[3] = {1, 0, 3};
+// 3 = mixed (three chunks of four as in 1, the fourth as in 0).  Mode 1 halves the PCIe bytes but adds a read
+// and a write of host memory per mirrored row, mode 0 the reverse.  The automatic choice is between 0 and 1
+// (seconds per result byte of each, exponentially averaged over the context's own calls); the mix can only be
+// pinned: where it was measured (one B200 per 16-vCPU guest: 103 ms mirrored, 112 ms mixed, 139 ms full) the
+// copy engine, slowed by the host threads' memory traffic, stays the bottleneck, so moving more bytes over it
+// to spare host traffic loses.
 int choose_mode(nxs_ctx* ctx, bool can_mirror, size_t result_bytes, int64_t nchunks) {
   if (!can_mirror) return 0;
   if (const char* e = getenv("NXS_HOST_NO_MIRROR")) {
     if (e[0] && e[0] != '0') return 0;
   }
-  const bool mix_ok = nchunks >= 4;
-  if (ctx->host_mode_forced >= 0) return ctx->host_mode_forced == 3 && !mix_ok ? 1 : ctx->host_mode_forced;
+  if (ctx->host_mode_forced >= 0) return ctx->host_mode_forced == 3 && nchunks < 4 ? 1 : ctx->host_mode_forced;
   if (result_bytes < (size_t(32) << 20)) return 1;  // too small to measure: one-sided transfer
-  for (int m : kModes)                              // unknown costs first
-    if (ctx->host_cost[m] <= 0.0 && (m != 3 || mix_ok)) return m;
-  int best = 1;
-  for (int m : kModes)
-    if ((m != 3 || mix_ok) && ctx->host_cost[m] < ctx->host_cost[best]) best = m;
-  // re-probe another mode every 16th call: what the box is short of changes with its load
-  if (++ctx->host_calls % 16 == 0) {
-    const int other = kModes[(ctx->host_calls / 16) % 3];
-    if (other != best && (other != 3 || mix_ok)) return other;
-  }
-  return best;
+  if (ctx->host_cost[1] <= 0.0) return 1;           // unknown costs first
+  if (ctx->host_cost[0] <= 0.0) return 0;
+  const int best = ctx->host_cost[1] <= ctx->host_cost[0] ? 1 : 0;
+  // re-probe the other mode every 16th call: what the box is short of changes with its load
+  return (++ctx->host_calls % 16 == 0) ? 1 - best : best;
 }
 
 }  // namespace
