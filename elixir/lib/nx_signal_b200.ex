@@ -99,6 +99,22 @@ defmodule NxSignalB200 do
   @pad %{valid: 0, same: 1, reflect: 2}
   @scaling %{nil => 0, spectrum: 1, psd: 2}
 
+  @doc """
+  True when the NIF is loaded and a CUDA device answers (the backend has no CPU path: when this is false the
+  reference's own graphs are the only implementation).  `NxSignal`'s heads can delegate on it:
+
+      if NxSignalB200.available?() and not match?(%Nx.Tensor{data: %Nx.Defn.Expr{}}, data), do: NxSignalB200.stft(...)
+  """
+  def available? do
+    try do
+      is_reference(Ctx.get())
+    rescue
+      _ -> false
+    catch
+      _, _ -> false
+    end
+  end
+
   defp next_pow2(n), do: Bitwise.bsl(1, ceil(:math.log2(n)))
 
   defp fft_len(:power_of_two, n), do: next_pow2(n)
