@@ -49,6 +49,20 @@ __device__ __forceinline__ cpx mul_w16(cpx a) {
   else return make_float2(a.y * S1 - a.x * C1, -(a.x * S1 + a.y * C1));  // I == 7
 }
 
+// a * W_32^I, I in [0,16): the first stage of the radix-32 butterfly (odd I; even I are W_16 powers)
+template <int I>
+__device__ __forceinline__ cpx mul_w32(cpx a) {
+  if constexpr (I % 2 == 0) return mul_w16<I / 2>(a);
+  else {
+    // cos(2 pi j / 32), j = 0 .. 8
+    constexpr float c[9] = {1.0f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f, 0.70710678118654752f,
+                            0.55557023301960218f, 0.38268343236508977f, 0.19509032201612825f, 0.0f};
+    constexpr float co = I <= 8 ? c[I] : -c[16 - I];
+    constexpr float si = I <= 8 ? c[8 - I] : c[I - 8];
+    return make_float2(a.x * co + a.y * si, a.y * co - a.x * si);
+  }
+}
+
 // In-place decimation-in-frequency DFT of R points (forward, e^{-i...}).
 // Result X[k] is left at v[bitrev(k, log2 R)].
 template <int R, int I>
@@ -57,7 +71,8 @@ struct DifStage {
     if constexpr (I < R / 2) {
       cpx a = v[I], b = v[I + R / 2];
       v[I] = cadd(a, b);
-      v[I + R / 2] = mul_w16<I * (16 / R)>(csub(a, b));
+      if constexpr (R == 32) v[I + R / 2] = mul_w32<I>(csub(a, b));
+      else v[I + R / 2] = mul_w16<I * (16 / R)>(csub(a, b));
       DifStage<R, I + 1>::run(v);
     }
   }
@@ -65,7 +80,7 @@ struct DifStage {
 
 template <int R>
 struct Dft {
-  static_assert(R == 2 || R == 4 || R == 8 || R == 16, "radix");
+  static_assert(R == 2 || R == 4 || R == 8 || R == 16 || R == 32, "radix");
   static __device__ __forceinline__ void run(cpx* v) {
     if constexpr (R == 2) {
       cpx a = v[0], b = v[1];
@@ -210,6 +225,11 @@ struct TwDerive {
       w[8] = base[7 * NS];
 #pragma unroll
       for (int q = 1; q < 8; ++q) w[8 + q] = cmul(w[8], w[q]);
+    }
+    if constexpr (R >= 32) {
+      w[16] = base[15 * NS];
+#pragma unroll
+      for (int q = 1; q < 16; ++q) w[16 + q] = cmul(w[16], w[q]);
     }
   }
 };

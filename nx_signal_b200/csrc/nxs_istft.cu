@@ -816,6 +816,10 @@ static int try_istft_rola(nxs_ctx* ctx, const IstftArgs& a, int64_t channels, cu
     if constexpr (PL::N == 1024) {  // tuning variant (tests/test_istft_gpu.py)
       const char* var = getenv("NXS_ISTFT_VARIANT");
       if (var && atoi(var) == 1) return run_istft_rola<PL, THREADS, MINB, 4>(ctx, a, channels, st);
+      // one warp per frame, 32 points per lane, radices 32 x 32: ONE exchange per transform, no group barriers
+      if (var && atoi(var) == 2) return run_istft_rola<Plan<1024, 32, 32, 32>, 384, 1, 4>(ctx, a, channels, st);
+      if (var && atoi(var) == 3) return run_istft_rola<Plan<1024, 32, 32, 32>, 256, 1, 4>(ctx, a, channels, st);
+      if (var && atoi(var) == 4) return run_istft_rola<Plan<1024, 32, 32, 32>, 320, 1, 4>(ctx, a, channels, st);
       return run_istft_rola<PL, THREADS, MINB, 4, true>(ctx, a, channels, st);  // two exchange buffers still fit 2 CTAs/SM
     }
     return run_istft_rola<PL, THREADS, MINB, 4>(ctx, a, channels, st);
