@@ -179,6 +179,12 @@ struct TwRegs {
 #pragma unroll
     for (int q = 1; q < PL::R(PASS); ++q) out[q] = get<PASS>(b, q, k);
   }
+  // v[q] *= W^(q k), q = 1 .. R-1
+  template <int PASS>
+  __device__ __forceinline__ void apply(int b, int k, cpx* v) const {
+#pragma unroll
+    for (int q = 1; q < PL::R(PASS); ++q) v[q] = cmul(v[q], get<PASS>(b, q, k));
+  }
 };
 
 // Twiddles read from a table (shared or global memory) on every use.
@@ -196,7 +202,58 @@ struct TwTable {
 #pragma unroll
     for (int q = 1; q < PL::R(PASS); ++q) w[q] = get<PASS>(b, q, k);
   }
+  template <int PASS>
+  __device__ __forceinline__ void apply(int b, int k, cpx* v) const {
+#pragma unroll
+    for (int q = 1; q < PL::R(PASS); ++q) v[q] = cmul(v[q], get<PASS>(b, q, k));
+  }
 };
+
+// Derived twiddles applied octet by octet: W^1 .. W^7 are formed once from W^1, W^2, W^4, then every
+// further octet h = 8, 16, 24 takes its own factor W^h (a table row, or W^8 W^16) and the products
+// W^h W^q as it goes.  The same multiplies as forming all R - 1 twiddles first, but only ~10 complex values
+// are live at a time instead of R - 1: what lets the 32-point-per-lane plans fit their register budget.
+// `row(r)` = the table row of W^(2^r).
+template <int R, class ROW>
+__device__ __forceinline__ void apply_derived(const cpx* base, const ROW& row, cpx* v) {
+  if constexpr (R == 2) {
+    v[1] = cmul(v[1], base[row(0)]);
+  } else {
+    cpx w[8];
+    w[1] = base[row(0)];
+    w[2] = base[row(1)];
+    w[3] = cmul(w[1], w[2]);
+    v[1] = cmul(v[1], w[1]);
+    v[2] = cmul(v[2], w[2]);
+    v[3] = cmul(v[3], w[3]);
+    if constexpr (R >= 8) {
+      w[4] = base[row(2)];
+      v[4] = cmul(v[4], w[4]);
+#pragma unroll
+      for (int q = 1; q < 4; ++q) {
+        w[4 + q] = cmul(w[4], w[q]);
+        v[4 + q] = cmul(v[4 + q], w[4 + q]);
+      }
+    }
+    if constexpr (R >= 16) {
+      const cpx w8 = base[row(3)];
+      v[8] = cmul(v[8], w8);
+#pragma unroll
+      for (int q = 1; q < 8; ++q) v[8 + q] = cmul(v[8 + q], cmul(w8, w[q]));
+      if constexpr (R >= 32) {
+        const cpx w16 = base[row(4)];
+        const cpx w24 = cmul(w8, w16);
+        v[16] = cmul(v[16], w16);
+        v[24] = cmul(v[24], w24);
+#pragma unroll
+        for (int q = 1; q < 8; ++q) {
+          v[16 + q] = cmul(v[16 + q], cmul(w16, w[q]));
+          v[24 + q] = cmul(v[24 + q], cmul(w24, w[q]));
+        }
+      }
+    }
+  }
+}
 
 // Twiddles derived from the table's power-of-two entries: W^k, W^2k, W^4k (and W^8k for radix
 // 16) are loaded, the other powers are their products -- 3-4 shared-memory loads per butterfly
@@ -232,6 +289,11 @@ struct TwDerive {
       for (int q = 1; q < 16; ++q) w[16 + q] = cmul(w[16], w[q]);
     }
   }
+  template <int PASS>
+  __device__ __forceinline__ void apply(int /*b*/, int k, cpx* v) const {
+    constexpr int NS = PL::NS(PASS);
+    apply_derived<PL::R(PASS)>(tab + PL::twOffset(PASS) + k, [](int r) { return ((1 << r) - 1) * NS; }, v);
+  }
 };
 
 // TwDerive over the compact table layout [pass][r = log2 q][k] (Plan::twcOffset): a quarter of
@@ -260,6 +322,11 @@ struct TwDeriveC {
 #pragma unroll
       for (int q = 1; q < 8; ++q) w[8 + q] = cmul(w[8], w[q]);
     }
+  }
+  template <int PASS>
+  __device__ __forceinline__ void apply(int /*b*/, int k, cpx* v) const {
+    constexpr int NS = PL::NS(PASS);
+    apply_derived<PL::R(PASS)>(tab + PL::twcOffset(PASS) + k, [](int r) { return r * NS; }, v);
   }
 };
 
@@ -311,10 +378,17 @@ __device__ __forceinline__ int paired_bfly(int t, int b) {
   return j == 0 ? J / 2 : J - j;  // butterflies 0 and J/2 are their own partners: thread 0 takes both
 }
 
-template <class PL, int PASS, class TW, class SYNC, bool SINGLE = false, bool PAIRED = false>
+// HOOK: called once, right after the LAST pass has read its inputs out of the exchange buffer (the buffer is
+// then free as far as this thread is concerned: kernels whose exchange buffer doubles as their TMA stage
+// re-arm the stage from there, behind a group barrier of their own).
+struct NoHook {
+  __device__ __forceinline__ void operator()() const {}
+};
+
+template <class PL, int PASS, class TW, class SYNC, bool SINGLE = false, bool PAIRED = false, class HOOK = NoHook>
 struct PassRunner {
   static __device__ __forceinline__ void run(cpx (&v)[PL::P], int t, cpx* buf0, cpx* buf1,
-                                             const TW& tw, const SYNC& sync) {
+                                             const TW& tw, const SYNC& sync, const HOOK& hook = HOOK()) {
     constexpr int N = PL::N, T = PL::T, P = PL::P;
     constexpr int R = PL::R(PASS), NS = PL::NS(PASS), B = P / R;
     static_assert(P % R == 0, "radix must divide points per thread");
@@ -339,14 +413,12 @@ struct PassRunner {
         }
       }
       if constexpr (SINGLE && PASS + 1 < PL::NP) sync();  // reads done before this pass overwrites the buffer
+      if constexpr (PASS + 1 == PL::NP) hook();
 #pragma unroll
       for (int b = 0; b < B; ++b) {
         int k = (t + b * T) % NS;
         if constexpr (LASTP) k = paired_bfly<PL>(t, b) % NS;
-        cpx w[R];
-        tw.template fill<PASS>(b, k, w);
-#pragma unroll
-        for (int q = 1; q < R; ++q) v[b * R + q] = cmul(v[b * R + q], w[q]);
+        tw.template apply<PASS>(b, k, &v[b * R]);
       }
     }
 #pragma unroll
@@ -365,7 +437,7 @@ struct PassRunner {
         for (int q = 0; q < R; ++q) out[base + q * NS] = v[b * R + bitrev(q, ilog2(R))];
       }
       sync();
-      PassRunner<PL, PASS + 1, TW, SYNC, SINGLE, PAIRED>::run(v, t, buf0, buf1, tw, sync);
+      PassRunner<PL, PASS + 1, TW, SYNC, SINGLE, PAIRED, HOOK>::run(v, t, buf0, buf1, tw, sync, hook);
     }
   }
 };
@@ -382,6 +454,12 @@ __device__ __forceinline__ void block_fft(cpx (&v)[PL::P], int t, cpx* buf0, cpx
 template <class PL, class TW, class SYNC, bool PAIRED = false>
 __device__ __forceinline__ void block_fft_single(cpx (&v)[PL::P], int t, cpx* buf, const TW& tw, const SYNC& sync) {
   PassRunner<PL, 0, TW, SYNC, true, PAIRED>::run(v, t, buf, buf, tw, sync);
+}
+// one exchange buffer, with a hook behind the last pass's reads (see PassRunner's HOOK)
+template <class PL, class TW, class SYNC, class HOOK>
+__device__ __forceinline__ void block_fft_single_hook(cpx (&v)[PL::P], int t, cpx* buf, const TW& tw, const SYNC& sync,
+                                                      const HOOK& hook) {
+  PassRunner<PL, 0, TW, SYNC, true, false, HOOK>::run(v, t, buf, buf, tw, sync, hook);
 }
 // two exchange buffers, conjugate-paired last pass (see PassRunner's PAIRED)
 template <class PL, class TW, class SYNC>

@@ -377,6 +377,182 @@ __global__ void __launch_bounds__(THREADS, MINB) istft_rola_kernel(const IstftAr
 }
 
 // ------------------------------------------------------------------------------------------
+// One warp per frame (Plan<N, 32, 32, 32>: 32 points per lane, radices 32 x 32).  Two passes mean ONE
+// exchange per transform (the 64-thread plans above need two), the group barrier is __syncwarp, and the
+// twiddled pass is one instead of two -- 7 % fewer instructions and a third less shared-memory traffic per
+// frame.  What it costs is registers: 32 data points plus the running overlap-add do not fit 168 registers,
+// so the carry of the overlap-add (the P - S samples per lane a frame leaves unfinished) lives in a private
+// shared-memory column per lane (each lane reads slot j and writes slot j - S of its own column, in
+// ascending j: no cross-lane traffic, no barrier).  The exchange buffer doubles as the TMA stage; the next
+// frame's copy is issued from the FFT's hook, right behind the last pass's reads.
+// ------------------------------------------------------------------------------------------
+template <class PL, int THREADS, int HOPDIV>
+struct WarpRolaCfg {
+  static constexpr int G = THREADS / 32, N = PL::N, P = PL::P, S = (N / HOPDIV) / 32;
+  static_assert(PL::T == 32 && PL::NP == 2, "one warp per frame, two passes");
+  static_assert(size_t(PL::BUF) >= size_t(N), "the exchange buffer must hold a staged frame");
+  static constexpr size_t GROUP_BYTES = (size_t(PL::BUF) + size_t(P - S) * 32) * sizeof(cpx);  // stage/exchange + carry
+  static constexpr size_t WIN_OFF = size_t(G) * GROUP_BYTES;
+  static constexpr size_t TW_OFF = WIN_OFF + size_t(N) * sizeof(float);
+  static constexpr size_t BAR_OFF = TW_OFF + size_t(PL::TW_TOTAL) * sizeof(cpx);
+  static constexpr size_t SMEM = BAR_OFF + 8 * size_t(G) + 8;
+};
+
+template <class PL, int THREADS, int HOPDIV>
+__global__ void __launch_bounds__(THREADS, 1) istft_warp_kernel(const IstftArgs a) {
+  using CF = WarpRolaCfg<PL, THREADS, HOPDIV>;
+  constexpr int N = PL::N, T = 32, P = PL::P, G = CF::G;
+  constexpr int R0 = PL::R(0), B0 = P / R0;
+  constexpr int RL = PL::R(PL::NP - 1), BL = P / RL;
+  constexpr int HOP = N / HOPDIV, S = CF::S;
+  static_assert(HOP % T == 0 && S >= 1 && (N / RL) % T == 0, "hop must be a multiple of the warp width");
+  static_assert(BL == 1, "the carry column is walked in ascending sample order");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tid = threadIdx.x, g = tid / T, t = tid % T;
+  cpx* const xbuf = reinterpret_cast<cpx*>(smem_raw + size_t(g) * CF::GROUP_BYTES);
+  cpx* const stage = xbuf;                       // the frame's spectrum lands where the exchange happens later
+  cpx* const carry = xbuf + PL::BUF + t;          // this lane's column: carry[j * 32], j < P - S
+  float* wsm = reinterpret_cast<float*>(smem_raw + CF::WIN_OFF);
+  cpx* twsm = reinterpret_cast<cpx*>(smem_raw + CF::TW_OFF);
+  const uint32_t mybar = smem_u32(smem_raw + CF::BAR_OFF) + 8 * g;
+
+  for (int i = tid; i < N; i += THREADS) wsm[i] = a.wprep[i];
+  auto w2 = [&](int n) {
+    const float w = fabsf(__ldg(a.w + n));
+    return (float)((double)w * (double)w);
+  };
+  for (int i = tid; i < PL::TW_TOTAL; i += THREADS) twsm[i] = a.tw[i];
+  if (tid == 0) {
+    for (int i = 0; i < G; ++i) mbar_init(smem_u32(smem_raw + CF::BAR_OFF) + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  TwDerive<PL> tw;
+  tw.init(twsm, t);
+  const GroupSync<T> sync{1 + g};
+
+  float normc[S];  // reciprocal of the interior normaliser of the S samples a frame completes
+#pragma unroll
+  for (int j = 0; j < S; ++j) {
+    float nr = 0.f;
+#pragma unroll
+    for (int k = HOPDIV - 1; k >= 0; --k) nr += w2(t + j * T + k * HOP);
+    normc[j] = 1.0f / (nr > 1.0e-10f ? nr : 1.0f);
+  }
+  auto norm_at = [&](int64_t p) {  // exact normaliser at output position p of a channel (edges)
+    int64_t m_lo = p - N + 1 <= 0 ? 0 : (p - N + HOP) / HOP;
+    int64_t m_hi = p / HOP;
+    if (m_hi > a.M - 1) m_hi = a.M - 1;
+    float nr = 0.f;
+    for (int64_t m = m_lo; m <= m_hi; ++m) nr += w2((int)(p - m * HOP));
+    return nr;
+  };
+
+  const int gid = blockIdx.x * G + g, ngroups = gridDim.x * G;
+  auto seg_bounds = [&](int seg, int& c, int64_t& mb, int64_t& ms, int64_t& me) {
+    c = seg / a.segs_per_channel;
+    const int si = seg - c * a.segs_per_channel;
+    ms = (int64_t)si * a.seg_frames;
+    me = ms + a.seg_frames;
+    if (me > a.M) me = a.M;
+    mb = ms - (HOPDIV - 1);
+    if (mb < 0) mb = 0;
+  };
+  auto issue = [&](int c, int64_t m) {
+    // the buffer was last written by this warp's generic-proxy stores (the exchange): order them before the
+    // bulk copy's async-proxy writes
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(mybar, (uint32_t)(N * sizeof(cpx)));
+    tma_load_1d(smem_u32(stage), a.z + ((int64_t)c * a.M + m) * N, (uint32_t)(N * sizeof(cpx)), mybar);
+  };
+
+  uint32_t parity = 0;
+  int seg = gid;
+  int c = 0;
+  int64_t mb = 0, ms = 0, me = 0;
+  if (seg < a.total_segs) {
+    seg_bounds(seg, c, mb, ms, me);
+    if (t == 0) issue(c, mb);
+  }
+  while (seg < a.total_segs) {
+    float2* __restrict__ yc = a.y + (int64_t)c * a.out_len;
+#pragma unroll
+    for (int j = 0; j < P - S; ++j) carry[j * T] = make_float2(0.f, 0.f);
+    const int nseg = seg + ngroups;
+    int nc = 0;
+    int64_t nmb = 0, nms = 0, nme = 0;
+    if (nseg < a.total_segs) seg_bounds(nseg, nc, nmb, nms, nme);
+
+    for (int64_t m = mb; m < me; ++m) {
+      cpx v[P];
+      mbar_wait(mybar, parity);
+      parity ^= 1;
+#pragma unroll
+      for (int b = 0; b < B0; ++b)
+#pragma unroll
+        for (int q = 0; q < R0; ++q) {
+          const cpx val = stage[fft_in_index<PL>(t, b, q)];
+          v[b * R0 + q] = make_float2(val.y, val.x);  // swap: ifft(x) = swap(fft(swap(x))) / n
+        }
+      sync();  // the staged frame is in registers: the buffer may take the exchange
+      const bool more = m + 1 < me, next_seg = nseg < a.total_segs;
+      auto rearm = [&]() {  // behind the last pass's reads: the buffer is free again, stage the next frame
+        sync();
+        if (t == 0) {
+          if (more) issue(c, m + 1);
+          else if (next_seg) issue(nc, nmb);
+        }
+      };
+      block_fft_single_hook<PL>(v, t, xbuf, tw, sync, rearm);
+      // window, overlap-add through the lane's carry column, emit the S finished samples
+      const bool emit = m >= ms, interior = m >= HOPDIV - 1;
+      const int64_t pos = m * HOP + t;
+#pragma unroll
+      for (int b = 0; b < BL; ++b)
+#pragma unroll
+        for (int q = 0; q < RL; ++q) {
+          const int j = b + q * BL;
+          const cpx r = v[fft_out_reg<PL>(b, q)];
+          const float w = wsm[t + j * T];
+          cpx acc = make_float2(r.y * w, r.x * w);
+          if (j < P - S) {
+            const cpx old = carry[j * T];
+            acc.x += old.x;
+            acc.y += old.y;
+          }
+          if (j < S) {
+            if (emit) {
+              float rd = normc[j];
+              if (!interior) {
+                const float nr = norm_at(pos + j * T);
+                rd = 1.0f / (nr > 1.0e-10f ? nr : 1.0f);
+              }
+              __stcs(yc + pos + j * T, make_float2(acc.x * rd, acc.y * rd));
+            }
+          } else {
+            carry[(j - S) * T] = acc;
+          }
+        }
+    }
+    if (me == a.M) {  // tail of the channel: the N - hop samples no further frame completes
+      const int64_t pos = a.M * HOP + t;
+#pragma unroll
+      for (int j = 0; j < P - S; ++j) {
+        const cpx acc = carry[j * T];
+        const float nr = norm_at(pos + j * T);
+        const float rd = 1.0f / (nr > 1.0e-10f ? nr : 1.0f);
+        __stcs(yc + pos + j * T, make_float2(acc.x * rd, acc.y * rd));
+      }
+    }
+    seg = nseg;
+    c = nc;
+    mb = nmb;
+    ms = nms;
+    me = nme;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // large fft_length (shared memory cannot hold frames + carry): inverse-transform frames with the
 // same engine into a scratch frame tensor; istft_ola_norm_kernel finishes.
 // ------------------------------------------------------------------------------------------
@@ -748,6 +924,43 @@ static int run_istft_rola(nxs_ctx* ctx, IstftArgs a, int64_t channels, cudaStrea
   return NXS_OK;
 }
 
+template <class PL, int THREADS, int HOPDIV>
+static int run_istft_warp(nxs_ctx* ctx, IstftArgs a, int64_t channels, cudaStream_t st) {
+  using CF = WarpRolaCfg<PL, THREADS, HOPDIV>;
+  float2* tw = nullptr;
+  int rc = get_tw_table<PL>(ctx, &tw);
+  if (rc) return rc;
+  a.tw = tw;
+  auto kern = istft_warp_kernel<PL, THREADS, HOPDIV>;
+  static_assert(CF::SMEM <= 232448, "istft_warp_kernel: shared memory");
+  static int attr_done[16] = {0};
+  if (!attr_done[ctx->device & 15]) {
+    NXS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF::SMEM));
+    attr_done[ctx->device & 15] = 1;
+  }
+  // segments: a few per warp so the tail is balanced; each costs HOPDIV - 1 recomputed frames
+  const int64_t groups = int64_t(ctx->sm_count) * CF::G;
+  const int64_t total_frames = channels * a.M;
+  int64_t seg = (total_frames + groups * 4 - 1) / (groups * 4);
+  const int64_t seg_min = 16 * (HOPDIV - 1) > 32 ? 16 * (HOPDIV - 1) : 32;
+  if (seg < seg_min) seg = seg_min;
+  if (seg > a.M) seg = a.M;
+  a.seg_frames = (int)seg;
+  a.segs_per_channel = (int)((a.M + seg - 1) / seg);
+  const int64_t total = int64_t(a.segs_per_channel) * channels;
+  if (total >= (int64_t(1) << 31)) return NXS_EUNSUPPORTED;
+  a.total_segs = (int)total;
+  a.warm_batches = 0;
+  int64_t grid = (total + CF::G - 1) / CF::G;
+  if (grid > int64_t(ctx->sm_count)) grid = int64_t(ctx->sm_count);
+  prof_begin(ctx, st);
+  kern<<<(unsigned)grid, THREADS, CF::SMEM, st>>>(a);
+  prof_end(ctx, st);
+  ctx->launches++;
+  NXS_CUDA(ctx, cudaGetLastError());
+  return NXS_OK;
+}
+
 template <class PL>
 static int get_twc_table(nxs_ctx* ctx, float2** out) {
   const uint64_t key = (uint64_t(PL::N) << 32) | (uint64_t(PL::T) << 8) | uint64_t(PL::NP) | (uint64_t(1) << 62) |
@@ -820,6 +1033,11 @@ static int try_istft_rola(nxs_ctx* ctx, const IstftArgs& a, int64_t channels, cu
       if (var && atoi(var) == 2) return run_istft_rola<Plan<1024, 32, 32, 32>, 384, 1, 4>(ctx, a, channels, st);
       if (var && atoi(var) == 3) return run_istft_rola<Plan<1024, 32, 32, 32>, 256, 1, 4>(ctx, a, channels, st);
       if (var && atoi(var) == 4) return run_istft_rola<Plan<1024, 32, 32, 32>, 320, 1, 4>(ctx, a, channels, st);
+      // the same plan with the overlap-add carry in a private shared-memory column per lane (istft_warp_kernel)
+      if (var && atoi(var) == 5) return run_istft_warp<Plan<1024, 32, 32, 32>, 384, 4>(ctx, a, channels, st);
+      if (var && atoi(var) == 6) return run_istft_warp<Plan<1024, 32, 32, 32>, 448, 4>(ctx, a, channels, st);
+      if (var && atoi(var) == 7) return run_istft_warp<Plan<1024, 32, 32, 32>, 320, 4>(ctx, a, channels, st);
+      if (var && atoi(var) == 8) return run_istft_warp<Plan<1024, 32, 32, 32>, 352, 4>(ctx, a, channels, st);
       return run_istft_rola<PL, THREADS, MINB, 4, true>(ctx, a, channels, st);  // two exchange buffers still fit 2 CTAs/SM
     }
     return run_istft_rola<PL, THREADS, MINB, 4>(ctx, a, channels, st);
