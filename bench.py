@@ -684,6 +684,14 @@ def cfg1_leg(env, nx):
     xp = torch.from_numpy(x).pin_memory()
     zp = torch.empty((1, M1, NFFT), dtype=torch.complex64, pin_memory=True)
     pinned_s = lat(lambda: host_call(A.ptr(xp), A.ptr(zp)))
+    transfer_mode = _lib.host_mode(env.local_rank)["result"]
+    # the way back on the same small shape: nxs_istft_c64_host on the spectrum just computed
+    out_len = (M1 - 1) * HOP + NFFT
+    yp = torch.empty((1, out_len), dtype=torch.complex64, pin_memory=True)
+    istft_s = lat(lambda: _lib.check(lib.nxs_istft_c64_host(ctx, A.ptr(zp), 1, M1, NFFT, wh.ctypes.data, NFFT, HOP, NFFT, 0,
+                                                            float(FS), A.ptr(yp)), ctx, "istft(host, cfg1)"))
+    rt = yp.numpy()[0, NFFT:out_len - NFFT].real
+    roundtrip_err = float(np.abs(rt - x[0, NFFT:out_len - NFFT]).max() / np.abs(x).max())
     xd, wd = xp.to(env.dev), torch.from_numpy(wh).to(env.dev)
     zd = torch.empty((1, M1, NFFT), dtype=torch.complex64, device=env.dev)
     n0 = _lib.launch_count(env.local_rank)
@@ -697,6 +705,8 @@ def cfg1_leg(env, nx):
     err = float((np.abs(z[0] - zo).max(-1) / np.abs(zo).max(-1)).max())
     return {"workload": "cfg1 (BASELINE configs[0]): 1 x 48000 f32, hann(1024), hop 256 -> 184 frames x 1024 bins",
             "gpu_host_call_pageable_us": 1e6 * pageable_s, "gpu_host_call_pinned_us": 1e6 * pinned_s,
+            "host_call_transfer_mode": transfer_mode, "gpu_istft_host_call_pinned_us": 1e6 * istft_s,
+            "stft_istft_roundtrip_interior_err": roundtrip_err,
             "gpu_dev_call_us": None if dev_ms is None else 1e3 * dev_ms, "kernel_launches_per_dev_call": launches_per_call,
             "frames_per_s_host_call": M1 / pageable_s,
             "cpu_literal_restatement_1core_ms": 1e3 * lit_s, "cpu_c_port_1thread_ms": 1e3 * c_s,

@@ -100,7 +100,7 @@ int nxs_ctx_profile_read(nxs_ctx* ctx, double* total_ms, int64_t* launches);
  * memory, [3] host mirror threads done (= result complete).  bench.py reports them. */
 int nxs_ctx_host_timeline(const nxs_ctx* ctx, double out_seconds[4]);
 
-/* nxs_stft_f32_host moves the result in one of four ways, reported by nxs_ctx_host_mode for the
+/* nxs_stft_f32_host moves the result in one of five ways, reported by nxs_ctx_host_mode for the
  * last call: 0 = both spectrum halves over PCIe; 1 = bins 0 .. fft_length/2 over PCIe straight into
  * the caller's rows, host threads write the conjugate-mirror bins; 3 = mixed: three channel chunks of
  * four as in 1, the fourth as in 0 (balances PCIe against host memory bandwidth); 2 = the result
@@ -110,7 +110,9 @@ int nxs_ctx_host_timeline(const nxs_ctx* ctx, double out_seconds[4]);
  * context measures the cost of modes 0 and 1 on its own calls and uses the cheaper (which one
  * depends on whether the box is short of PCIe or of host memory bandwidth; mode 3 never won where it
  * was measured and can only be pinned); nxs_ctx_set_host_mode pins a mode: -1 auto (default), 0, 1
- * or 3.  All modes give bit-identical results. */
+ * or 3.  4 = small call (input and result up to 4 MiB, no mode pinned): one stream, both halves
+ * over PCIe, no host threads -- the latency path of the short calls NxSignal.stft usually gets.
+ * All modes give bit-identical results. */
 int nxs_ctx_set_host_mode(nxs_ctx* ctx, int mode);
 int nxs_ctx_host_mode(const nxs_ctx* ctx, int* mode);
 

@@ -171,7 +171,8 @@ def host_timeline(device=0):
 
 
 HOST_MODES = {0: "full_d2h", 1: "onesided_d2h+host_mirror", 2: "onesided_d2h+pinned_ring_unstage",
-              3: "mixed: 3 of 4 chunks onesided_d2h+host_mirror, 1 of 4 full_d2h"}
+              3: "mixed: 3 of 4 chunks onesided_d2h+host_mirror, 1 of 4 full_d2h",
+              4: "small_call_single_stream_full_d2h"}
 
 
 def host_mode(device=0):

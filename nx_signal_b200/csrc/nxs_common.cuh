@@ -167,6 +167,25 @@ int resolve_padding(int64_t length, int64_t window_length, int pad_mode, int64_t
                     PadGeom* g);
 int64_t frames_for(int64_t length, int64_t window_length, int64_t stride, const PadGeom& g);
 
+// cudaFuncSetAttribute + occupancy query once per (kernel instantiation, device), not per call
+struct LaunchCache {
+  int occ[16] = {0};
+  size_t smem[16] = {0};
+  template <class K>
+  int get(nxs_ctx* ctx, K kern, int threads, size_t smem_bytes, int* out) {
+    const int d = ctx->device & 15;
+    if (occ[d] == 0 || smem[d] != smem_bytes) {
+      NXS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+      int o = 1;
+      NXS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, threads, smem_bytes));
+      smem[d] = smem_bytes;
+      occ[d] = o < 1 ? 1 : o;
+    }
+    *out = occ[d];
+    return NXS_OK;
+  }
+};
+
 // kernels' host launchers (each returns NXS_* and bumps ctx->launches)
 int launch_stft(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, int64_t x_ld,
                 const float* window, int64_t frame_length, int64_t hop, int64_t fft_length,

@@ -21,11 +21,49 @@ namespace nxs {
 
 typedef float2 cpx;
 
-__device__ __forceinline__ cpx cadd(cpx a, cpx b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ cpx csub(cpx a, cpx b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ cpx cmul(cpx a, cpx b) {
-  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+// Complex arithmetic, scalar or (PK) on the packed fp32x2 instructions of sm_100 (FADD2 / FMUL2 / FFMA2: one
+// issue slot for the real and the imaginary lane).  The transforms here are bound by instruction issue, not by
+// the FMA pipe, and a complex value already sits in an aligned register pair; the half swaps, broadcasts and
+// sign flips below are operand modifiers of the packed instructions (R.F32x2.LO_HI.NP, R.F32), not
+// instructions.  Every packed operation rounds exactly like its two scalar halves.  Whether it pays is a
+// per-kernel matter -- where the register allocator has to move values into aligned pairs the moves eat the
+// saving (profiles/r02x_packed_fp32x2.txt) -- so the choice rides on the plan (Plan::PK).
+template <bool PK>
+__device__ __forceinline__ cpx cadd_(cpx a, cpx b) {
+  if constexpr (PK) return __fadd2_rn(a, b);
+  else return make_float2(a.x + b.x, a.y + b.y);
 }
+template <bool PK>
+__device__ __forceinline__ cpx csub_(cpx a, cpx b) {
+  if constexpr (PK) return __fadd2_rn(a, make_float2(-b.x, -b.y));
+  else return make_float2(a.x - b.x, a.y - b.y);
+}
+template <bool PK>
+__device__ __forceinline__ cpx cmul_(cpx a, cpx b) {
+  // the swizzled, half-negated operand goes FIRST, the broadcast second: that is the operand order FFMA2 has the
+  // modifiers for (the other order costs a MOV and an FADD per product)
+#if defined(NXS_CMUL_F1)  // A/B build: the operand order that costs a MOV and an FADD
+  if constexpr (PK) return __ffma2_rn(make_float2(a.y, a.y), make_float2(-b.y, b.x), __fmul2_rn(make_float2(a.x, a.x), b));
+#else
+  if constexpr (PK) return __ffma2_rn(make_float2(-b.y, b.x), make_float2(a.y, a.y), __fmul2_rn(make_float2(a.x, a.x), b));
+#endif
+  else return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+// a * (c - i s)
+template <bool PK>
+__device__ __forceinline__ cpx crot_(cpx a, float c, float s) {
+  if constexpr (PK) return __ffma2_rn(make_float2(a.y, -a.x), make_float2(s, s), __fmul2_rn(a, make_float2(c, c)));
+  else return make_float2(a.x * c + a.y * s, a.y * c - a.x * s);
+}
+// a * s, s real
+template <bool PK>
+__device__ __forceinline__ cpx cscale_(cpx a, float s) {
+  if constexpr (PK) return __fmul2_rn(a, make_float2(s, s));
+  else return make_float2(a.x * s, a.y * s);
+}
+__device__ __forceinline__ cpx cadd(cpx a, cpx b) { return cadd_<false>(a, b); }
+__device__ __forceinline__ cpx csub(cpx a, cpx b) { return csub_<false>(a, b); }
+__device__ __forceinline__ cpx cmul(cpx a, cpx b) { return cmul_<false>(a, b); }
 __device__ __forceinline__ cpx cconj(cpx a) { return make_float2(a.x, -a.y); }
 
 constexpr int ilog2(int x) { return x <= 1 ? 0 : 1 + ilog2(x >> 1); }
@@ -36,60 +74,60 @@ constexpr int bitrev(int k, int bits) {
 }
 
 // a * W_16^I, I in [0,8), W_16 = exp(-2 pi i / 16); constants become FFMA immediates
-template <int I>
+template <int I, bool PK = false>
 __device__ __forceinline__ cpx mul_w16(cpx a) {
   constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, H = 0.70710678118654752f;
   if constexpr (I == 0) return a;
   else if constexpr (I == 4) return make_float2(a.y, -a.x);
-  else if constexpr (I == 2) return make_float2((a.x + a.y) * H, (a.y - a.x) * H);
-  else if constexpr (I == 6) return make_float2((a.y - a.x) * H, -(a.x + a.y) * H);
-  else if constexpr (I == 1) return make_float2(a.x * C1 + a.y * S1, a.y * C1 - a.x * S1);
-  else if constexpr (I == 3) return make_float2(a.x * S1 + a.y * C1, a.y * S1 - a.x * C1);
-  else if constexpr (I == 5) return make_float2(a.y * C1 - a.x * S1, -(a.x * C1 + a.y * S1));
-  else return make_float2(a.y * S1 - a.x * C1, -(a.x * S1 + a.y * C1));  // I == 7
+  else if constexpr (I == 2) return cscale_<PK>(cadd_<PK>(a, make_float2(a.y, -a.x)), H);
+  else if constexpr (I == 6) return cscale_<PK>(csub_<PK>(make_float2(a.y, -a.x), a), H);
+  else if constexpr (I == 1) return crot_<PK>(a, C1, S1);
+  else if constexpr (I == 3) return crot_<PK>(a, S1, C1);
+  else if constexpr (I == 5) return crot_<PK>(a, -S1, C1);
+  else return crot_<PK>(a, -C1, S1);  // I == 7
 }
 
 // a * W_32^I, I in [0,16): the first stage of the radix-32 butterfly (odd I; even I are W_16 powers)
-template <int I>
+template <int I, bool PK = false>
 __device__ __forceinline__ cpx mul_w32(cpx a) {
-  if constexpr (I % 2 == 0) return mul_w16<I / 2>(a);
+  if constexpr (I % 2 == 0) return mul_w16<I / 2, PK>(a);
   else {
     // cos(2 pi j / 32), j = 0 .. 8
     constexpr float c[9] = {1.0f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f, 0.70710678118654752f,
                             0.55557023301960218f, 0.38268343236508977f, 0.19509032201612825f, 0.0f};
     constexpr float co = I <= 8 ? c[I] : -c[16 - I];
     constexpr float si = I <= 8 ? c[8 - I] : c[I - 8];
-    return make_float2(a.x * co + a.y * si, a.y * co - a.x * si);
+    return crot_<PK>(a, co, si);
   }
 }
 
 // In-place decimation-in-frequency DFT of R points (forward, e^{-i...}).
 // Result X[k] is left at v[bitrev(k, log2 R)].
-template <int R, int I>
+template <int R, int I, bool PK>
 struct DifStage {
   static __device__ __forceinline__ void run(cpx* v) {
     if constexpr (I < R / 2) {
       cpx a = v[I], b = v[I + R / 2];
-      v[I] = cadd(a, b);
-      if constexpr (R == 32) v[I + R / 2] = mul_w32<I>(csub(a, b));
-      else v[I + R / 2] = mul_w16<I * (16 / R)>(csub(a, b));
-      DifStage<R, I + 1>::run(v);
+      v[I] = cadd_<PK>(a, b);
+      if constexpr (R == 32) v[I + R / 2] = mul_w32<I, PK>(csub_<PK>(a, b));
+      else v[I + R / 2] = mul_w16<I * (16 / R), PK>(csub_<PK>(a, b));
+      DifStage<R, I + 1, PK>::run(v);
     }
   }
 };
 
-template <int R>
+template <int R, bool PK = false>
 struct Dft {
   static_assert(R == 2 || R == 4 || R == 8 || R == 16 || R == 32, "radix");
   static __device__ __forceinline__ void run(cpx* v) {
     if constexpr (R == 2) {
       cpx a = v[0], b = v[1];
-      v[0] = cadd(a, b);
-      v[1] = csub(a, b);
+      v[0] = cadd_<PK>(a, b);
+      v[1] = csub_<PK>(a, b);
     } else {
-      DifStage<R, 0>::run(v);
-      Dft<R / 2>::run(v);
-      Dft<R / 2>::run(v + R / 2);
+      DifStage<R, 0, PK>::run(v);
+      Dft<R / 2, PK>::run(v);
+      Dft<R / 2, PK>::run(v + R / 2);
     }
   }
 };
@@ -97,9 +135,10 @@ struct Dft {
 // ---------------------------------------------------------------------------------------
 // Plan: N points, T threads, up to 4 passes (unused radices = 1).
 // ---------------------------------------------------------------------------------------
-template <int N_, int T_, int R0, int R1 = 1, int R2 = 1, int R3 = 1>
+template <int N_, int T_, int R0, int R1 = 1, int R2 = 1, int R3 = 1, bool PK_ = false>
 struct Plan {
   static constexpr int N = N_, T = T_, P = N_ / T_;
+  static constexpr bool PK = PK_;  // complex arithmetic on the packed fp32x2 instructions
   static constexpr int NP = 1 + (R1 > 1) + (R2 > 1) + (R3 > 1);
   static_assert(R0 * R1 * R2 * R3 == N_, "radices must multiply to N");
   static_assert(N_ % T_ == 0, "T must divide N");
@@ -153,6 +192,7 @@ __device__ __forceinline__ int pad_idx(int i) {
 // Twiddles held in registers for the lifetime of a persistent CTA.
 template <class PL>
 struct TwRegs {
+  static constexpr bool PK = PL::PK;
   cpx w[PL::TW_REGS > 0 ? PL::TW_REGS : 1];
   template <int PASS>
   __device__ __forceinline__ void init_pass(const cpx* __restrict__ tab, int t) {
@@ -183,13 +223,14 @@ struct TwRegs {
   template <int PASS>
   __device__ __forceinline__ void apply(int b, int k, cpx* v) const {
 #pragma unroll
-    for (int q = 1; q < PL::R(PASS); ++q) v[q] = cmul(v[q], get<PASS>(b, q, k));
+    for (int q = 1; q < PL::R(PASS); ++q) v[q] = cmul_<PK>(v[q], get<PASS>(b, q, k));
   }
 };
 
 // Twiddles read from a table (shared or global memory) on every use.
 template <class PL>
 struct TwTable {
+  static constexpr bool PK = PL::PK;
   const cpx* tab;
   __device__ __forceinline__ void init(const cpx* t_, int) { tab = t_; }
   template <int PASS>
@@ -205,7 +246,7 @@ struct TwTable {
   template <int PASS>
   __device__ __forceinline__ void apply(int b, int k, cpx* v) const {
 #pragma unroll
-    for (int q = 1; q < PL::R(PASS); ++q) v[q] = cmul(v[q], get<PASS>(b, q, k));
+    for (int q = 1; q < PL::R(PASS); ++q) v[q] = cmul_<PK>(v[q], get<PASS>(b, q, k));
   }
 };
 
@@ -214,41 +255,41 @@ struct TwTable {
 // W^h W^q as it goes.  The same multiplies as forming all R - 1 twiddles first, but only ~10 complex values
 // are live at a time instead of R - 1: what lets the 32-point-per-lane plans fit their register budget.
 // `row(r)` = the table row of W^(2^r).
-template <int R, class ROW>
+template <int R, bool PK, class ROW>
 __device__ __forceinline__ void apply_derived(const cpx* base, const ROW& row, cpx* v) {
   if constexpr (R == 2) {
-    v[1] = cmul(v[1], base[row(0)]);
+    v[1] = cmul_<PK>(v[1], base[row(0)]);
   } else {
     cpx w[8];
     w[1] = base[row(0)];
     w[2] = base[row(1)];
-    w[3] = cmul(w[1], w[2]);
-    v[1] = cmul(v[1], w[1]);
-    v[2] = cmul(v[2], w[2]);
-    v[3] = cmul(v[3], w[3]);
+    w[3] = cmul_<PK>(w[1], w[2]);
+    v[1] = cmul_<PK>(v[1], w[1]);
+    v[2] = cmul_<PK>(v[2], w[2]);
+    v[3] = cmul_<PK>(v[3], w[3]);
     if constexpr (R >= 8) {
       w[4] = base[row(2)];
-      v[4] = cmul(v[4], w[4]);
+      v[4] = cmul_<PK>(v[4], w[4]);
 #pragma unroll
       for (int q = 1; q < 4; ++q) {
-        w[4 + q] = cmul(w[4], w[q]);
-        v[4 + q] = cmul(v[4 + q], w[4 + q]);
+        w[4 + q] = cmul_<PK>(w[4], w[q]);
+        v[4 + q] = cmul_<PK>(v[4 + q], w[4 + q]);
       }
     }
     if constexpr (R >= 16) {
       const cpx w8 = base[row(3)];
-      v[8] = cmul(v[8], w8);
+      v[8] = cmul_<PK>(v[8], w8);
 #pragma unroll
-      for (int q = 1; q < 8; ++q) v[8 + q] = cmul(v[8 + q], cmul(w8, w[q]));
+      for (int q = 1; q < 8; ++q) v[8 + q] = cmul_<PK>(v[8 + q], cmul_<PK>(w8, w[q]));
       if constexpr (R >= 32) {
         const cpx w16 = base[row(4)];
-        const cpx w24 = cmul(w8, w16);
-        v[16] = cmul(v[16], w16);
-        v[24] = cmul(v[24], w24);
+        const cpx w24 = cmul_<PK>(w8, w16);
+        v[16] = cmul_<PK>(v[16], w16);
+        v[24] = cmul_<PK>(v[24], w24);
 #pragma unroll
         for (int q = 1; q < 8; ++q) {
-          v[16 + q] = cmul(v[16 + q], cmul(w16, w[q]));
-          v[24 + q] = cmul(v[24 + q], cmul(w24, w[q]));
+          v[16 + q] = cmul_<PK>(v[16 + q], cmul_<PK>(w16, w[q]));
+          v[24 + q] = cmul_<PK>(v[24 + q], cmul_<PK>(w24, w[q]));
         }
       }
     }
@@ -261,6 +302,7 @@ __device__ __forceinline__ void apply_derived(const cpx* base, const ROW& row, c
 // memory pipe is what bounds the large plans (ncu: LSU wavefronts ~80 % of peak).
 template <class PL>
 struct TwDerive {
+  static constexpr bool PK = PL::PK;
   const cpx* tab;
   __device__ __forceinline__ void init(const cpx* t_, int) { tab = t_; }
   template <int PASS>
@@ -270,29 +312,29 @@ struct TwDerive {
     w[1] = base[0];
     if constexpr (R >= 4) {
       w[2] = base[1 * NS];
-      w[3] = cmul(w[1], w[2]);
+      w[3] = cmul_<PK>(w[1], w[2]);
     }
     if constexpr (R >= 8) {
       w[4] = base[3 * NS];
-      w[5] = cmul(w[4], w[1]);
-      w[6] = cmul(w[4], w[2]);
-      w[7] = cmul(w[4], w[3]);
+      w[5] = cmul_<PK>(w[4], w[1]);
+      w[6] = cmul_<PK>(w[4], w[2]);
+      w[7] = cmul_<PK>(w[4], w[3]);
     }
     if constexpr (R >= 16) {
       w[8] = base[7 * NS];
 #pragma unroll
-      for (int q = 1; q < 8; ++q) w[8 + q] = cmul(w[8], w[q]);
+      for (int q = 1; q < 8; ++q) w[8 + q] = cmul_<PK>(w[8], w[q]);
     }
     if constexpr (R >= 32) {
       w[16] = base[15 * NS];
 #pragma unroll
-      for (int q = 1; q < 16; ++q) w[16 + q] = cmul(w[16], w[q]);
+      for (int q = 1; q < 16; ++q) w[16 + q] = cmul_<PK>(w[16], w[q]);
     }
   }
   template <int PASS>
   __device__ __forceinline__ void apply(int /*b*/, int k, cpx* v) const {
     constexpr int NS = PL::NS(PASS);
-    apply_derived<PL::R(PASS)>(tab + PL::twOffset(PASS) + k, [](int r) { return ((1 << r) - 1) * NS; }, v);
+    apply_derived<PL::R(PASS), PK>(tab + PL::twOffset(PASS) + k, [](int r) { return ((1 << r) - 1) * NS; }, v);
   }
 };
 
@@ -300,6 +342,7 @@ struct TwDerive {
 // the full table's shared memory for radix 16.
 template <class PL>
 struct TwDeriveC {
+  static constexpr bool PK = PL::PK;
   const cpx* tab;
   __device__ __forceinline__ void init(const cpx* t_, int) { tab = t_; }
   template <int PASS>
@@ -309,24 +352,24 @@ struct TwDeriveC {
     w[1] = base[0];
     if constexpr (R >= 4) {
       w[2] = base[1 * NS];
-      w[3] = cmul(w[1], w[2]);
+      w[3] = cmul_<PK>(w[1], w[2]);
     }
     if constexpr (R >= 8) {
       w[4] = base[2 * NS];
-      w[5] = cmul(w[4], w[1]);
-      w[6] = cmul(w[4], w[2]);
-      w[7] = cmul(w[4], w[3]);
+      w[5] = cmul_<PK>(w[4], w[1]);
+      w[6] = cmul_<PK>(w[4], w[2]);
+      w[7] = cmul_<PK>(w[4], w[3]);
     }
     if constexpr (R >= 16) {
       w[8] = base[3 * NS];
 #pragma unroll
-      for (int q = 1; q < 8; ++q) w[8 + q] = cmul(w[8], w[q]);
+      for (int q = 1; q < 8; ++q) w[8 + q] = cmul_<PK>(w[8], w[q]);
     }
   }
   template <int PASS>
   __device__ __forceinline__ void apply(int /*b*/, int k, cpx* v) const {
     constexpr int NS = PL::NS(PASS);
-    apply_derived<PL::R(PASS)>(tab + PL::twcOffset(PASS) + k, [](int r) { return r * NS; }, v);
+    apply_derived<PL::R(PASS), PK>(tab + PL::twcOffset(PASS) + k, [](int r) { return r * NS; }, v);
   }
 };
 
@@ -422,7 +465,7 @@ struct PassRunner {
       }
     }
 #pragma unroll
-    for (int b = 0; b < B; ++b) Dft<R>::run(&v[b * R]);
+    for (int b = 0; b < B; ++b) Dft<R, PL::PK>::run(&v[b * R]);
     if constexpr (PASS + 1 < PL::NP) {
       constexpr int A = PL::padA(PASS), C = PL::padC(PASS);
       constexpr int LR = ilog2(NS * R);

@@ -501,9 +501,16 @@ __global__ void __launch_bounds__(THREADS, MINB) fir_ols_r2c_kernel(const FirArg
         const cpx A = v[fft_out_reg<PL>(b, q)];
         const cpx Bc = cconj(xbuf[(N - k) & (N - 1)]);
         const cpx pk = Ps[k], qk = Qs[k];
-        const float yr = fmaf(pk.x, A.x, fmaf(-pk.y, A.y, fmaf(qk.x, Bc.x, -qk.y * Bc.y)));
-        const float yi = fmaf(pk.x, A.y, fmaf(pk.y, A.x, fmaf(qk.x, Bc.y, qk.y * Bc.x)));
-        u[b * R0 + q] = make_float2(yi, yr);  // swap for the inverse transform
+        if constexpr (PL::PK) {  // (yi, yr) = B.y (-qk.x, qk.y) + B.x (qk.y, qk.x) + A.y (pk.x, -pk.y) + A.x (pk.y, pk.x), B = conj(Bc)
+          cpx s = __fmul2_rn(make_float2(-qk.x, qk.y), make_float2(-Bc.y, -Bc.y));
+          s = __ffma2_rn(make_float2(qk.y, qk.x), make_float2(Bc.x, Bc.x), s);
+          s = __ffma2_rn(make_float2(pk.x, -pk.y), make_float2(A.y, A.y), s);
+          u[b * R0 + q] = __ffma2_rn(make_float2(pk.y, pk.x), make_float2(A.x, A.x), s);
+        } else {
+          const float yr = fmaf(pk.x, A.x, fmaf(-pk.y, A.y, fmaf(qk.x, Bc.x, -qk.y * Bc.y)));
+          const float yi = fmaf(pk.x, A.y, fmaf(pk.y, A.x, fmaf(qk.x, Bc.y, qk.y * Bc.x)));
+          u[b * R0 + q] = make_float2(yi, yr);  // swap for the inverse transform
+        }
       }
     sync();  // every partner read done before the inverse transform's exchanges
     block_fft_single<PL>(u, t, xbuf, tw, sync);
@@ -792,15 +799,16 @@ int launch_fir(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, i
   const bool r2c_mid = mid_r2c && pg && variant != 1 && variant != 3;  // served by the real-packed block below
   if (!r2c_mid && (short_on_long_rows || (K > 129 && K <= 513))) {
     if (pg && variant == 1) return run_fir_pg<Plan<1024, 64, 8, 16, 8>, 256, 2>(ctx, a, channels, taps, st);
-    if (pg) return run_fir_pg<Plan<1024, 64, 8, 16, 8>, 384, 2>(ctx, a, channels, taps, st);
+    // packed fp32x2 butterflies (Plan::PK): 4.94 -> 4.53 ms at K = 255 on 64 ch x 600 s (profiles/r02x_packed_fp32x2.txt)
+    if (pg) return run_fir_pg<Plan<1024, 64, 8, 16, 8, 1, true>, 384, 2>(ctx, a, channels, taps, st);
     return run_fir<Plan<1024, 64, 8, 16, 8>, 256, 2>(ctx, a, channels, taps, st);
   }
   if ((K > 513 || mid_r2c) && pg && variant != 1 && variant != 3) {
     // real-packed overlap-save: one 8192-sample real block per 4096-point transform pair, V = 8193 - KP
     // outputs kept; long filters are cut into n equal runs of KP taps whose partial convolutions are
     // accumulated, y[n] += (x * h_p)[n - p KP] (work per output ~ n / (8193 - K / n); later passes
-    // read-modify-write y)
-    using PL = Plan<4096, 256, 16, 16, 16>;
+    // read-modify-write y).  Packed fp32x2 butterflies (Plan::PK): cfg4 6.15 -> 5.82 ms.
+    using PL = Plan<4096, 256, 16, 16, 16, 1, true>;
     int64_t n_best = 1;
     double c_best = 1e300;
     for (int64_t n = 1; n <= (K + 1023) / 1024; ++n) {

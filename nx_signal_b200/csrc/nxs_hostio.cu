@@ -95,6 +95,8 @@ struct StftHostJob {
 // pinned: where it was measured (one B200 per 16-vCPU guest: 103 ms mirrored, 112 ms mixed, 139 ms full) the
 // copy engine, slowed by the host threads' memory traffic, stays the bottleneck, so moving more bytes over it
 // to spare host traffic loses.
+constexpr size_t kSmallCallBytes = size_t(4) << 20;  // results and inputs up to here take the single-stream path
+
 int choose_mode(nxs_ctx* ctx, bool can_mirror, size_t result_bytes, int64_t nchunks) {
   if (!can_mirror) return 0;
   if (const char* e = getenv("NXS_HOST_NO_MIRROR")) {
@@ -146,7 +148,36 @@ int nxs_stft_f32_host(nxs_ctx* ctx, const float* x, int64_t channels, int64_t le
 
   const int64_t rows = channels * M;
   const size_t result_bytes = size_t(rows) * size_t(fft_length) * sizeof(float2);
+  // Small calls (what most NxSignal.stft calls are: BASELINE configs[0] is 184 frames): one stream, both
+  // spectrum halves over PCIe, no events, no host threads -- the call costs its four enqueues and one wait.
+  // A pageable input goes through the driver's own bounce buffer; a pageable RESULT keeps the ring path below
+  // (lower half into the pinned ring, host threads copy it out and mirror it: 142 us against 159 us for the
+  // driver's pageable D2H of the 1.5 MB of configs[0]).
+  const size_t span_bytes = size_t((channels - 1) * x_ld + length) * sizeof(float);
   const bool z_pinned = host_is_pinned(z), x_pinned = host_is_pinned(x);
+  if (result_bytes <= kSmallCallBytes && span_bytes <= kSmallCallBytes && ctx->host_mode_forced < 0 && z_pinned) {
+    rc = grow_buf(ctx, &ctx->d_stage_in, &ctx->d_stage_in_bytes, span_bytes + size_t(frame_length) * sizeof(float) + 512, false);
+    if (rc) return rc;
+    rc = grow_buf(ctx, &ctx->d_stage_out, &ctx->d_stage_out_bytes, result_bytes + 256, false);
+    if (rc) return rc;
+    float* d_x = (float*)ctx->d_stage_in;
+    float* d_w = (float*)((char*)ctx->d_stage_in + (span_bytes + 255) / 256 * 256);
+    float2* d_z = (float2*)ctx->d_stage_out;
+    ctx->host_mode_last = 4;
+    cudaError_t e = cudaMemcpyAsync(d_x, x, span_bytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_w, window, size_t(frame_length) * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+      rc = launch_stft(ctx, d_x, channels, length, x_ld, d_w, frame_length, hop, fft_length, g, M, scaling, sampling_rate,
+                       d_z, fft_length, 0, ctx->stream);
+      if (rc == NXS_OK) e = cudaMemcpyAsync(z, d_z, result_bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    const cudaError_t es = cudaStreamSynchronize(ctx->stream);  // nothing of ours touches the caller's buffers after return
+    if (rc) return rc;
+    NXS_CUDA(ctx, e);
+    NXS_CUDA(ctx, es);
+    ctx->host_t[0] = ctx->host_t[1] = ctx->host_t[2] = ctx->host_t[3] = wall_seconds() - t_start;
+    return NXS_OK;
+  }
   const bool can_mirror = stft_has_exact_mirror(fft_length);
   const bool unstage = !z_pinned;
   const bool stage_in = !x_pinned;

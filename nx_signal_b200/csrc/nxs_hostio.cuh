@@ -95,15 +95,21 @@ int host_pipeline(nxs_ctx* ctx, const PipeSpec& s, F&& launch) {
   const size_t big = s.in_pitch > s.out_pitch ? s.in_pitch : s.out_pitch;
   int64_t per = (int64_t)(s.chunk_target / (big ? big : 1));
   if (per < 1) per = 1;
-  if (s.rows >= 4 && per > (s.rows + 3) / 4) per = (s.rows + 3) / 4;  // at least four chunks when there are four rows
+  const bool small_call = size_t(s.rows) * big <= (size_t(4) << 20);  // not worth a pipeline: one chunk, one stream
+  if (s.rows >= 4 && per > (s.rows + 3) / 4 && !small_call) per = (s.rows + 3) / 4;  // at least four chunks when there are four rows
   if (per > s.rows) per = s.rows;
   const int64_t nchunks = (s.rows + per - 1) / per;
   auto span = [](int64_t n, size_t pitch, size_t row) { return n > 0 ? size_t(n - 1) * pitch + row : size_t(0); };
   const size_t in_slot = (span(per, s.in_pitch, s.in_row_bytes) + 255) / 256 * 256;
   const size_t out_slot = (span(per, s.out_pitch, s.out_row_bytes) + 255) / 256 * 256;
   const size_t aux_pad = (s.aux_bytes + 255) / 256 * 256;
-  const bool in_pg = s.in_row_bytes && !host_is_pinned(s.in);
-  const bool out_pg = s.out_row_bytes && !host_is_pinned(s.out);
+  // a single small chunk: everything on the compute stream (no cross-stream hand-offs), and pageable memory
+  // through the driver's own bounce buffer, which beats waking the host threads below about a MiB
+  const bool single = nchunks == 1;
+  const size_t kDriverStaged = size_t(1) << 20;
+  cudaStream_t const s_in = single ? ctx->stream : ctx->copy_stream;
+  const bool in_pg = s.in_row_bytes && !(single && in_slot <= kDriverStaged) && !host_is_pinned(s.in);
+  const bool out_pg = s.out_row_bytes && !(single && out_slot <= kDriverStaged) && !host_is_pinned(s.out);
 
   int rc = grow_buf(ctx, &ctx->d_stage_in, &ctx->d_stage_in_bytes, NS * in_slot + aux_pad + 256, false);
   if (rc) return rc;
@@ -115,6 +121,7 @@ int host_pipeline(nxs_ctx* ctx, const PipeSpec& s, F&& launch) {
     if (rc) return rc;
   }
   if (!ctx->out_stream) NXS_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->out_stream, cudaStreamNonBlocking));
+  cudaStream_t const s_out = single ? ctx->stream : ctx->out_stream;
   rc = ensure_events(ctx, 3 * NS);
   if (rc) return rc;
   char* const d_in = (char*)ctx->d_stage_in;
@@ -159,7 +166,7 @@ int host_pipeline(nxs_ctx* ctx, const PipeSpec& s, F&& launch) {
     char* dout = d_out + slot * out_slot;
     // H2D of chunk k (its device slot is free once the kernels of chunk k - NS have run)
     if (s.in_row_bytes) {
-      if (k >= NS) NXS_PIPE_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ev_krn[slot], 0));
+      if (k >= NS) NXS_PIPE_CUDA(cudaStreamWaitEvent(s_in, ev_krn[slot], 0));
       const char* src = (const char*)s.in + r0 * s.in_pitch;
       if (in_pg) {
         char* hs = h_in + (k & 1) * in_slot;
@@ -169,32 +176,34 @@ int host_pipeline(nxs_ctx* ctx, const PipeSpec& s, F&& launch) {
         parallel_copy(ctx, pieces);
         src = hs;
       }
-      NXS_PIPE_CUDA(cudaMemcpyAsync(di, src, span(n, s.in_pitch, s.in_row_bytes), cudaMemcpyHostToDevice, ctx->copy_stream));
-      NXS_PIPE_CUDA(cudaEventRecord(ev_h2d[slot], ctx->copy_stream));
-      NXS_PIPE_CUDA(cudaStreamWaitEvent(ctx->stream, ev_h2d[slot], 0));
+      NXS_PIPE_CUDA(cudaMemcpyAsync(di, src, span(n, s.in_pitch, s.in_row_bytes), cudaMemcpyHostToDevice, s_in));
+      if (!single) {
+        NXS_PIPE_CUDA(cudaEventRecord(ev_h2d[slot], s_in));
+        NXS_PIPE_CUDA(cudaStreamWaitEvent(ctx->stream, ev_h2d[slot], 0));
+      }
     }
     // kernels (the out slot is free once the D2H of chunk k - NS has drained it)
     if (k >= NS && s.out_row_bytes) NXS_PIPE_CUDA(cudaStreamWaitEvent(ctx->stream, ev_d2h[slot], 0));
     rc = launch(r0, n, (void*)di, (void*)d_aux, (void*)dout);
     if (rc) return fail(rc);
-    NXS_PIPE_CUDA(cudaEventRecord(ev_krn[slot], ctx->stream));
+    if (!single) NXS_PIPE_CUDA(cudaEventRecord(ev_krn[slot], ctx->stream));
     // D2H
     if (s.out_row_bytes) {
-      NXS_PIPE_CUDA(cudaStreamWaitEvent(ctx->out_stream, ev_krn[slot], 0));
+      if (!single) NXS_PIPE_CUDA(cudaStreamWaitEvent(s_out, ev_krn[slot], 0));
       char* dst = out_pg ? h_out + (k & 1) * out_slot : (char*)s.out + r0 * s.out_pitch;
       if (s.out_pitch == s.out_row_bytes || out_pg)
-        NXS_PIPE_CUDA(cudaMemcpyAsync(dst, dout, span(n, s.out_pitch, s.out_row_bytes), cudaMemcpyDeviceToHost, ctx->out_stream));
+        NXS_PIPE_CUDA(cudaMemcpyAsync(dst, dout, span(n, s.out_pitch, s.out_row_bytes), cudaMemcpyDeviceToHost, s_out));
       else  // never write the caller's bytes between rows
         NXS_PIPE_CUDA(cudaMemcpy2DAsync(dst, s.out_pitch, dout, s.out_pitch, s.out_row_bytes, (size_t)n,
-                                        cudaMemcpyDeviceToHost, ctx->out_stream));
-      NXS_PIPE_CUDA(cudaEventRecord(ev_d2h[slot], ctx->out_stream));
+                                        cudaMemcpyDeviceToHost, s_out));
+      if (!single || out_pg) NXS_PIPE_CUDA(cudaEventRecord(ev_d2h[slot], s_out));
       if (out_pg && k >= 1) NXS_PIPE_CUDA(unstage(k - 1));
     }
   }
   if (out_pg) NXS_PIPE_CUDA(unstage(nchunks - 1));
-  NXS_PIPE_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+  if (!single) NXS_PIPE_CUDA(cudaStreamSynchronize(ctx->copy_stream));
   NXS_PIPE_CUDA(cudaStreamSynchronize(ctx->stream));
-  NXS_PIPE_CUDA(cudaStreamSynchronize(ctx->out_stream));
+  if (!single) NXS_PIPE_CUDA(cudaStreamSynchronize(ctx->out_stream));
 #undef NXS_PIPE_CUDA
   return NXS_OK;
 }

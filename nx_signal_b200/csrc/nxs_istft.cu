@@ -338,8 +338,12 @@ __global__ void __launch_bounds__(THREADS, MINB) istft_rola_kernel(const IstftAr
           const int j = b + q * BL;
           const cpx r = v[fft_out_reg<PL>(b, q)];
           const float w = wsm[t + j * T];
-          acc[j].x += r.y * w;
-          acc[j].y += r.x * w;
+          if constexpr (PL::PK) {
+            acc[j] = __ffma2_rn(make_float2(r.y, r.x), make_float2(w, w), acc[j]);
+          } else {
+            acc[j].x += r.y * w;
+            acc[j].y += r.x * w;
+          }
         }
       if (m >= ms) {
         const int64_t pos = m * HOP + t;
@@ -351,7 +355,7 @@ __global__ void __launch_bounds__(THREADS, MINB) istft_rola_kernel(const IstftAr
             const float nr = norm_at(pos + j * T);
             rd = 1.0f / (nr > 1.0e-10f ? nr : 1.0f);  // select(norm > 1e-10, norm, 1.0)
           }
-          __stcs(yc + pos + j * T, make_float2(acc[j].x * rd, acc[j].y * rd));
+          __stcs(yc + pos + j * T, cscale_<PL::PK>(acc[j], rd));
         }
       }
 #pragma unroll
@@ -702,10 +706,10 @@ static int run_istft(nxs_ctx* ctx, IstftArgs a, int64_t channels, cudaStream_t s
   a.total_segs = (int)total;
   auto kern = istft_kernel<PL, THREADS, MINB>;
   if (CF::SMEM > 231424) return NXS_EUNSUPPORTED;
-  NXS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF::SMEM));
+  static LaunchCache cache;
   int occ = 1;
-  NXS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, CF::SMEM));
-  if (occ < 1) occ = 1;
+  rc = cache.get(ctx, kern, THREADS, CF::SMEM, &occ);
+  if (rc) return rc;
   int64_t grid = int64_t(ctx->sm_count) * occ;
   if (grid > total) grid = total;
   prof_begin(ctx, st);
@@ -888,6 +892,25 @@ __global__ void __launch_bounds__(THREADS, MINB) istft_ring_kernel(const IstftAr
   }
 }
 
+// Frames per segment (a segment = consecutive frames of one channel that one group walks, after `warm`
+// recomputed frames that rebuild the overlap-add carry).  Large calls: a few segments per group so the tail is
+// balanced, never so short that the recomputed frames exceed ~6 %.  Calls too small to give every group such a
+// segment are latency-bound (BASELINE configs[0] is 184 frames): segments shrink until every group has one,
+// down to 8 frames -- more recomputation on a machine that is mostly idle anyway.  The sums are formed in
+// the same order whatever the segmentation, so the result does not depend on it.
+static inline int64_t segment_frames(int64_t total_frames, int64_t groups, int64_t warm, int64_t frames_per_channel) {
+  int64_t seg = (total_frames + groups * 4 - 1) / (groups * 4);
+  const int64_t seg_min = 16 * warm > 32 ? 16 * warm : 32;
+  if (seg < seg_min) {
+    seg = (total_frames + groups - 1) / groups;
+    if (seg > seg_min) seg = seg_min;
+    const int64_t lat_min = 2 * warm > 8 ? 2 * warm : 8;
+    if (seg < lat_min) seg = lat_min;
+  }
+  if (seg > frames_per_channel) seg = frames_per_channel;
+  return seg < 1 ? 1 : seg;
+}
+
 // register overlap-add kernel: requires z_len == N, hop * HOPDIV == N, hop % T == 0 and 16-byte aligned rows
 template <class PL, int THREADS, int MINB, int HOPDIV, bool XD = false>
 static int run_istft_rola(nxs_ctx* ctx, IstftArgs a, int64_t channels, cudaStream_t st) {
@@ -897,17 +920,14 @@ static int run_istft_rola(nxs_ctx* ctx, IstftArgs a, int64_t channels, cudaStrea
   if (rc) return rc;
   a.tw = tw;
   auto kern = istft_rola_kernel<PL, THREADS, MINB, HOPDIV, XD>;
-  NXS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF::SMEM));
+  static LaunchCache cache;
   int occ = 1;
-  NXS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, CF::SMEM));
-  if (occ < 1) occ = 1;
+  rc = cache.get(ctx, kern, THREADS, CF::SMEM, &occ);
+  if (rc) return rc;
   // segments: a few per group so the tail is balanced; each costs HOPDIV-1 recomputed frames
   const int64_t groups = int64_t(ctx->sm_count) * occ * CF::G;
   const int64_t total_frames = channels * a.M;
-  int64_t seg = (total_frames + groups * 4 - 1) / (groups * 4);
-  const int64_t seg_min = 16 * (HOPDIV - 1) > 32 ? 16 * (HOPDIV - 1) : 32;
-  if (seg < seg_min) seg = seg_min;
-  if (seg > a.M) seg = a.M;
+  const int64_t seg = segment_frames(total_frames, groups, HOPDIV - 1, a.M);
   a.seg_frames = (int)seg;
   a.segs_per_channel = (int)((a.M + seg - 1) / seg);
   const int64_t total = int64_t(a.segs_per_channel) * channels;
@@ -941,10 +961,7 @@ static int run_istft_warp(nxs_ctx* ctx, IstftArgs a, int64_t channels, cudaStrea
   // segments: a few per warp so the tail is balanced; each costs HOPDIV - 1 recomputed frames
   const int64_t groups = int64_t(ctx->sm_count) * CF::G;
   const int64_t total_frames = channels * a.M;
-  int64_t seg = (total_frames + groups * 4 - 1) / (groups * 4);
-  const int64_t seg_min = 16 * (HOPDIV - 1) > 32 ? 16 * (HOPDIV - 1) : 32;
-  if (seg < seg_min) seg = seg_min;
-  if (seg > a.M) seg = a.M;
+  const int64_t seg = segment_frames(total_frames, groups, HOPDIV - 1, a.M);
   a.seg_frames = (int)seg;
   a.segs_per_channel = (int)((a.M + seg - 1) / seg);
   const int64_t total = int64_t(a.segs_per_channel) * channels;
@@ -990,17 +1007,14 @@ static int run_istft_ring(nxs_ctx* ctx, IstftArgs a, int64_t channels, cudaStrea
   a.tw = tw;
   auto kern = istft_ring_kernel<PL, THREADS, MINB>;
   if (CF::SMEM > 232448) return NXS_EUNSUPPORTED;
-  NXS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF::SMEM));
+  static LaunchCache cache;
   int occ = 1;
-  NXS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, CF::SMEM));
-  if (occ < 1) occ = 1;
+  rc = cache.get(ctx, kern, THREADS, CF::SMEM, &occ);
+  if (rc) return rc;
   const int64_t kcov = (PL::N + a.hop - 1) / a.hop;
   const int64_t groups = int64_t(ctx->sm_count) * occ * CF::G;
   const int64_t total_frames = channels * a.M;
-  int64_t seg = (total_frames + groups * 4 - 1) / (groups * 4);
-  const int64_t seg_min = 16 * (kcov - 1) > 32 ? 16 * (kcov - 1) : 32;  // <= 6 % recomputed frames
-  if (seg < seg_min) seg = seg_min;
-  if (seg > a.M) seg = a.M;
+  const int64_t seg = segment_frames(total_frames, groups, kcov - 1, a.M);
   a.seg_frames = (int)seg;
   a.segs_per_channel = (int)((a.M + seg - 1) / seg);
   const int64_t total = int64_t(a.segs_per_channel) * channels;
@@ -1028,17 +1042,17 @@ static int try_istft_rola(nxs_ctx* ctx, const IstftArgs& a, int64_t channels, cu
   if (a.hop * 4 == PL::N) {
     if constexpr (PL::N == 1024) {  // tuning variant (tests/test_istft_gpu.py)
       const char* var = getenv("NXS_ISTFT_VARIANT");
-      if (var && atoi(var) == 1) return run_istft_rola<PL, THREADS, MINB, 4>(ctx, a, channels, st);
-      // one warp per frame, 32 points per lane, radices 32 x 32: ONE exchange per transform, no group barriers
-      if (var && atoi(var) == 2) return run_istft_rola<Plan<1024, 32, 32, 32>, 384, 1, 4>(ctx, a, channels, st);
-      if (var && atoi(var) == 3) return run_istft_rola<Plan<1024, 32, 32, 32>, 256, 1, 4>(ctx, a, channels, st);
-      if (var && atoi(var) == 4) return run_istft_rola<Plan<1024, 32, 32, 32>, 320, 1, 4>(ctx, a, channels, st);
-      // the same plan with the overlap-add carry in a private shared-memory column per lane (istft_warp_kernel)
-      if (var && atoi(var) == 5) return run_istft_warp<Plan<1024, 32, 32, 32>, 384, 4>(ctx, a, channels, st);
-      if (var && atoi(var) == 6) return run_istft_warp<Plan<1024, 32, 32, 32>, 448, 4>(ctx, a, channels, st);
-      if (var && atoi(var) == 7) return run_istft_warp<Plan<1024, 32, 32, 32>, 320, 4>(ctx, a, channels, st);
-      if (var && atoi(var) == 8) return run_istft_warp<Plan<1024, 32, 32, 32>, 352, 4>(ctx, a, channels, st);
-      return run_istft_rola<PL, THREADS, MINB, 4, true>(ctx, a, channels, st);  // two exchange buffers still fit 2 CTAs/SM
+      const int v = var ? atoi(var) : 0;
+      if (v == 1) return run_istft_rola<PL, THREADS, MINB, 4>(ctx, a, channels, st);
+      if (v == 2) return run_istft_rola<PL, THREADS, MINB, 4, true>(ctx, a, channels, st);  // T = 64, two exchange buffers, 2 CTAs/SM
+      if (v == 4) return run_istft_rola<Plan<1024, 32, 32, 32>, 320, 1, 4>(ctx, a, channels, st);
+      // the warp-per-frame plan with the overlap-add carry in a private shared-memory column per lane
+      // (istft_warp_kernel): more warps per SM, but the carry traffic costs more than the occupancy buys
+      if (v == 5) return run_istft_warp<Plan<1024, 32, 32, 32>, 384, 4>(ctx, a, channels, st);
+      // default: one warp per frame, 32 points per lane, radices 32 x 32 -- ONE exchange per transform and no
+      // group barrier (0.713 ms at cfg5 against 0.735 for v == 2 and 0.758 for v == 5, profiles/r02v_istft_variants.txt)
+      // with the butterflies on the packed fp32x2 instructions (Plan::PK): 0.720 -> 0.668 ms
+      return run_istft_rola<Plan<1024, 32, 32, 32, 1, 1, PL::PK>, 256, 1, 4>(ctx, a, channels, st);
     }
     return run_istft_rola<PL, THREADS, MINB, 4>(ctx, a, channels, st);
   }
@@ -1306,12 +1320,19 @@ static int launch_istft_main(nxs_ctx* ctx, const float2* z, int64_t channels, in
   const bool pow2 = (nfft & (nfft - 1)) == 0;
   if (pow2 && nfft >= 256 && nfft <= 4096) {  // register overlap-add fast path (hop = N/2, N/4, N/8)
     bool done = false;
+    const bool scalar = getenv("NXS_ISTFT_SCALAR") != nullptr;
     switch (nfft) {
-      case 256: rc = try_istft_rola<Plan<256, 32, 8, 8, 4>, 256, 2>(ctx, a, channels, st, &done); break;
-      case 512: rc = try_istft_rola<Plan<512, 64, 8, 8, 8>, 256, 2>(ctx, a, channels, st, &done); break;
-      case 1024: rc = try_istft_rola<Plan<1024, 64, 16, 8, 8>, 256, 2>(ctx, a, channels, st, &done); break;
-      case 2048: rc = try_istft_rola<Plan<2048, 128, 16, 16, 8>, 256, 2>(ctx, a, channels, st, &done); break;
-      case 4096: rc = try_istft_rola<Plan<4096, 256, 16, 16, 16>, 512, 1>(ctx, a, channels, st, &done); break;
+      // FFT engine, window and overlap-add on the packed fp32x2 instructions (Plan::PK; nxs_fft.cuh): cfg5 0.720 ->
+      // 0.637 ms, nfft 2048 0.847 -> 0.769 ms (profiles/r02x_packed_fp32x2.txt); NXS_ISTFT_SCALAR=1 runs the scalar plans
+#define NXS_ROLA(TH, MB, ...)                                                                          \
+  rc = scalar ? try_istft_rola<Plan<__VA_ARGS__>, TH, MB>(ctx, a, channels, st, &done)                 \
+              : try_istft_rola<Plan<__VA_ARGS__, 1, true>, TH, MB>(ctx, a, channels, st, &done)
+      case 256: NXS_ROLA(256, 2, 256, 32, 8, 8, 4); break;
+      case 512: NXS_ROLA(256, 2, 512, 64, 8, 8, 8); break;
+      case 1024: NXS_ROLA(256, 2, 1024, 64, 16, 8, 8); break;
+      case 2048: NXS_ROLA(256, 2, 2048, 128, 16, 16, 8); break;
+      case 4096: NXS_ROLA(512, 1, 4096, 256, 16, 16, 16); break;
+#undef NXS_ROLA
       default: break;
     }
     if (rc || done) return rc;
@@ -1621,16 +1642,13 @@ static int run_istft_rola_c2r(nxs_ctx* ctx, IstftC2rArgs a, int64_t channels, cu
   if (rc) return rc;
   a.pre = pre;
   auto kern = istft_rola_c2r_kernel<PL, THREADS, MINB, HOPDIV>;
-  NXS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF::SMEM));
+  static LaunchCache cache;
   int occ = 1;
-  NXS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, CF::SMEM));
-  if (occ < 1) occ = 1;
+  rc = cache.get(ctx, kern, THREADS, CF::SMEM, &occ);
+  if (rc) return rc;
   const int64_t groups = int64_t(ctx->sm_count) * occ * CF::G;
   const int64_t total_frames = channels * a.M;
-  int64_t seg = (total_frames + groups * 4 - 1) / (groups * 4);
-  const int64_t seg_min = 16 * (HOPDIV - 1) > 32 ? 16 * (HOPDIV - 1) : 32;
-  if (seg < seg_min) seg = seg_min;
-  if (seg > a.M) seg = a.M;
+  const int64_t seg = segment_frames(total_frames, groups, HOPDIV - 1, a.M);
   a.seg_frames = (int)seg;
   a.segs_per_channel = (int)((a.M + seg - 1) / seg);
   const int64_t total = int64_t(a.segs_per_channel) * channels;
@@ -1712,11 +1730,16 @@ int launch_istft_c2r(nxs_ctx* ctx, const float2* z, int64_t channels, int64_t nu
     a.seg_frames = a.segs_per_channel = a.total_segs = 0;
     a.tw = a.pre = nullptr;
     bool done = false;
+    const bool scalar = getenv("NXS_ISTFT_SCALAR") != nullptr;
     switch (nfft) {
-      case 512: rc = try_istft_rola_c2r<Plan<256, 32, 8, 8, 4>, 256, 2>(ctx, a, hop, channels, st, &done); break;
-      case 1024: rc = try_istft_rola_c2r<Plan<512, 64, 8, 8, 8>, 256, 2>(ctx, a, hop, channels, st, &done); break;
-      case 2048: rc = try_istft_rola_c2r<Plan<1024, 64, 16, 8, 8>, 256, 2>(ctx, a, hop, channels, st, &done); break;
-      case 4096: rc = try_istft_rola_c2r<Plan<2048, 128, 16, 16, 8>, 256, 2>(ctx, a, hop, channels, st, &done); break;
+#define NXS_ROLA_C2R(TH, MB, ...)                                                                      \
+  rc = scalar ? try_istft_rola_c2r<Plan<__VA_ARGS__>, TH, MB>(ctx, a, hop, channels, st, &done)         \
+              : try_istft_rola_c2r<Plan<__VA_ARGS__, 1, true>, TH, MB>(ctx, a, hop, channels, st, &done)
+      case 512: NXS_ROLA_C2R(256, 2, 256, 32, 8, 8, 4); break;
+      case 1024: NXS_ROLA_C2R(256, 2, 512, 64, 8, 8, 8); break;  // packed engine: 0.514 -> 0.488 ms at cfg5's shape
+      case 2048: NXS_ROLA_C2R(256, 2, 1024, 64, 16, 8, 8); break;
+      case 4096: NXS_ROLA_C2R(256, 2, 2048, 128, 16, 16, 8); break;
+#undef NXS_ROLA_C2R
       default: break;
     }
     if (rc) return rc;

@@ -225,9 +225,12 @@ __global__ void __launch_bounds__(THREADS) stft_r2c_kernel(const StftArgs a) {
 // so no barrier separates a middle pass's reads from its writes: three group barriers per frame instead of
 // four, paid for with shared memory (one 512-thread CTA per SM instead of two of 256).
 template <class PL_, int THREADS_, int HOPDIV_, bool TWREG_, bool PERGROUP_ = false, bool LEAN_ = false,
-          bool WINREG_ = false, bool PAIRED_ = false, bool XD_ = false, bool TWC_ = XD_>
+          bool WINREG_ = false, bool PAIRED_ = false, bool XD_ = false, bool TWC_ = XD_, int KPK_ = 0>
 struct StagedCfg {
   using PL = PL_;
+  // packed fp32x2 arithmetic outside the FFT engine (which follows Plan::PK): 1 = the window multiply,
+  // 2 = the split pass, 4 = the conjugate stores formed from the split pass's operands
+  static constexpr int KPK = KPK_;
   static constexpr int THREADS = THREADS_, HOPDIV = HOPDIV_;
   static constexpr bool TWREG = TWREG_, PERGROUP = PERGROUP_, LEAN = LEAN_, WINREG = WINREG_, PAIRED = PAIRED_, XD = XD_;
   static constexpr bool TWC = TWC_ || XD_;  // compact twiddle table (power-of-two rows; TwDeriveC)
@@ -450,7 +453,8 @@ __global__ void __launch_bounds__(CF::THREADS, MINB) stft_r2c_staged_kernel(cons
               float2 ww;
               if constexpr (CF::WINREG) ww = wreg[b * R0 + q];
               else ww = wp[i];
-              v[b * R0 + q] = make_float2(xx.x * ww.x, xx.y * ww.y);
+              if constexpr ((CF::KPK & 1) != 0) v[b * R0 + q] = __fmul2_rn(xx, ww);
+              else v[b * R0 + q] = make_float2(xx.x * ww.x, xx.y * ww.y);
             }
         } else {  // odd sample offset: the pairs are not 8-byte aligned in shared memory
 #pragma unroll
@@ -608,14 +612,17 @@ __global__ void __launch_bounds__(CF::THREADS, MINB) stft_r2c_staged_kernel(cons
         int kk;
         cpx A, Bc, w, Zh = make_float2(0.f, 0.f);
         load_pair(v, pb, i, kk, A, Bc, w, Zh);
-        const cpx E = cadd(A, Bc), O = csub(A, Bc);
-        const cpx Tm = cmul(w, O);
-        const cpx X0 = cadd(E, Tm), X1 = csub(E, Tm);
+        constexpr bool PK = (CF::KPK & 2) != 0, PKC = (CF::KPK & 4) != 0;
+        const cpx E = cadd_<PK>(A, Bc), O = csub_<PK>(A, Bc);
+        const cpx Tm = cmul_<PK>(O, w);
+        const cpx X0 = cadd_<PK>(E, Tm), X1 = csub_<PK>(E, Tm);
         __stcs(zf + kk, X0);
         if (!ONESIDED || kk == 0) __stcs(zf + N + kk, X1);
         if (kk > 0) {
-          __stcs(zf + N - kk, cconj(X1));
-          if constexpr (!ONESIDED) __stcs(zf + NFFT - kk, cconj(X0));
+          // conj(X1), conj(X0) formed from E and Tm (packed: the half negations are operand modifiers)
+          __stcs(zf + N - kk, PKC ? cadd_<PKC>(make_float2(E.x, -E.y), make_float2(-Tm.x, Tm.y)) : cconj(X1));
+          if constexpr (!ONESIDED)
+            __stcs(zf + NFFT - kk, PKC ? cadd_<PKC>(make_float2(E.x, -E.y), make_float2(Tm.x, -Tm.y)) : cconj(X0));
         } else {
           __stcs(zf + N / 2, make_float2(2.f * Zh.x, -2.f * Zh.y));
           if constexpr (!ONESIDED) __stcs(zf + N + N / 2, make_float2(2.f * Zh.x, 2.f * Zh.y));
@@ -740,25 +747,6 @@ static int prep_for(nxs_ctx* ctx, StftArgs& a, int nfft, cudaStream_t st) {
   a.winline = 0;
   return rc;
 }
-
-// cudaFuncSetAttribute + occupancy query once per (kernel instantiation, device), not per call
-struct LaunchCache {
-  int occ[16] = {0};
-  size_t smem[16] = {0};
-  template <class K>
-  int get(nxs_ctx* ctx, K kern, int threads, size_t smem_bytes, int* out) {
-    const int d = ctx->device & 15;
-    if (occ[d] == 0 || smem[d] != smem_bytes) {
-      NXS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-      int o = 1;
-      NXS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, threads, smem_bytes));
-      smem[d] = smem_bytes;
-      occ[d] = o < 1 ? 1 : o;
-    }
-    *out = occ[d];
-    return NXS_OK;
-  }
-};
 
 template <class PL, class TW, int THREADS>
 static int run_r2c(nxs_ctx* ctx, StftArgs a, cudaStream_t st) {
@@ -965,6 +953,9 @@ int launch_stft(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, 
         if (variant == 6) { using CF = StagedCfg<Plan<512, 32, 16, 16, 2>, 256, 2, false, true, true>; NXS_TRY_STAGED(CF, 2); }
         if (variant == 7) { using CF = StagedCfg<Plan<512, 32, 16, 16, 2>, 128, 2, false, true, true>; NXS_TRY_STAGED(CF, 4); }
         if (variant == 8) { using CF = StagedCfg<Plan<512, 32, 16, 16, 2>, 256, 2, false, true, false>; NXS_TRY_STAGED(CF, 2); }
+        // FFT engine on packed fp32x2 (Plan::PK): 1.354 ms against 1.345 (with the window multiply too: 1.396) -- the kernel
+        // is HBM-bound and the re-pairing moves cost more than the packed butterflies save
+        if (variant == 14) { using CF = StagedCfg<Plan<512, 64, 8, 8, 8, 1, true>, 256, 2, true, true, false, true>; NXS_TRY_STAGED(CF, 2); }
         { using CF = StagedCfg<PL, 256, 2, true, true, false, true>; NXS_TRY_STAGED(CF, 2); }
         return run_r2c<PL, TwRegs<PL>, 512>(ctx, a, st);
       }
@@ -975,7 +966,9 @@ int launch_stft(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, 
         // the paired split pass loses here (1.58 vs 1.45 ms on 8 ch x 600 s): with T = 64 the thread-0 special
         // case of the pairing diverges in every second warp; kept as a tuning variant
         if (variant_env() == 3) { using CF = StagedCfg<PL, 256, 2, false, true, true, false, true>; NXS_TRY_STAGED(CF, 2); }
-        { using CF = StagedCfg<PL, 256, 2, false, true, true>; NXS_TRY_STAGED(CF, 2); }
+        if (variant_env() == 9) { using CF = StagedCfg<PL, 256, 2, false, true, true>; NXS_TRY_STAGED(CF, 2); }  // scalar arithmetic
+        // default: the FFT engine on packed fp32x2 (Plan::PK): 1.161 -> 1.111 ms on 64 ch x 60 s (with the window too: 1.114)
+        { using CF = StagedCfg<Plan<1024, 64, 16, 8, 8, 1, true>, 256, 2, false, true, true>; NXS_TRY_STAGED(CF, 2); }
         return run_r2c<PL, TwTable<PL>, 512>(ctx, a, st);
       }
       case 4096: {
@@ -990,12 +983,20 @@ int launch_stft(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, 
         // default for the spectrum outputs: paired split pass, two exchange buffers, one 512-thread CTA per SM
         // (cfg3 shard: 2.48 ms; paired 256 x 2 (variant 8): 2.52 - 2.64 ms; unpaired (4): 2.53 ms; P = 32 (6 / 7): 2.61 / 2.91 ms);
         // the fused log-mel epilogue keeps the single-buffer paired layout
-        if (variant_env() != 8 && !a.mel_out) { using CF = StagedCfg<PL, 512, 4, false, true, true, false, true, true>; NXS_TRY_STAGED(CF, 1); }
+        // scalar arithmetic = variant 9; FFT engine on the packed fp32x2 instructions (Plan::PK) = variant 10
+        if (variant_env() == 9 && !a.mel_out) { using CF = StagedCfg<PL, 512, 4, false, true, true, false, true, true>; NXS_TRY_STAGED(CF, 1); }
+        using PLK = Plan<2048, 128, 16, 16, 8, 1, true>;
+        if (variant_env() == 10 && !a.mel_out) { using CF = StagedCfg<PLK, 512, 4, false, true, true, false, true, true, true, 0>; NXS_TRY_STAGED(CF, 1); }
+        // default: engine + window multiply packed.  cfg3 shard, ms: scalar 2.39, engine 2.27, engine + window 2.21,
+        // engine + split pass 2.44, all three 2.37 (the split pass's select-built operands have to be moved into pairs)
+        if (variant_env() != 8 && !a.mel_out) { using CF = StagedCfg<PLK, 512, 4, false, true, true, false, true, true, true, 1>; NXS_TRY_STAGED(CF, 1); }
         { using CF = StagedCfg<PL, 256, 4, false, true, true, false, true>; NXS_TRY_STAGED(CF, 2); }
         return run_r2c<PL, TwTable<PL>, 512>(ctx, a, st);
       }
       case 8192: {
         using PL = Plan<4096, 256, 16, 16, 16>;
+        // packed fp32x2: engine only 0.751 ms, engine + window (variant 15) 0.700 ms against 0.706 ms scalar: no gain, tuning only
+        if (variant_env() == 15) { using CF = StagedCfg<Plan<4096, 256, 16, 16, 16, 1, true>, 512, 4, false, true, true, false, false, false, false, 1>; NXS_TRY_STAGED(CF, 1); }
         if (variant_env() != 1) { using CF = StagedCfg<PL, 512, 4, false, true, true>; NXS_TRY_STAGED(CF, 1); }
         return run_r2c<PL, TwTable<PL>, 512>(ctx, a, st);
       }

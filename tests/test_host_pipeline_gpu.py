@@ -69,6 +69,59 @@ def test_stft_host_entry_equals_device_entry_for_every_memory_kind_and_mode(mode
         _lib.set_host_mode(-1)
 
 
+@pytest.mark.parametrize("pinned", [True, False])
+@pytest.mark.parametrize("Cn,L,x_ld,N,H", [(1, 48_000, 48_000, 1024, 256), (3, 20_000, 20_040, 512, 128), (2, 5_000, 5_000, 120, 40)])
+def test_stft_small_call_path_equals_device_entry(pinned, Cn, L, x_ld, N, H):
+    """calls whose input and result fit 4 MiB (BASELINE configs[0] is one) take the single-stream path
+    (csrc/nxs_hostio.cu): same bits as the device entry, padded input rows, pinned or pageable memory"""
+    import torch
+
+    xfull = synth((Cn, x_ld), 411)
+    x = xfull[:, :L]
+    w = o.hann(N)
+    M = (L - N) // H + 1
+    zd, _, _ = nx.stft(torch.from_numpy(np.ascontiguousarray(x)).cuda(), torch.from_numpy(w).cuda(), overlap_length=N - H,
+                       fft_length=N, sampling_rate=FS)
+    xin = _pinned(xfull) if pinned else xfull
+    zout = torch.zeros((Cn, M, N), dtype=torch.complex64, pin_memory=True) if pinned else np.zeros((Cn, M, N), np.complex64)
+    ctx = _lib.context(0)
+    for _ in range(2):
+        rc = _lib.lib().nxs_stft_f32_host(ctx, A.ptr(xin), Cn, L, x_ld, w.ctypes.data, N, H, N, _lib.PAD_VALID, 0, 0,
+                                          _lib.SCALE_NONE, float(FS), A.ptr(zout))
+        _lib.check(rc, ctx, "stft(host, small)")
+        assert _lib.host_mode()["result"] == ("small_call_single_stream_full_d2h" if pinned else "onesided_d2h+pinned_ring_unstage")
+        np.testing.assert_array_equal(_bits(zout), _bits(zd))
+
+
+@pytest.mark.parametrize("pinned", [True, False])
+def test_small_calls_of_the_other_host_entries_equal_the_device_entries(pinned):
+    """host_pipeline's one-chunk path (everything on the compute stream): ISTFT and FIR on a short signal"""
+    import torch
+
+    rng = np.random.default_rng(412)
+    M, N, H = 184, 1024, 256
+    z = (rng.standard_normal((2, M, N)) + 1j * rng.standard_normal((2, M, N))).astype(np.complex64)
+    w = o.hann(N)
+    yd = nx.istft(torch.from_numpy(z).cuda(), torch.from_numpy(w).cuda(), overlap_length=N - H, fft_length=N, sampling_rate=FS)
+    out_len = M * H + N - H
+    zin = _pinned(z) if pinned else z
+    y = torch.zeros((2, out_len), dtype=torch.complex64, pin_memory=True) if pinned else np.zeros((2, out_len), np.complex64)
+    ctx = _lib.context(0)
+    _lib.check(_lib.lib().nxs_istft_c64_host(ctx, A.ptr(zin), 2, M, N, w.ctypes.data, N, H, N, 0, float(FS), A.ptr(y)), ctx, "istft")
+    np.testing.assert_array_equal(_bits(y), _bits(yd))
+    Cn, L, K = 5, 30_000, 129
+    x = synth((Cn, L), 413)
+    taps = synth((1, K), 414)[0]
+    for mode in ("full", "same", "valid"):
+        out_len = {"full": L + K - 1, "same": L, "valid": L - K + 1}[mode]
+        yd = conv.convolve(torch.from_numpy(x).cuda(), torch.from_numpy(taps).cuda()[None, :], mode=mode, method="fft")
+        xin = _pinned(x) if pinned else x
+        yh = torch.zeros((Cn, out_len), dtype=torch.float32).pin_memory() if pinned else np.zeros((Cn, out_len), np.float32)
+        rc = _lib.lib().nxs_fir_f32_host(ctx, A.ptr(xin), Cn, L, L, taps.ctypes.data, K, _lib.MODE[mode], A.ptr(yh), out_len)
+        _lib.check(rc, ctx, "fir(host, small)")
+        np.testing.assert_array_equal(_bits(yh), _bits(yd))
+
+
 def test_stft_host_generic_length_on_pageable_memory():
     """a non-power-of-two fft_length has no mirror mode: full rows travel, through the ring when pageable"""
     import torch

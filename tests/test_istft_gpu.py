@@ -248,13 +248,16 @@ def test_edge_samples_meet_plain_tolerance_only_with_f64_fixup(monkeypatch):
     assert np.abs(y0[:, 1:60] - yo[:, 1:60]).max() > np.abs(y[:, 1:60] - yo[:, 1:60]).max()
 
 
-def test_rola_two_exchange_buffer_variant(monkeypatch):
+@pytest.mark.parametrize("variant", ["1", "2", "4", "5"])
+def test_rola_tuning_variants(monkeypatch, variant):
+    """nfft 1024 / hop 256 kernels that are not the default (csrc/nxs_istft.cu try_istft_rola): T = 64 with one or
+    two exchange buffers, one warp per frame at 320 threads, and the shared-memory-carry kernel."""
     rng = np.random.default_rng(21)
     z = (rng.standard_normal((3, 700, 1024)) + 1j * rng.standard_normal((3, 700, 1024))).astype(np.complex64)
     w = o.hann(1024)
     kw = dict(overlap_length=768, fft_length=1024)
     yo = o.istft_fast(z, w, **kw)
-    monkeypatch.setenv("NXS_ISTFT_VARIANT", "1")
+    monkeypatch.setenv("NXS_ISTFT_VARIANT", variant)
     assert rel(nx.istft(z, w, **kw), yo) <= TOL
 
 
