@@ -41,7 +41,11 @@ def onesided_random(rng, shape_cm, nfft, z_ld=None):
 
 @pytest.mark.parametrize("nfft,hopdiv", [(512, 2), (512, 4), (512, 8), (1024, 2), (1024, 4), (1024, 8), (2048, 2),
                                          (2048, 4), (2048, 8), (4096, 2), (4096, 4), (4096, 8)])
-def test_fast_plans_vs_oracle(nfft, hopdiv):
+@pytest.mark.parametrize("scalar", [False, True])
+def test_fast_plans_vs_oracle(nfft, hopdiv, scalar, monkeypatch):
+    """default: FFT engine on packed fp32x2 arithmetic (Plan::PK); NXS_ISTFT_SCALAR=1: the scalar plans"""
+    if scalar:
+        monkeypatch.setenv("NXS_ISTFT_SCALAR", "1")
     rng = np.random.default_rng(nfft + hopdiv)
     hop = nfft // hopdiv
     M = 41

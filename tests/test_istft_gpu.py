@@ -261,6 +261,20 @@ def test_rola_tuning_variants(monkeypatch, variant):
     assert rel(nx.istft(z, w, **kw), yo) <= TOL
 
 
+@pytest.mark.parametrize("nfft,hop", [(256, 64), (512, 256), (1024, 256), (1024, 128), (2048, 512), (4096, 1024)])
+def test_rola_scalar_plans(monkeypatch, nfft, hop):
+    """the register-overlap-add plans run on packed fp32x2 arithmetic by default (Plan::PK); NXS_ISTFT_SCALAR
+    selects the scalar plans -- both within the same bound of the oracle"""
+    rng = np.random.default_rng(23 + nfft + hop)
+    z = (rng.standard_normal((2, 150, nfft)) + 1j * rng.standard_normal((2, 150, nfft))).astype(np.complex64)
+    w = o.hann(nfft)
+    kw = dict(overlap_length=nfft - hop, fft_length=nfft)
+    yo = o.istft_fast(z, w, **kw)
+    assert rel(nx.istft(z, w, **kw), yo) <= TOL
+    monkeypatch.setenv("NXS_ISTFT_SCALAR", "1")
+    assert rel(nx.istft(z, w, **kw), yo) <= TOL
+
+
 # ---- ring overlap-add kernel (any hop <= N) -----------------------------------------------------
 @pytest.mark.parametrize("nfft", [256, 512, 1024, 2048])
 @pytest.mark.parametrize("hop_spec", ["250/1024", "441/1024", "3/16", "1000/1024", "1/1", "17/1024", "1/40"])

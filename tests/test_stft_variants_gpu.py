@@ -1,5 +1,6 @@
 """Every STFT kernel variant selectable by NXS_STFT_VARIANT gives the same results as the default
-(parity of tuning variants; the default is what ships)."""
+(parity of tuning variants; the default is what ships).  Variants 9 / 10 / 14 / 15 switch the packed fp32x2
+arithmetic of the FFT engine (Plan::PK) off or on against the default of their size."""
 import numpy as np
 import pytest
 
@@ -10,8 +11,10 @@ from tests.util import TOL, frame_rel_err, synth
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("nfft,variant", [(1024, v) for v in "012345678"] + [(2048, v) for v in "012"] +
-                         [(4096, v) for v in "0123"] + [(8192, v) for v in "01"])
+@pytest.mark.parametrize("nfft,variant", [(1024, v) for v in "012345678"] + [(1024, "14")] +
+                         [(2048, v) for v in ["0", "1", "2", "3", "9"]] +
+                         [(4096, v) for v in ["0", "1", "2", "3", "4", "6", "7", "8", "9", "10"]] +
+                         [(8192, v) for v in ["0", "1", "15"]])
 @pytest.mark.parametrize("padding", ["valid", "reflect"])
 def test_variant_parity(nfft, variant, padding, monkeypatch):
     monkeypatch.setenv("NXS_STFT_VARIANT", variant)
