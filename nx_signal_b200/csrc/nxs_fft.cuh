@@ -101,6 +101,22 @@ __device__ __forceinline__ cpx mul_w32(cpx a) {
   }
 }
 
+// a * W_64^I, I in [0,32): the first stage of the radix-64 butterfly (odd I; even I are W_32 powers)
+template <int I, bool PK = false>
+__device__ __forceinline__ cpx mul_w64(cpx a) {
+  if constexpr (I % 2 == 0) return mul_w32<I / 2, PK>(a);
+  else {
+    // cos(2 pi j / 64), j = 0 .. 16
+    constexpr float c[17] = {1.0f, 0.99518472667219689f, 0.98078528040323043f, 0.95694033573220887f, 0.92387953251128674f,
+                             0.88192126434835503f, 0.83146961230254524f, 0.77301045336273696f, 0.70710678118654752f,
+                             0.63439328416364549f, 0.55557023301960218f, 0.47139673682599764f, 0.38268343236508977f,
+                             0.29028467725446236f, 0.19509032201612825f, 0.09801714032956060f, 0.0f};
+    constexpr float co = I <= 16 ? c[I] : -c[32 - I];
+    constexpr float si = I <= 16 ? c[16 - I] : c[I - 16];
+    return crot_<PK>(a, co, si);
+  }
+}
+
 // In-place decimation-in-frequency DFT of R points (forward, e^{-i...}).
 // Result X[k] is left at v[bitrev(k, log2 R)].
 template <int R, int I, bool PK>
@@ -109,7 +125,8 @@ struct DifStage {
     if constexpr (I < R / 2) {
       cpx a = v[I], b = v[I + R / 2];
       v[I] = cadd_<PK>(a, b);
-      if constexpr (R == 32) v[I + R / 2] = mul_w32<I, PK>(csub_<PK>(a, b));
+      if constexpr (R == 64) v[I + R / 2] = mul_w64<I, PK>(csub_<PK>(a, b));
+      else if constexpr (R == 32) v[I + R / 2] = mul_w32<I, PK>(csub_<PK>(a, b));
       else v[I + R / 2] = mul_w16<I * (16 / R), PK>(csub_<PK>(a, b));
       DifStage<R, I + 1, PK>::run(v);
     }
@@ -118,7 +135,7 @@ struct DifStage {
 
 template <int R, bool PK = false>
 struct Dft {
-  static_assert(R == 2 || R == 4 || R == 8 || R == 16 || R == 32, "radix");
+  static_assert(R == 2 || R == 4 || R == 8 || R == 16 || R == 32 || R == 64, "radix");
   static __device__ __forceinline__ void run(cpx* v) {
     if constexpr (R == 2) {
       cpx a = v[0], b = v[1];
@@ -290,6 +307,16 @@ __device__ __forceinline__ void apply_derived(const cpx* base, const ROW& row, c
         for (int q = 1; q < 8; ++q) {
           v[16 + q] = cmul_<PK>(v[16 + q], cmul_<PK>(w16, w[q]));
           v[24 + q] = cmul_<PK>(v[24 + q], cmul_<PK>(w24, w[q]));
+        }
+        if constexpr (R >= 64) {
+          const cpx w32 = base[row(5)];
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {  // octets 32, 40, 48, 56: W^32 times 1, W^8, W^16, W^24
+            const cpx wh = h == 0 ? w32 : cmul_<PK>(w32, h == 1 ? w8 : h == 2 ? w16 : w24);
+            v[32 + 8 * h] = cmul_<PK>(v[32 + 8 * h], wh);
+#pragma unroll
+            for (int q = 1; q < 8; ++q) v[32 + 8 * h + q] = cmul_<PK>(v[32 + 8 * h + q], cmul_<PK>(wh, w[q]));
+          }
         }
       }
     }

@@ -826,8 +826,10 @@ int launch_fir(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, i
       ap.K = (int)(K - p * KP < KP ? K - p * KP : KP);
       ap.start = a.start - p * KP;
       ap.accumulate = p > 0;
-      rc = variant == 4 ? run_fir_r2c<PL, 512, 1>(ctx, ap, channels, taps + p * KP, st)
-                        : run_fir_r2c<PL, 768, 1>(ctx, ap, channels, taps + p * KP, st);
+      // variant 7: two warps per block pair, 64 points per thread, radices 64 x 64 -- ONE exchange per transform
+      rc = variant == 7 ? run_fir_r2c<Plan<4096, 64, 64, 64, 1, 1, true>, 256, 1>(ctx, ap, channels, taps + p * KP, st)
+           : variant == 4 ? run_fir_r2c<PL, 512, 1>(ctx, ap, channels, taps + p * KP, st)
+                          : run_fir_r2c<PL, 768, 1>(ctx, ap, channels, taps + p * KP, st);
       if (rc) return rc;
     }
     return NXS_OK;

@@ -518,11 +518,17 @@ __global__ void __launch_bounds__(THREADS, 1) istft_warp_kernel(const IstftArgs 
           const int j = b + q * BL;
           const cpx r = v[fft_out_reg<PL>(b, q)];
           const float w = wsm[t + j * T];
-          cpx acc = make_float2(r.y * w, r.x * w);
-          if (j < P - S) {
-            const cpx old = carry[j * T];
-            acc.x += old.x;
-            acc.y += old.y;
+          cpx acc;
+          if constexpr (PL::PK) {
+            if (j < P - S) acc = __ffma2_rn(make_float2(r.y, r.x), make_float2(w, w), carry[j * T]);
+            else acc = __fmul2_rn(make_float2(r.y, r.x), make_float2(w, w));
+          } else {
+            acc = make_float2(r.y * w, r.x * w);
+            if (j < P - S) {
+              const cpx old = carry[j * T];
+              acc.x += old.x;
+              acc.y += old.y;
+            }
           }
           if (j < S) {
             if (emit) {
@@ -531,7 +537,7 @@ __global__ void __launch_bounds__(THREADS, 1) istft_warp_kernel(const IstftArgs 
                 const float nr = norm_at(pos + j * T);
                 rd = 1.0f / (nr > 1.0e-10f ? nr : 1.0f);
               }
-              __stcs(yc + pos + j * T, make_float2(acc.x * rd, acc.y * rd));
+              __stcs(yc + pos + j * T, cscale_<PL::PK>(acc, rd));
             }
           } else {
             carry[(j - S) * T] = acc;
@@ -1045,10 +1051,11 @@ static int try_istft_rola(nxs_ctx* ctx, const IstftArgs& a, int64_t channels, cu
       const int v = var ? atoi(var) : 0;
       if (v == 1) return run_istft_rola<PL, THREADS, MINB, 4>(ctx, a, channels, st);
       if (v == 2) return run_istft_rola<PL, THREADS, MINB, 4, true>(ctx, a, channels, st);  // T = 64, two exchange buffers, 2 CTAs/SM
-      if (v == 4) return run_istft_rola<Plan<1024, 32, 32, 32>, 320, 1, 4>(ctx, a, channels, st);
+      if (v == 4) return run_istft_rola<Plan<1024, 32, 32, 32, 1, 1, PL::PK>, 320, 1, 4>(ctx, a, channels, st);
       // the warp-per-frame plan with the overlap-add carry in a private shared-memory column per lane
       // (istft_warp_kernel): more warps per SM, but the carry traffic costs more than the occupancy buys
-      if (v == 5) return run_istft_warp<Plan<1024, 32, 32, 32>, 384, 4>(ctx, a, channels, st);
+      if (v == 5) return run_istft_warp<Plan<1024, 32, 32, 32, 1, 1, PL::PK>, 384, 4>(ctx, a, channels, st);
+      if (v == 6) return run_istft_warp<Plan<1024, 32, 32, 32, 1, 1, PL::PK>, 320, 4>(ctx, a, channels, st);
       // default: one warp per frame, 32 points per lane, radices 32 x 32 -- ONE exchange per transform and no
       // group barrier (0.713 ms at cfg5 against 0.735 for v == 2 and 0.758 for v == 5, profiles/r02v_istft_variants.txt)
       // with the butterflies on the packed fp32x2 instructions (Plan::PK): 0.720 -> 0.668 ms
@@ -1552,6 +1559,8 @@ __global__ void __launch_bounds__(THREADS, MINB) istft_rola_c2r_kernel(const Ist
             Bc = make_float2(nyq, 0.f);
           }
           const cpx pw = PRE_REGS ? pre[PRE_REGS ? b * R0 + q : 0] : __ldg(a.pre + k);
+          // scalar on purpose: the packed forms of this pre-pass and of the overlap-add below cost 4 % at cfg5's
+          // shape (0.489 -> 0.508 ms; the operands are assembled from scalars) -- only the FFT engine follows PL::PK
           const cpx Z = cadd(cadd(A, Bc), cmul(pw, csub(A, Bc)));
           v[b * R0 + q] = make_float2(Z.y, Z.x);  // swap: ifft(x) = swap(fft(swap(x))) / n
           // large plans: keep the compiler from hoisting all 2 P stage loads (register pressure)

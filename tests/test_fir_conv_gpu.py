@@ -168,7 +168,7 @@ def test_fir_linearity_and_device_entry_at_scale():
 # ---- per-group (TMA-staged) overlap-save kernel: alignment cases, variants, old-kernel agreement ----
 @pytest.mark.parametrize("K", [130, 513, 514, 2049, 3585])
 @pytest.mark.parametrize("L", [65_536, 65_537, 50_002])
-@pytest.mark.parametrize("variant", ["0", "1"])
+@pytest.mark.parametrize("variant", ["0", "1", "3", "4", "7"])
 def test_fir_pg_alignment_and_variants(K, L, variant, monkeypatch):
     """L % 4 == 0 rows are staged by TMA (spans start at arbitrary sample offsets: the kernel floors
     them to 16 bytes), other row strides take the per-thread load path of the same kernel."""

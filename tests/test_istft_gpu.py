@@ -248,7 +248,7 @@ def test_edge_samples_meet_plain_tolerance_only_with_f64_fixup(monkeypatch):
     assert np.abs(y0[:, 1:60] - yo[:, 1:60]).max() > np.abs(y[:, 1:60] - yo[:, 1:60]).max()
 
 
-@pytest.mark.parametrize("variant", ["1", "2", "4", "5"])
+@pytest.mark.parametrize("variant", ["1", "2", "4", "5", "6"])
 def test_rola_tuning_variants(monkeypatch, variant):
     """nfft 1024 / hop 256 kernels that are not the default (csrc/nxs_istft.cu try_istft_rola): T = 64 with one or
     two exchange buffers, one warp per frame at 320 threads, and the shared-memory-carry kernel."""
