@@ -827,7 +827,9 @@ int launch_fir(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, i
       ap.start = a.start - p * KP;
       ap.accumulate = p > 0;
       // variant 7: two warps per block pair, 64 points per thread, radices 64 x 64 -- ONE exchange per transform
-      rc = variant == 7 ? run_fir_r2c<Plan<4096, 64, 64, 64, 1, 1, true>, 256, 1>(ctx, ap, channels, taps + p * KP, st)
+      // variant 8: the default layout on scalar arithmetic (A/B against the packed fp32x2 plan)
+      rc = variant == 8 ? run_fir_r2c<Plan<4096, 256, 16, 16, 16>, 768, 1>(ctx, ap, channels, taps + p * KP, st)
+           : variant == 7 ? run_fir_r2c<Plan<4096, 64, 64, 64, 1, 1, true>, 256, 1>(ctx, ap, channels, taps + p * KP, st)
            : variant == 4 ? run_fir_r2c<PL, 512, 1>(ctx, ap, channels, taps + p * KP, st)
                           : run_fir_r2c<PL, 768, 1>(ctx, ap, channels, taps + p * KP, st);
       if (rc) return rc;
