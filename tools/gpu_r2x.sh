@@ -1,4 +1,5 @@
 #!/bin/bash
+# (historical: this run used a global NXS_F32X2 build switch; the choice is per plan now -- Plan::PK, NXS_STFT_VARIANT / NXS_ISTFT_SCALAR / NXS_FIR_VARIANT=8)
 # r02x: packed fp32x2 complex arithmetic (FADD2/FMUL2/FFMA2) in the FFT engine against the scalar build: parity + timings
 OUT=gpurun_out/r02x; mkdir -p $OUT
 timeout 1200 python -m pytest tests/test_stft_gpu.py tests/test_istft_gpu.py tests/test_istft_c2r_gpu.py tests/test_fir_conv_gpu.py tests/test_mel_gpu.py tests/test_golden_gpu.py tests/test_host_pipeline_gpu.py -m gpu -q -x > $OUT/pytest.log 2>&1; tail -2 $OUT/pytest.log

@@ -1,4 +1,5 @@
 #!/bin/bash
+# (historical: NXS_ISTFT_PK was replaced by packed defaults with NXS_ISTFT_SCALAR=1 as the A/B switch)
 # r03a: FFT engine on packed fp32x2 (Plan::PK) for the remaining transform kernels: parity + timings per variant
 OUT=gpurun_out/r03a; mkdir -p $OUT
 for v in 14 15; do NXS_STFT_VARIANT=$v timeout 900 python -m pytest tests/test_stft_gpu.py tests/test_mel_gpu.py tests/test_golden_gpu.py -m gpu -q > $OUT/pytest_stft_v$v.log 2>&1; echo "stft variant $v: $(tail -1 $OUT/pytest_stft_v$v.log)"; done
