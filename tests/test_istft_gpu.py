@@ -261,10 +261,11 @@ def test_rola_tuning_variants(monkeypatch, variant):
     assert rel(nx.istft(z, w, **kw), yo) <= TOL
 
 
-@pytest.mark.parametrize("nfft,hop", [(256, 64), (512, 256), (1024, 256), (1024, 128), (2048, 512), (4096, 1024)])
+@pytest.mark.parametrize("nfft,hop", [(256, 64), (512, 256), (1024, 256), (1024, 128), (2048, 512), (4096, 1024),
+                                      (1024, 250), (1024, 441), (512, 160), (2048, 700), (256, 100)])
 def test_rola_scalar_plans(monkeypatch, nfft, hop):
-    """the register-overlap-add plans run on packed fp32x2 arithmetic by default (Plan::PK); NXS_ISTFT_SCALAR
-    selects the scalar plans -- both within the same bound of the oracle"""
+    """the register-overlap-add plans and the ring plans (any hop) run on packed fp32x2 arithmetic by default
+    (Plan::PK); NXS_ISTFT_SCALAR selects the scalar plans -- both within the same bound of the oracle"""
     rng = np.random.default_rng(23 + nfft + hop)
     z = (rng.standard_normal((2, 150, nfft)) + 1j * rng.standard_normal((2, 150, nfft))).astype(np.complex64)
     w = o.hann(nfft)
