@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(CF::THREADS, MINB) stft_r2c_staged_kernel(cons
   constexpr int N = PL::N, T = PL::T, P = PL::P, G = CF::G, NFFT = 2 * N;
   constexpr int R0 = PL::R(0), B0 = P / R0;
   constexpr int RL = PL::R(PL::NP - 1), BL = P / RL;
-  static_assert(THREADS % T == 0 && P >= 2 && G <= 15, "bad plan");
+  static_assert(THREADS % T == 0 && P >= 2 && G <= (T > 32 ? 15 : 64), "bad plan");  // named barriers 1 .. 15 (groups of a warp or less use __syncwarp)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, g = tid / T, t = tid % T;
   cpx* bufA = reinterpret_cast<cpx*>(smem_raw) + (size_t)(CF::NXBUF * g) * PL::BUF;
@@ -929,9 +929,25 @@ int launch_stft(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, 
 #define NXS_TRY_STAGED(CF, MINB) \
   if (staged_ok<CF>(a, channels)) return run_r2c_staged<CF, MINB>(ctx, a, channels, st)
     switch (nfft) {
-      case 64: return run_r2c<Plan<32, 4, 8, 4>, TwTable<Plan<32, 4, 8, 4>>, 256>(ctx, a, st);
-      case 128: return run_r2c<Plan<64, 8, 8, 8>, TwTable<Plan<64, 8, 8, 8>>, 256>(ctx, a, st);
-      case 256: return run_r2c<Plan<128, 16, 8, 8, 2>, TwTable<Plan<128, 16, 8, 8, 2>>, 256>(ctx, a, st);
+      case 64:  // the staged form does not pay at 256-byte frames (3.26 against 3.22 ms): tuning variant
+        if (variant_env() == 16 && !a.mel_out) { using CF = StagedCfg<Plan<32, 4, 8, 4, 1, 1, true>, 128, 2, true, true>; NXS_TRY_STAGED(CF, 4); }
+        return run_r2c<Plan<32, 4, 8, 4>, TwTable<Plan<32, 4, 8, 4>>, 256>(ctx, a, st);
+      // nfft 128 / 256: packed fp32x2 engine by default (2.24 -> 2.20 ms, 1.90 -> 1.86 ms on 8 ch x 600 s); variant 9 = scalar
+      case 128:
+        if (variant_env() == 9) return run_r2c<Plan<64, 8, 8, 8>, TwTable<Plan<64, 8, 8, 8>>, 256>(ctx, a, st);
+        // default: the TMA-staged per-group kernel, 8 threads per frame: 2.20 -> 1.86 ms at hop 32, 1.24 -> 0.95 ms at hop 64
+        // (8 ch x 600 s); variant 18 = the general kernel
+        if (variant_env() != 18 && !a.mel_out) { using CF = StagedCfg<Plan<64, 8, 8, 8, 1, 1, true>, 128, 2, true, true>; NXS_TRY_STAGED(CF, 4); }
+        return run_r2c<Plan<64, 8, 8, 8, 1, 1, true>, TwTable<Plan<64, 8, 8, 8, 1, 1, true>>, 256>(ctx, a, st);
+      case 256:
+        if (variant_env() == 9) return run_r2c<Plan<128, 16, 8, 8, 2>, TwTable<Plan<128, 16, 8, 8, 2>>, 256>(ctx, a, st);
+        // default: the TMA-staged per-group kernel with half-warp groups (16 threads per frame, __syncwarp as the group
+        // barrier, 16 groups per 256-thread CTA): 1.86 -> 1.38 ms on 8 ch x 600 s at hop 64 (0.68 -> 0.92 of the HBM peak), any hop / padding offset;
+        // variant 18 = the general kernel, 17 = window in registers as well (1.52 ms)
+        if (variant_env() == 17 && !a.mel_out) { using CF = StagedCfg<Plan<128, 16, 8, 8, 2, 1, true>, 128, 2, true, true, false, true>; NXS_TRY_STAGED(CF, 4); }
+        if (variant_env() == 16 && !a.mel_out) { using CF = StagedCfg<Plan<128, 16, 8, 8, 2, 1, true>, 128, 2, true, true>; NXS_TRY_STAGED(CF, 4); }  // 1.40 ms
+        if (variant_env() != 18 && !a.mel_out) { using CF = StagedCfg<Plan<128, 16, 8, 8, 2, 1, true>, 256, 2, true, true>; NXS_TRY_STAGED(CF, 2); }
+        return run_r2c<Plan<128, 16, 8, 8, 2, 1, true>, TwTable<Plan<128, 16, 8, 8, 2, 1, true>>, 256>(ctx, a, st);
       case 512: {
         using PL = Plan<256, 32, 8, 8, 4>;
         if (variant_env() == 9) { using CF = StagedCfg<PL, 256, 2, true, true>; NXS_TRY_STAGED(CF, 2); }  // scalar arithmetic

@@ -11,7 +11,8 @@ from tests.util import TOL, frame_rel_err, synth
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("nfft,variant", [(512, "0"), (512, "9")] + [(1024, v) for v in "012345678"] + [(1024, "14")] +
+@pytest.mark.parametrize("nfft,variant", [(64, "0"), (64, "16"), (128, "0"), (128, "9"), (128, "18"), (256, "0"), (256, "9"),
+                                          (256, "16"), (256, "17"), (256, "18"), (512, "0"), (512, "9")] + [(1024, v) for v in "012345678"] + [(1024, "14")] +
                          [(2048, v) for v in ["0", "1", "2", "3", "9"]] +
                          [(4096, v) for v in ["0", "1", "2", "3", "4", "6", "7", "8", "9", "10"]] +
                          [(8192, v) for v in ["0", "1", "15"]])
