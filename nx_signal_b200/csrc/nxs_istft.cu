@@ -1325,7 +1325,7 @@ static int launch_istft_main(nxs_ctx* ctx, const float2* z, int64_t channels, in
   a.seg_frames = a.segs_per_channel = a.total_segs = a.warm_batches = 0;
 
   const bool pow2 = (nfft & (nfft - 1)) == 0;
-  if (pow2 && nfft >= 256 && nfft <= 4096) {  // register overlap-add fast path (hop = N/2, N/4, N/8)
+  if (pow2 && nfft >= 128 && nfft <= 4096) {  // register overlap-add fast path (hop = N/2, N/4, N/8)
     bool done = false;
     const bool scalar = getenv("NXS_ISTFT_SCALAR") != nullptr;
     switch (nfft) {
@@ -1334,6 +1334,9 @@ static int launch_istft_main(nxs_ctx* ctx, const float2* z, int64_t channels, in
 #define NXS_ROLA(TH, MB, ...)                                                                          \
   rc = scalar ? try_istft_rola<Plan<__VA_ARGS__>, TH, MB>(ctx, a, channels, st, &done)                 \
               : try_istft_rola<Plan<__VA_ARGS__, 1, true>, TH, MB>(ctx, a, channels, st, &done)
+      case 128:  // half-warp groups (16 threads per frame); NXS_ISTFT_NO_ROLA128 keeps the gather kernel (A/B)
+        if (!getenv("NXS_ISTFT_NO_ROLA128")) NXS_ROLA(256, 2, 128, 16, 8, 8, 2);
+        break;
       case 256: NXS_ROLA(256, 2, 256, 32, 8, 8, 4); break;
       case 512: NXS_ROLA(256, 2, 512, 64, 8, 8, 8); break;
       case 1024: NXS_ROLA(256, 2, 1024, 64, 16, 8, 8); break;

@@ -36,7 +36,15 @@ struct GroupSync {
   int id;
   __device__ __forceinline__ void operator()() const {
     if constexpr (T > 32) asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(T) : "memory");
-    else __syncwarp();  // a group of one warp (or less) needs no barrier unit
+    else if constexpr (T == 32) __syncwarp();  // a group of one warp needs no barrier unit
+    else {
+      // several groups per warp: each synchronises over its OWN lanes only.  The groups of a warp walk segments of
+      // different lengths, so their barrier counts differ; a full-warp __syncwarp would pair one group's barrier
+      // with an unrelated one of its neighbour (harmless for the data, but not what the code means, and
+      // compute-sanitizer's racecheck rightly cannot follow it)
+      const unsigned lane = threadIdx.x & 31u;
+      __syncwarp(((1u << T) - 1u) << (lane / T * T));
+    }
   }
 };
 

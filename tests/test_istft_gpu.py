@@ -261,7 +261,7 @@ def test_rola_tuning_variants(monkeypatch, variant):
     assert rel(nx.istft(z, w, **kw), yo) <= TOL
 
 
-@pytest.mark.parametrize("nfft,hop", [(256, 64), (512, 256), (1024, 256), (1024, 128), (2048, 512), (4096, 1024),
+@pytest.mark.parametrize("nfft,hop", [(128, 64), (128, 32), (128, 16), (256, 64), (512, 256), (1024, 256), (1024, 128), (2048, 512), (4096, 1024),
                                       (1024, 250), (1024, 441), (512, 160), (2048, 700), (256, 100)])
 def test_rola_scalar_plans(monkeypatch, nfft, hop):
     """the register-overlap-add plans and the ring plans (any hop) run on packed fp32x2 arithmetic by default
@@ -274,6 +274,25 @@ def test_rola_scalar_plans(monkeypatch, nfft, hop):
     assert rel(nx.istft(z, w, **kw), yo) <= TOL
     monkeypatch.setenv("NXS_ISTFT_SCALAR", "1")
     assert rel(nx.istft(z, w, **kw), yo) <= TOL
+
+
+@pytest.mark.parametrize("hop", [64, 32, 16])
+def test_rola_half_warp_groups_many_uneven_segments(hop, monkeypatch):
+    """nfft 128: 16 threads per frame, two groups per warp walking segments of different lengths (channel ends,
+    warm-up frames) -- the groups' __syncwarp counts differ; the result must equal the gather kernel's"""
+    import torch
+
+    C, M, nfft = 5, 20_011, 128
+    z = torch.view_as_complex(torch.randn(C, M, nfft, 2, device="cuda", generator=torch.Generator(device="cuda").manual_seed(7 + hop)))
+    w = torch.from_numpy((o.hann(nfft) + np.float32(0.05)).astype(np.float32)).cuda()
+    kw = dict(overlap_length=nfft - hop, fft_length=nfft)
+    y = nx.istft(z, w, **kw)
+    monkeypatch.setenv("NXS_ISTFT_NO_ROLA128", "1")
+    y0 = nx.istft(z, w, **kw)
+    assert rel(y.cpu().numpy(), y0.cpu().numpy()) <= TOL
+    zs = z[:, :300].cpu().numpy()
+    monkeypatch.delenv("NXS_ISTFT_NO_ROLA128")
+    assert rel(nx.istft(zs, w.cpu().numpy(), **kw), o.istft_fast(zs, w.cpu().numpy(), **kw)) <= TOL
 
 
 # ---- ring overlap-add kernel (any hop <= N) -----------------------------------------------------
