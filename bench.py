@@ -310,10 +310,14 @@ def multi_gpu_legs(env, nx, w1024, comm, peak, steps):
     z3 = torch.empty((sh.count, M3, N3), dtype=torch.complex64, device=dev)
     env._lib.profile(True, env.local_rank)
     env._lib.profile_read(env.local_rank)
-    ms = env.time_steps(lambda: env.stft_dev(x3, w3, z3, N3, H3), max(3, min(steps, 10)), 3)
+    ncalls3 = max(3, min(steps, 10))
+    ms = env.time_steps(lambda: env.stft_dev(x3, w3, z3, N3, H3), ncalls3, 3)
     kms, kn = env._lib.profile_read(env.local_rank)
     env._lib.profile(False, env.local_rank)
-    kern_ms = env.max_over_ranks(kms / max(kn, 1))
+    # kernel time PER CALL: a call over more than ~16 GB is walked in channel blocks, i.e. several launches
+    # (csrc/nxs_stft.cu launch_stft); the profiler saw the 3 warm-up calls too
+    kern_ms = env.max_over_ranks(kms / (ncalls3 + 3))
+    launches_per_call3 = kn / (ncalls3 + 3)
     algo_rank = 4 * sh.count * L3 + 8 * sh.count * M3 * N3 + 4 * N3
     gbs = algo_rank / (kern_ms * 1e-3) / 1e9
 
@@ -338,8 +342,8 @@ def multi_gpu_legs(env, nx, w1024, comm, peak, steps):
         "workload": f"cfg3 (BASELINE configs[2]): {C3} ch x 60 s @48 kHz f32, hann({N3}), hop {H3}, :valid -> "
                     f"{C3 * M3} frames in total, channels sharded over {world} GPU(s) ({sh.count} ch per GPU)",
         "scaling": "strong", "frames_total": C3 * M3, "ms_per_step": ms, "frames_per_s": C3 * M3 / (ms * 1e-3),
-        "per_gpu": {"kernel_ms": kern_ms, "algorithmic_bytes": int(algo_rank), "achieved_gbs": gbs,
-                    "frac_of_hbm_peak": gbs / peak},
+        "per_gpu": {"kernel_ms": kern_ms, "kernel_launches_per_call": launches_per_call3, "algorithmic_bytes": int(algo_rank),
+                    "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peak},
         "window_broadcast": "nxs_bcast_coeffs_dev (one ncclBroadcast)" if comm is not None else "single rank: none",
         "checked": ("every other rank's last 64-channel block, sent to rank 0 over NCCL p2p, vs the same block computed "
                     "alone on rank 0" if world > 1 else "last 64-channel block of the 1024-channel call vs the block alone"),

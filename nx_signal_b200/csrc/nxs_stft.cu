@@ -889,6 +889,30 @@ int launch_stft(nxs_ctx* ctx, const float* x, int64_t channels, int64_t length, 
   if (num_frames <= 0 || channels <= 0) return NXS_OK;
   if (fft_length > (int64_t(1) << 24) || frame_length > (int64_t(1) << 24)) return NXS_EUNSUPPORTED;
   const int64_t nfft = fft_length;
+  // One nfft-4096 launch over tens of GB runs below the rate of shard-sized launches over the same tensors (the achieved
+  // bandwidth falls with the footprint of a launch: 1024 ch x 60 s, 106 GB: 22.3 ms as one launch against 19.6 ms as
+  // seven; 256 ch: 4.78 against 4.42 ms; profiles/r03i_footprint.txt): such inputs are walked in channel blocks of
+  // ~16 GB.  Measured for this kernel only -- cfg2's nfft-1024 kernel LOSES 5 % when split (66 GB: 10.8 -> 11.4 ms) --
+  // so the other sizes keep the single launch.
+  if (!mel && channels > 1 && nfft == 4096) {
+    const char* e = getenv("NXS_STFT_SPLIT_BYTES");
+    const double split_bytes = e && atof(e) > 0 ? atof(e) : 16e9;
+    const int64_t z_row = onesided ? z_ld : nfft;
+    const double per_ch = 4.0 * double(length) + 8.0 * double(num_frames) * double(z_row);
+    int64_t blk = (int64_t)(split_bytes / per_ch);
+    if (blk < 1) blk = 1;
+    if (channels > blk + blk / 2) {
+      const int64_t nblk = (channels + blk - 1) / blk;
+      blk = (channels + nblk - 1) / nblk;
+      for (int64_t c0 = 0; c0 < channels; c0 += blk) {
+        const int64_t n = channels - c0 < blk ? channels - c0 : blk;
+        const int rcb = launch_stft(ctx, x + c0 * x_ld, n, length, x_ld, window, frame_length, hop, fft_length, g, num_frames,
+                                    scaling, sampling_rate, z + c0 * num_frames * z_row, z_ld, onesided, st, nullptr);
+        if (rcb) return rcb;
+      }
+      return NXS_OK;
+    }
+  }
   int rc = ensure_coef(ctx, size_t(nfft) * sizeof(float));
   if (rc) return rc;
 

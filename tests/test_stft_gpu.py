@@ -217,3 +217,21 @@ def test_host_entry_pinned_buffers_and_repeat():
         zd, _, _ = nx.stft(xh.cuda(), torch.from_numpy(w).cuda(), overlap_length=nfft - hop, fft_length=nfft,
                            sampling_rate=48000)
         assert torch.equal(torch.view_as_real(zh), torch.view_as_real(zd).cpu())
+
+
+@pytest.mark.parametrize("nfft,onesided", [(4096, False), (4096, True)])
+def test_large_calls_walked_in_channel_blocks_give_the_same_bits(nfft, onesided, monkeypatch):
+    """launch_stft walks nfft-4096 inputs of tens of GB in channel blocks (csrc/nxs_stft.cu); NXS_STFT_SPLIT_BYTES lowers
+    the block size so that a small call takes that route: same bits as the single launch, uneven last block included"""
+    import torch
+
+    Cn, L = 7, 60 * nfft + 16
+    x = torch.from_numpy(synth((Cn, L), 900 + nfft)).cuda()
+    w = torch.from_numpy(o.hann(nfft)).cuda()
+    kw = dict(overlap_length=nfft - nfft // 4, fft_length=nfft, sampling_rate=48000)
+    if onesided:
+        kw["onesided"] = True
+    z0 = nx.stft(x, w, **kw)[0]
+    monkeypatch.setenv("NXS_STFT_SPLIT_BYTES", str(2.5 * (4 * L + 8 * ((L - nfft) // (nfft // 4) + 1) * nfft)))  # blocks of 2-3 channels
+    z1 = nx.stft(x, w, **kw)[0]
+    assert torch.equal(torch.view_as_real(z0), torch.view_as_real(z1))

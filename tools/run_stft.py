@@ -26,4 +26,6 @@ _lib.profile(True); _lib.profile_read()
 for _ in range(iters): step()
 ms, n = _lib.profile_read()
 algo = 4 * C * L + 8 * C * M * nfft
-print(f"C={C} L={L} nfft={nfft} hop={hop} frames={C*M}: kernel {ms/n:.4f} ms  {algo/(ms/n*1e-3)/1e9:.1f} GB/s algorithmic  {C*M/(ms/n*1e-3)/1e6:.1f} Mframes/s")
+per = ms / iters  # kernel time per CALL: a call over more than ~16 GB is several launches (launch_stft walks channel blocks)
+print(f"C={C} L={L} nfft={nfft} hop={hop} frames={C*M}: kernel {per:.4f} ms  {algo/(per*1e-3)/1e9:.1f} GB/s algorithmic  {C*M/(per*1e-3)/1e6:.1f} Mframes/s"
+      + (f"  ({n // iters} launches per call)" if n != iters else ""))
